@@ -1,0 +1,105 @@
+// gm_intersect_batch: the set operators applied to a batch of independent list pairs.
+// One warp per pair, pairs handed out by a grid-stride loop.  This is (1) the unit-test entry for
+// every operator variant of gm/set_ops.cuh against the CPU oracle and (2) the streaming HBM
+// microbenchmark of SURVEY.md §8(d): pairs laid out contiguously, each list read once.
+#include "gm_internal.cuh"
+#include "batch_kernels.cuh"
+
+using namespace gm;
+
+namespace gm {
+
+struct BatchArgs {
+  const vidType *pool;
+  const int64_t *a_off; const int32_t *a_len;
+  const int64_t *b_off; const int32_t *b_len;
+  const vidType *bound, *anc, *anc2;
+  int64_t npairs;
+  unsigned long long *out;
+  vidType *out_pool; const int64_t *out_off;
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) batch_bsearch_kernel(BatchArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp; i < p.npairs; i += nwarps) {
+    const vidType *a = p.pool + p.a_off[i]; vidType na = p.a_len[i];
+    const vidType *b = p.pool + p.b_off[i]; vidType nb = p.b_len[i];
+    vidType bound = p.bound ? p.bound[i] : kVidMax;
+    vidType anc = p.anc ? p.anc[i] : -1, anc2 = p.anc2 ? p.anc2[i] : -1;
+    vidType *c = p.out_pool ? p.out_pool + p.out_off[i] : nullptr;
+    unsigned long long r = 0; bool partial = true;
+    switch (OP) {
+      case GM_OP_INTERSECT_NUM: r = intersect_num(a, na, b, nb); break;
+      case GM_OP_INTERSECT_NUM_BOUND: r = intersect_num(a, na, b, nb, bound); break;
+      case GM_OP_INTERSECT_NUM_BOUND_EXCEPT: r = intersect_num(a, na, b, nb, bound, anc); break;
+      case GM_OP_INTERSECT_NUM_EXCEPT2: r = intersect_num_except(a, na, b, nb, anc, anc2); break;
+      case GM_OP_DIFFERENCE_NUM: r = difference_num_except(a, na, b, nb, kVidMax, anc); break;
+      case GM_OP_DIFFERENCE_NUM_BOUND: r = difference_num_except(a, na, b, nb, bound, anc); break;
+      case GM_OP_INTERSECT_SET: r = intersect(a, na, b, nb, c); partial = false; break;
+      case GM_OP_INTERSECT_SET_BOUND: r = intersect(a, na, b, nb, bound, c); partial = false; break;
+      case GM_OP_DIFFERENCE_SET: r = difference_set_except(a, na, b, nb, kVidMax, anc, c); partial = false; break;
+      case GM_OP_DIFFERENCE_SET_BOUND: r = difference_set_except(a, na, b, nb, bound, anc, c); partial = false; break;
+      case GM_OP_COUNT_SMALLER: r = count_smaller(bound, a, na); partial = false; break;
+    }
+    if (partial) r = warp_reduce(r);
+    if (lane == 0) p.out[i] = r;
+  }
+}
+
+template <int OP>
+static void launch_bsearch(const BatchArgs &a, int grid, cudaStream_t s) { batch_bsearch_kernel<OP><<<grid, 256, 0, s>>>(a); }
+
+}  // namespace gm
+
+extern "C" int gm_intersect_batch(const int32_t *d_pool, const int64_t *d_a_off, const int32_t *d_a_len,
+                                  const int64_t *d_b_off, const int32_t *d_b_len,
+                                  const int32_t *d_bound, const int32_t *d_anc, const int32_t *d_anc2,
+                                  int64_t npairs, int op, int algo, uint64_t *d_out,
+                                  int32_t *d_out_pool, const int64_t *d_out_off,
+                                  int device, void *cuda_stream) {
+  if (npairs < 0 || !d_out || (npairs > 0 && (!d_pool || !d_a_off || !d_a_len))) { set_error("gm_intersect_batch: bad arguments"); return GM_EINVAL; }
+  if (op < GM_OP_INTERSECT_NUM || op > GM_OP_COUNT_SMALLER) { set_error("gm_intersect_batch: unknown op %d", op); return GM_EINVAL; }
+  if (op != GM_OP_COUNT_SMALLER && npairs > 0 && (!d_b_off || !d_b_len)) { set_error("gm_intersect_batch: op %d needs the b lists", op); return GM_EINVAL; }
+  bool is_set = op >= GM_OP_INTERSECT_SET && op <= GM_OP_DIFFERENCE_SET_BOUND;
+  if (is_set && (!d_out_pool || !d_out_off)) { set_error("gm_intersect_batch: materialising op needs d_out_pool/d_out_off"); return GM_EINVAL; }
+  bool needs_bound = op == GM_OP_INTERSECT_NUM_BOUND || op == GM_OP_INTERSECT_NUM_BOUND_EXCEPT || op == GM_OP_DIFFERENCE_NUM_BOUND ||
+                     op == GM_OP_INTERSECT_SET_BOUND || op == GM_OP_DIFFERENCE_SET_BOUND || op == GM_OP_COUNT_SMALLER;
+  if (needs_bound && !d_bound) { set_error("gm_intersect_batch: op %d needs d_bound", op); return GM_EINVAL; }
+  int ndev = 0; gm_device_count(&ndev);
+  if (device < 0 || device >= ndev) { set_error("gm_intersect_batch: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
+  if (npairs == 0) return GM_OK;
+  GM_CUDA(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  BatchArgs a{d_pool, d_a_off, d_a_len, d_b_off ? d_b_off : d_a_off, d_b_len ? d_b_len : d_a_len,
+              d_bound, d_anc, d_anc2, npairs,
+              reinterpret_cast<unsigned long long *>(d_out), d_out_pool, d_out_off};
+  cudaDeviceProp prop;
+  GM_CUDA(cudaGetDeviceProperties(&prop, device));
+  int sms = prop.multiProcessorCount;
+
+  if (algo == GM_ALGO_MERGE || algo == GM_ALGO_HASH || algo == GM_ALGO_GALLOP) {
+    if (op != GM_OP_INTERSECT_NUM) { set_error("gm_intersect_batch: algo %d implements GM_OP_INTERSECT_NUM only", algo); return GM_EUNSUPPORTED; }
+    return launch_batch_variant(algo, d_pool, d_a_off, d_a_len, d_b_off, d_b_len, npairs,
+                                reinterpret_cast<unsigned long long *>(d_out), sms, s);
+  }
+  if (algo != GM_ALGO_AUTO && algo != GM_ALGO_BSEARCH) { set_error("gm_intersect_batch: unknown algo %d", algo); return GM_EINVAL; }
+  int grid = int(std::min<int64_t>((npairs + 7) / 8, int64_t(sms) * 32));
+  switch (op) {
+    case GM_OP_INTERSECT_NUM: launch_bsearch<GM_OP_INTERSECT_NUM>(a, grid, s); break;
+    case GM_OP_INTERSECT_NUM_BOUND: launch_bsearch<GM_OP_INTERSECT_NUM_BOUND>(a, grid, s); break;
+    case GM_OP_INTERSECT_NUM_BOUND_EXCEPT: launch_bsearch<GM_OP_INTERSECT_NUM_BOUND_EXCEPT>(a, grid, s); break;
+    case GM_OP_INTERSECT_NUM_EXCEPT2: launch_bsearch<GM_OP_INTERSECT_NUM_EXCEPT2>(a, grid, s); break;
+    case GM_OP_DIFFERENCE_NUM: launch_bsearch<GM_OP_DIFFERENCE_NUM>(a, grid, s); break;
+    case GM_OP_DIFFERENCE_NUM_BOUND: launch_bsearch<GM_OP_DIFFERENCE_NUM_BOUND>(a, grid, s); break;
+    case GM_OP_INTERSECT_SET: launch_bsearch<GM_OP_INTERSECT_SET>(a, grid, s); break;
+    case GM_OP_INTERSECT_SET_BOUND: launch_bsearch<GM_OP_INTERSECT_SET_BOUND>(a, grid, s); break;
+    case GM_OP_DIFFERENCE_SET: launch_bsearch<GM_OP_DIFFERENCE_SET>(a, grid, s); break;
+    case GM_OP_DIFFERENCE_SET_BOUND: launch_bsearch<GM_OP_DIFFERENCE_SET_BOUND>(a, grid, s); break;
+    case GM_OP_COUNT_SMALLER: launch_bsearch<GM_OP_COUNT_SMALLER>(a, grid, s); break;
+  }
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}

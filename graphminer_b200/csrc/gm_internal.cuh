@@ -1,0 +1,120 @@
+// Internal definitions shared by the translation units of libgminer_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gminer_b200.h"
+#include "../../include/gm/graph_gpu.cuh"
+
+namespace gm {
+
+void set_error(const char *fmt, ...);
+
+#define GM_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      gm::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+      return GM_ECUDA;                                                                         \
+    }                                                                                          \
+  } while (0)
+
+#define GM_TRY(call)                 \
+  do {                               \
+    int r__ = (call);                \
+    if (r__ != GM_OK) return r__;    \
+  } while (0)
+
+constexpr int kNumSMsB200 = 148;
+
+// One unit of vertex-centric work: root vertex + a slice of its partner list.
+struct WorkItem {
+  vidType root;
+  vidType pbegin;   // first partner (index into the root's partner row)
+  vidType pcount;   // number of partners in this item
+};
+
+struct ItemList {
+  WorkItem *d_items = nullptr;
+  int64_t n = 0;
+};
+
+struct Options {
+  std::string tc_algo = "auto";
+  std::string clique_algo = "auto";
+  int chunk = 0;   // 0 = default per kernel
+};
+Options &options();
+
+}  // namespace gm
+
+// The opaque handle of the C ABI.
+struct gm_graph {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool own_csr = false;
+  gm::vidType nv = 0;
+  gm::eidType ne = 0;
+  gm::vidType max_degree = 0;
+  gm::vidType src_begin = 0, src_end = 0;
+
+  gm::eidType *d_rowptr = nullptr;
+  gm::vidType *d_colidx = nullptr;
+
+  // aligned view (built by prepare)
+  uint2 *d_vinfo = nullptr;
+  gm::vidType *d_acol = nullptr;
+  int64_t acol_len = 0;
+
+  // COO task lists: [0] plain (dst aliases colidx), [1] symmetry-broken (src > dst)
+  gm::vidType *d_src[2] = {nullptr, nullptr};
+  gm::vidType *d_dst[2] = {nullptr, nullptr};
+  gm::eidType nnz[2] = {0, 0};
+  bool coo_ready[2] = {false, false};
+
+  // reverse (in-neighbour) adjacency of a DAG, for the partner-side choice of the hash kernels
+  gm::eidType *d_rrowptr = nullptr;
+  gm::vidType *d_rcolidx = nullptr;
+
+  // vertex-centric work items, by class (0: warp-sized tables, 1: CTA small, 2: CTA large, 3: fallback)
+  gm::ItemList items[2][4];
+  bool items_ready[2] = {false, false};   // [0] forward partners, [1] reverse partners
+
+  // scratch + results
+  unsigned long long *d_counts = nullptr;     // 8 accumulators
+  unsigned long long *h_counts = nullptr;     // pinned
+  int *d_ticket = nullptr;                    // dynamic work counters (8)
+  void *d_scratch = nullptr; size_t scratch_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  uint64_t last_alg_bytes = 0;
+  uint64_t tc_bytes_cache = 0;
+  int num_sms = gm::kNumSMsB200;
+  int smem_optin = 0;
+
+  gm::GraphGPU view(int coo = 0) const {
+    gm::GraphGPU g;
+    g.num_vertices = nv; g.num_edges = ne;
+    g.d_rowptr = d_rowptr; g.d_colidx = d_colidx;
+    g.d_src_list = d_src[coo]; g.d_dst_list = d_dst[coo]; g.num_tasks = nnz[coo];
+    g.d_vinfo = d_vinfo; g.d_acol = d_acol;
+    return g;
+  }
+};
+
+namespace gm {
+int ensure_aligned(gm_graph *g);
+int ensure_coo(gm_graph *g, int sym_break);
+int ensure_reverse(gm_graph *g);
+int ensure_items(gm_graph *g, int reverse);
+int ensure_scratch(gm_graph *g, size_t bytes);
+int begin_timed(gm_graph *g);
+int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out);
+}  // namespace gm

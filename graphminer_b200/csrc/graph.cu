@@ -1,0 +1,467 @@
+// Device graph handle: upload / adopt / free, and the one-time auxiliary structures the kernels
+// read (aligned CSR, COO task lists, reverse adjacency, vertex-centric work items).
+//
+// Replaces GraphGPU::init / init_edgelist / clean of the reference (include/graph_gpu.h:56-210).
+// Everything after the initial H2D copy is built ON THE DEVICE: the reference
+// builds the COO list in a single host thread (src/common/graph.cc:308-321).
+#include "gm_internal.cuh"
+
+#include <cub/cub.cuh>
+#include <mutex>
+
+namespace gm {
+
+static thread_local std::string g_err;
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+}
+Options &options() { static Options o; return o; }
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__global__ void k_degree(vidType nv, const eidType *rowptr, uint32_t *units, vidType *maxdeg) {
+  vidType v = blockIdx.x * blockDim.x + threadIdx.x;
+  vidType d = 0;
+  if (v < nv) {
+    d = vidType(rowptr[v + 1] - rowptr[v]);
+    units[v] = (uint32_t(d) + 3u) >> 2;
+  }
+  if (maxdeg) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(kFullMask, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(maxdeg, d);
+  }
+}
+
+__global__ void k_make_vinfo(vidType nv, const eidType *rowptr, const uint32_t *off_units, uint2 *vinfo) {
+  vidType v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nv) vinfo[v] = make_uint2(off_units[v], uint32_t(rowptr[v + 1] - rowptr[v]));
+}
+
+// 8 lanes per vertex copy the row into its aligned slot and pad the tail with kVidMax.
+__global__ void k_fill_aligned(vidType nv, const eidType *rowptr, const vidType *colidx,
+                               const uint2 *vinfo, vidType *acol) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  vidType v = vidType(t >> 3);
+  int sub = int(t & 7);
+  if (v >= nv) return;
+  uint2 vi = vinfo[v];
+  const vidType *src = colidx + rowptr[v];
+  vidType *dst = acol + (size_t(vi.x) << 2);
+  int deg = int(vi.y), padded = (deg + 3) & ~3;
+  for (int i = sub; i < padded; i += 8) dst[i] = i < deg ? src[i] : kVidMax;
+}
+
+// COO sources for rows [vb, ve): src[e - base] = v for e in row v (plain list).
+__global__ void k_fill_src_plain(vidType vb, vidType ve, const eidType *rowptr, eidType base, vidType *src) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  vidType v = vb + vidType(t >> 3);
+  int sub = int(t & 7);
+  if (v >= ve) return;
+  eidType b = rowptr[v], e = rowptr[v + 1];
+  for (eidType i = b + sub; i < e; i += 8) src[i - base] = v;
+}
+
+// symmetry-broken COO (init_edgelist(sym_break=1), graph.cc:297-326): keep (v,u) with u < v.
+__global__ void k_count_lower(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx, eidType *cnt) {
+  vidType v = vb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= ve) return;
+  const vidType *row = colidx + rowptr[v];
+  cnt[v - vb] = lower_bound(row, vidType(rowptr[v + 1] - rowptr[v]), v);
+}
+__global__ void k_fill_lower(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx,
+                             const eidType *off, vidType *src, vidType *dst) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  vidType v = vb + vidType(t >> 3);
+  int sub = int(t & 7);
+  if (v >= ve) return;
+  const vidType *row = colidx + rowptr[v];
+  eidType o = off[v - vb], n = off[v - vb + 1] - o;
+  for (eidType i = sub; i < n; i += 8) { src[o + i] = v; dst[o + i] = row[i]; }
+}
+
+// reverse adjacency restricted to sources in [vb, ve)
+__global__ void k_count_in(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx, unsigned long long *indeg) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  vidType v = vb + vidType(t >> 3);
+  int sub = int(t & 7);
+  if (v >= ve) return;
+  for (eidType i = rowptr[v] + sub; i < rowptr[v + 1]; i += 8) atomicAdd(&indeg[colidx[i]], 1ull);
+}
+__global__ void k_fill_in(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx,
+                          const eidType *rrowptr, unsigned long long *cursor, vidType *rcol) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  vidType v = vb + vidType(t >> 3);
+  int sub = int(t & 7);
+  if (v >= ve) return;
+  for (eidType i = rowptr[v] + sub; i < rowptr[v + 1]; i += 8) {
+    vidType u = colidx[i];
+    unsigned long long p = atomicAdd(&cursor[u], 1ull);
+    rcol[rrowptr[u] + eidType(p)] = v;
+  }
+}
+
+// work items ---------------------------------------------------------------------------------
+__device__ __forceinline__ int item_class(vidType d) {
+  return d <= 32 ? 0 : d <= 512 ? 1 : d <= 2048 ? 2 : d <= 8192 ? 3 : 4;
+}
+// per root: number of items of class `cls` (0 when the root belongs to another class)
+__global__ void k_count_items(vidType vb, vidType ve, vidType min_deg, const eidType *rowptr,
+                              const eidType *prowptr, int cls, int merge_from, int chunk, int64_t *cnt) {
+  vidType r = vb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ve) return;
+  vidType d = vidType(rowptr[r + 1] - rowptr[r]);
+  eidType np = prowptr[r + 1] - prowptr[r];
+  int c = item_class(d);
+  if (c > 4) c = 4;
+  bool mine = (c == cls) || (merge_from >= 0 && c >= merge_from && cls == merge_from);
+  cnt[r - vb] = (mine && d >= min_deg && np > 0) ? (np + chunk - 1) / chunk : 0;
+}
+__global__ void k_fill_items(vidType vb, vidType ve, const eidType *prowptr, int chunk,
+                             const int64_t *off, WorkItem *items) {
+  vidType r = vb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ve) return;
+  int64_t o = off[r - vb], n = off[r - vb + 1] - o;
+  eidType np = prowptr[r + 1] - prowptr[r];
+  for (int64_t i = 0; i < n; i++) {
+    WorkItem it; it.root = r; it.pbegin = vidType(i * chunk);
+    eidType left = np - i * chunk;
+    it.pcount = vidType(left < chunk ? left : eidType(chunk));
+    items[o + i] = it;
+  }
+}
+
+template <typename T>
+static int exclusive_scan_inplace(gm_graph *g, T *d_data, int64_t n) {   // d_data has n+1 slots
+  size_t tmp = 0;
+  GM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_data, d_data, n + 1, g->stream));
+  GM_TRY(ensure_scratch(g, tmp));
+  GM_CUDA(cub::DeviceScan::ExclusiveSum(g->d_scratch, tmp, d_data, d_data, n + 1, g->stream));
+  return GM_OK;
+}
+
+int ensure_scratch(gm_graph *g, size_t bytes) {
+  if (bytes <= g->scratch_bytes) return GM_OK;
+  if (g->d_scratch) { GM_CUDA(cudaStreamSynchronize(g->stream)); GM_CUDA(cudaFree(g->d_scratch)); g->d_scratch = nullptr; }
+  size_t want = bytes + (bytes >> 2) + 256;
+  if (cudaMalloc(&g->d_scratch, want) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu B scratch)", want); return GM_ENOMEM; }
+  g->scratch_bytes = want;
+  return GM_OK;
+}
+
+static inline unsigned nblk(int64_t n, int per = 256) { return unsigned((n + per - 1) / per); }
+
+int ensure_aligned(gm_graph *g) {
+  if (g->d_vinfo) return GM_OK;
+  GM_CUDA(cudaSetDevice(g->device));
+  vidType nv = g->nv;
+  uint32_t *units = nullptr;
+  GM_CUDA(cudaMalloc(&units, sizeof(uint32_t) * (size_t(nv) + 1)));
+  GM_CUDA(cudaMemsetAsync(units, 0, sizeof(uint32_t) * (size_t(nv) + 1), g->stream));
+  if (nv > 0) k_degree<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, units, nullptr);
+  int r = exclusive_scan_inplace(g, units, nv);
+  if (r != GM_OK) { cudaFree(units); return r; }
+  uint32_t total_units = 0;
+  GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  if ((uint64_t(g->ne) + 3ull * uint64_t(nv)) / 4 >= (1ull << 32)) { cudaFree(units); set_error("graph too large for 32-bit aligned offsets"); return GM_EUNSUPPORTED; }
+  g->acol_len = int64_t(total_units) * 4;
+  GM_CUDA(cudaMalloc(&g->d_vinfo, sizeof(uint2) * size_t(nv > 0 ? nv : 1)));
+  GM_CUDA(cudaMalloc(&g->d_acol, sizeof(vidType) * size_t(g->acol_len > 0 ? g->acol_len : 4)));
+  if (nv > 0) {
+    k_make_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, units, g->d_vinfo);
+    k_fill_aligned<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, g->d_vinfo, g->d_acol);
+  }
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(cudaFree(units));
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int ensure_coo(gm_graph *g, int sb) {
+  if (g->coo_ready[sb]) return GM_OK;
+  GM_CUDA(cudaSetDevice(g->device));
+  vidType vb = g->src_begin, ve = g->src_end, n = ve - vb;
+  if (!sb) {
+    eidType base = 0, last = 0;
+    if (n > 0) {
+      GM_CUDA(cudaMemcpyAsync(&base, g->d_rowptr + vb, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
+      GM_CUDA(cudaMemcpyAsync(&last, g->d_rowptr + ve, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
+      GM_CUDA(cudaStreamSynchronize(g->stream));
+    }
+    g->nnz[0] = last - base;
+    GM_CUDA(cudaMalloc(&g->d_src[0], sizeof(vidType) * size_t(g->nnz[0] > 0 ? g->nnz[0] : 1)));
+    g->d_dst[0] = g->d_colidx + base;                       // dst aliases colidx (graph_gpu.h:166)
+    if (n > 0) k_fill_src_plain<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, base, g->d_src[0]);
+  } else {
+    eidType *off = nullptr;
+    GM_CUDA(cudaMalloc(&off, sizeof(eidType) * (size_t(n) + 1)));
+    GM_CUDA(cudaMemsetAsync(off, 0, sizeof(eidType) * (size_t(n) + 1), g->stream));
+    if (n > 0) k_count_lower<<<nblk(n), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, off);
+    int r = exclusive_scan_inplace(g, off, n);
+    if (r != GM_OK) { cudaFree(off); return r; }
+    GM_CUDA(cudaMemcpyAsync(&g->nnz[1], off + n, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    GM_CUDA(cudaMalloc(&g->d_src[1], sizeof(vidType) * size_t(g->nnz[1] > 0 ? g->nnz[1] : 1)));
+    GM_CUDA(cudaMalloc(&g->d_dst[1], sizeof(vidType) * size_t(g->nnz[1] > 0 ? g->nnz[1] : 1)));
+    if (n > 0) k_fill_lower<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, off, g->d_src[1], g->d_dst[1]);
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    GM_CUDA(cudaFree(off));
+  }
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(cudaGetLastError());
+  g->coo_ready[sb] = true;
+  return GM_OK;
+}
+
+int ensure_reverse(gm_graph *g) {
+  if (g->d_rrowptr) return GM_OK;
+  GM_CUDA(cudaSetDevice(g->device));
+  vidType nv = g->nv, vb = g->src_begin, ve = g->src_end, n = ve - vb;
+  unsigned long long *cursor = nullptr;
+  GM_CUDA(cudaMalloc(&g->d_rrowptr, sizeof(eidType) * (size_t(nv) + 1)));
+  GM_CUDA(cudaMalloc(&cursor, sizeof(unsigned long long) * (size_t(nv) + 1)));
+  GM_CUDA(cudaMemsetAsync(g->d_rrowptr, 0, sizeof(eidType) * (size_t(nv) + 1), g->stream));
+  GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
+  if (n > 0) k_count_in<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, reinterpret_cast<unsigned long long *>(g->d_rrowptr));
+  int r = exclusive_scan_inplace(g, g->d_rrowptr, nv);
+  if (r != GM_OK) { cudaFree(cursor); return r; }
+  eidType rne = 0;
+  GM_CUDA(cudaMemcpyAsync(&rne, g->d_rrowptr + nv, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(cudaMalloc(&g->d_rcolidx, sizeof(vidType) * size_t(rne > 0 ? rne : 1)));
+  if (n > 0) k_fill_in<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, g->d_rrowptr, cursor, g->d_rcolidx);
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(cudaFree(cursor));
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+// Vertex-centric work items.  reverse=0: root r probes with its own row as the table and its
+// out-neighbours as partners (roots limited to the source range).  reverse=1: partners are the
+// in-neighbours (already limited to the source range by ensure_reverse), roots are all vertices.
+int ensure_items(gm_graph *g, int reverse) {
+  if (g->items_ready[reverse]) return GM_OK;
+  GM_CUDA(cudaSetDevice(g->device));
+  if (reverse) GM_TRY(ensure_reverse(g));
+  const eidType *prow = reverse ? g->d_rrowptr : g->d_rowptr;
+  vidType vb = reverse ? 0 : g->src_begin, ve = reverse ? g->nv : g->src_end, n = ve - vb;
+  vidType min_deg = reverse ? 1 : 2;
+  int chunk_opt = options().chunk;
+  int64_t *off = nullptr;
+  GM_CUDA(cudaMalloc(&off, sizeof(int64_t) * (size_t(n) + 1)));
+  for (int cls = 0; cls < 4; cls++) {
+    // class 3 also absorbs the overflow class 4 (tables that do not fit shared memory: the kernel
+    // falls back to searching the root row in global memory)
+    int chunk = chunk_opt > 0 ? chunk_opt : (cls == 0 ? 64 : cls == 1 ? 128 : 256);
+    GM_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t) * (size_t(n) + 1), g->stream));
+    if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, g->d_rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off);
+    int r = exclusive_scan_inplace(g, off, n);
+    if (r != GM_OK) { cudaFree(off); return r; }
+    int64_t total = 0;
+    GM_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, g->stream));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    ItemList &il = g->items[reverse][cls];
+    il.n = total;
+    GM_CUDA(cudaMalloc(&il.d_items, sizeof(WorkItem) * size_t(total > 0 ? total : 1)));
+    if (n > 0 && total > 0) k_fill_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, prow, chunk, off, il.d_items);
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+  }
+  GM_CUDA(cudaFree(off));
+  GM_CUDA(cudaGetLastError());
+  g->items_ready[reverse] = true;
+  return GM_OK;
+}
+
+int begin_timed(gm_graph *g) {
+  GM_CUDA(cudaSetDevice(g->device));
+  GM_CUDA(cudaMemsetAsync(g->d_counts, 0, 8 * sizeof(unsigned long long), g->stream));
+  GM_CUDA(cudaMemsetAsync(g->d_ticket, 0, 8 * sizeof(int), g->stream));
+  GM_CUDA(cudaEventRecord(g->ev0, g->stream));
+  return GM_OK;
+}
+
+int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out) {
+  GM_CUDA(cudaEventRecord(g->ev1, g->stream));
+  GM_CUDA(cudaGetLastError());
+  GM_CUDA(cudaMemcpyAsync(g->h_counts, g->d_counts, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1));
+  g->last_launches = launches;
+  for (int i = 0; i < ncounts; i++) out[i] = g->h_counts[i];
+  return GM_OK;
+}
+
+static void free_aux(gm_graph *g) {
+  cudaFree(g->d_vinfo); cudaFree(g->d_acol); g->d_vinfo = nullptr; g->d_acol = nullptr;
+  for (int s = 0; s < 2; s++) {
+    cudaFree(g->d_src[s]); g->d_src[s] = nullptr;
+    if (s == 1) cudaFree(g->d_dst[s]);
+    g->d_dst[s] = nullptr; g->coo_ready[s] = false; g->nnz[s] = 0;
+    for (int c = 0; c < 4; c++) { cudaFree(g->items[s][c].d_items); g->items[s][c] = ItemList(); }
+    g->items_ready[s] = false;
+  }
+  cudaFree(g->d_rrowptr); cudaFree(g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
+}
+
+static int init_common(gm_graph *g) {
+  GM_CUDA(cudaSetDevice(g->device));
+  GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  g->own_stream = true;
+  GM_CUDA(cudaMalloc(&g->d_counts, 8 * sizeof(unsigned long long)));
+  GM_CUDA(cudaMalloc(&g->d_ticket, 8 * sizeof(int)));
+  GM_CUDA(cudaMallocHost(&g->h_counts, 8 * sizeof(unsigned long long)));
+  GM_CUDA(cudaEventCreate(&g->ev0));
+  GM_CUDA(cudaEventCreate(&g->ev1));
+  cudaDeviceProp p;
+  GM_CUDA(cudaGetDeviceProperties(&p, g->device));
+  g->num_sms = p.multiProcessorCount;
+  g->smem_optin = int(p.sharedMemPerBlockOptin);
+  g->src_begin = 0; g->src_end = g->nv;
+  if (g->max_degree <= 0 && g->nv > 0) {
+    vidType *d_md = nullptr; uint32_t *units = nullptr;
+    GM_CUDA(cudaMalloc(&d_md, sizeof(vidType)));
+    GM_CUDA(cudaMalloc(&units, sizeof(uint32_t) * size_t(g->nv)));
+    GM_CUDA(cudaMemsetAsync(d_md, 0, sizeof(vidType), g->stream));
+    k_degree<<<nblk(g->nv), 256, 0, g->stream>>>(g->nv, g->d_rowptr, units, d_md);
+    GM_CUDA(cudaMemcpyAsync(&g->max_degree, d_md, sizeof(vidType), cudaMemcpyDeviceToHost, g->stream));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    cudaFree(d_md); cudaFree(units);
+  }
+  return GM_OK;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" {
+
+const char *gm_last_error(void) { return g_err.c_str(); }
+int gm_version(void) { return 100; }
+
+int gm_device_count(int *count) {
+  if (!count) { set_error("count is NULL"); return GM_EINVAL; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *count = n;
+  return GM_OK;
+}
+
+int gm_set_option(const char *key, const char *value) {
+  if (!key || !value) { set_error("null option"); return GM_EINVAL; }
+  std::string k(key), v(value);
+  if (k == "tc.algo") {
+    if (v != "auto" && v != "hash" && v != "hash_rev" && v != "bs" && v != "merge") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
+    options().tc_algo = v;
+  } else if (k == "clique.algo") {
+    if (v != "auto" && v != "bitmap" && v != "list") { set_error("clique.algo: unknown value '%s'", value); return GM_EINVAL; }
+    options().clique_algo = v;
+  } else if (k == "sched.chunk") {
+    options().chunk = atoi(value);
+  } else { set_error("unknown option '%s'", key); return GM_EINVAL; }
+  return GM_OK;
+}
+
+int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
+                    int32_t max_degree, int device, gm_graph_t **out) {
+  if (!out || nv < 0 || ne < 0 || (!rowptr && nv >= 0) || (!colidx && ne > 0)) { set_error("gm_graph_upload: bad arguments"); return GM_EINVAL; }
+  if (rowptr[nv] != ne) { set_error("gm_graph_upload: rowptr[nv]=%lld != ne=%lld", (long long)rowptr[nv], (long long)ne); return GM_EINVAL; }
+  int ndev = 0; gm_device_count(&ndev);
+  if (device < 0 || device >= ndev) { set_error("gm_graph_upload: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
+  gm_graph *g = new gm_graph();
+  g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
+  int r = [&]() -> int {
+    GM_CUDA(cudaSetDevice(device));
+    GM_CUDA(cudaMalloc(&g->d_rowptr, sizeof(eidType) * (size_t(nv) + 1)));
+    GM_CUDA(cudaMalloc(&g->d_colidx, sizeof(vidType) * size_t(ne > 0 ? ne : 1)));
+    GM_CUDA(cudaMemcpy(g->d_rowptr, rowptr, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyHostToDevice));
+    if (ne > 0) GM_CUDA(cudaMemcpy(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice));
+    return init_common(g);
+  }();
+  if (r != GM_OK) { gm_graph_free(g); return r; }
+  *out = g;
+  return GM_OK;
+}
+
+int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv, int64_t ne,
+                   int32_t max_degree, int device, gm_graph_t **out) {
+  if (!out || nv < 0 || ne < 0 || !d_rowptr) { set_error("gm_graph_adopt: bad arguments"); return GM_EINVAL; }
+  int ndev = 0; gm_device_count(&ndev);
+  if (device < 0 || device >= ndev) { set_error("gm_graph_adopt: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
+  gm_graph *g = new gm_graph();
+  g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = false;
+  g->d_rowptr = const_cast<eidType *>(d_rowptr);
+  g->d_colidx = const_cast<vidType *>(d_colidx);
+  int r = init_common(g);
+  if (r != GM_OK) { gm_graph_free(g); return r; }
+  *out = g;
+  return GM_OK;
+}
+
+int gm_graph_free(gm_graph_t *g) {
+  if (!g) return GM_OK;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  free_aux(g);
+  if (g->own_csr) { cudaFree(g->d_rowptr); cudaFree(g->d_colidx); }
+  cudaFree(g->d_counts); cudaFree(g->d_ticket); cudaFree(g->d_scratch);
+  if (g->h_counts) cudaFreeHost(g->h_counts);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  cudaGetLastError();
+  delete g;
+  return GM_OK;
+}
+
+int gm_graph_set_stream(gm_graph_t *g, void *cuda_stream) {
+  if (!g) { set_error("null graph"); return GM_EINVAL; }
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  if (cuda_stream) { g->stream = static_cast<cudaStream_t>(cuda_stream); g->own_stream = false; }
+  else { GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)); g->own_stream = true; }
+  return GM_OK;
+}
+
+int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end) {
+  if (!g || begin < 0 || end > g->nv || begin > end) { set_error("gm_graph_set_source_range: bad range"); return GM_EINVAL; }
+  if (begin == g->src_begin && end == g->src_end) return GM_OK;
+  cudaSetDevice(g->device);
+  cudaStreamSynchronize(g->stream);
+  // range-dependent structures are rebuilt lazily
+  uint2 *vi = g->d_vinfo; vidType *ac = g->d_acol; g->d_vinfo = nullptr; g->d_acol = nullptr;
+  free_aux(g);
+  g->d_vinfo = vi; g->d_acol = ac;
+  g->src_begin = begin; g->src_end = end; g->tc_bytes_cache = 0;
+  return GM_OK;
+}
+
+int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, int *device) {
+  if (!g) { set_error("null graph"); return GM_EINVAL; }
+  if (nv) *nv = g->nv;
+  if (ne) *ne = g->ne;
+  if (max_degree) *max_degree = g->max_degree;
+  if (device) *device = g->device;
+  return GM_OK;
+}
+
+int gm_last_stats(gm_graph_t *g, float *kernel_ms, int *launches) {
+  if (!g) { set_error("null graph"); return GM_EINVAL; }
+  if (kernel_ms) *kernel_ms = g->last_ms;
+  if (launches) *launches = g->last_launches;
+  return GM_OK;
+}
+
+int gm_last_alg_bytes(gm_graph_t *g, uint64_t *bytes) {
+  if (!g || !bytes) { set_error("null argument"); return GM_EINVAL; }
+  *bytes = g->last_alg_bytes;
+  return GM_OK;
+}
+
+}  // extern "C"

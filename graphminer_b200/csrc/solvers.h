@@ -1,0 +1,148 @@
+// solvers.h -- host C++ mirror of the reference's solver boundary, header-only over the C ABI.
+//
+// The reference selects one definition of each solver symbol at link time:
+//   void TCSolver    (Graph &g, uint64_t &total, int n_gpu, int chunk_size);          triangle/main.cc:5
+//   void CliqueSolver(Graph &g, int k, uint64_t &total, int n_gpu, int chunk_size);   clique/main.cc:6
+//   void SglSolver   (Graph &g, Pattern &p, uint64_t &total, int n_gpu, int chunk);   sgl/main.cc:7
+//   void MotifSolver (Graph &g, int k, std::vector<uint64_t> &accum, int, int);       motif/main.cc:7
+// The same four signatures are defined here on top of libgminer_b200.so, with a minimal gm::Graph /
+// gm::Pattern carrying exactly what those solvers read.  Errors follow the reference's CLI
+// behaviour: message on stderr + exit(1) (the C ABI underneath never exits).
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "gminer_b200.h"
+
+namespace gm {
+
+typedef int32_t vidType;
+typedef int64_t eidType;
+
+inline void die_on(int rc, const char *what) {
+  if (rc == GM_OK) return;
+  std::cerr << what << ": " << gm_last_error() << "\n";
+  std::exit(1);
+}
+
+// Host CSR graph in the reference's binary format (src/common/graph.cc:4-124).
+class Graph {
+  std::string name_, path_;
+  vidType nv_ = 0, max_degree_ = 0;
+  eidType ne_ = 0;
+  std::vector<eidType> rowptr_;
+  std::vector<vidType> colidx_;
+
+ public:
+  Graph() {}
+  explicit Graph(const std::string &prefix, bool use_dag = false) {
+    size_t i = prefix.rfind('/');
+    if (i != std::string::npos) path_ = prefix.substr(0, i);
+    i = path_.rfind('/');
+    if (i != std::string::npos) name_ = path_.substr(i + 1);
+    std::cout << "input file path: " << path_ << ", graph name: " << name_ << "\n";
+    die_on(gm_host_read_meta(prefix.c_str(), &nv_, &ne_, &max_degree_), "reading graph meta");
+    rowptr_.resize(size_t(nv_) + 1);
+    colidx_.resize(size_t(ne_));
+    die_on(gm_host_read_graph(prefix.c_str(), nv_, ne_, rowptr_.data(), colidx_.data()), "reading graph");
+    if (use_dag) orientation();
+  }
+  Graph(vidType nv, std::vector<eidType> rowptr, std::vector<vidType> colidx, vidType max_degree)
+      : nv_(nv), max_degree_(max_degree), ne_(eidType(colidx.size())), rowptr_(std::move(rowptr)), colidx_(std::move(colidx)) {}
+
+  // Graph::orientation (graph.cc:233-279)
+  void orientation() {
+    std::cout << "Orientation enabled, using DAG\n";
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<eidType> rp(size_t(nv_) + 1);
+    std::vector<vidType> ci(size_t(ne_) > 0 ? size_t(ne_) : 1);
+    int64_t ne = gm_host_orient(nv_, rowptr_.data(), colidx_.data(), rp.data(), ci.data(), &max_degree_);
+    if (ne < 0) die_on(int(ne), "orientation");
+    ci.resize(size_t(ne));
+    rowptr_.swap(rp); colidx_.swap(ci); ne_ = ne;
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << "Time on generating the DAG: " << s << " sec\n";
+  }
+  vidType V() const { return nv_; }
+  eidType E() const { return ne_; }
+  vidType num_vertices() const { return nv_; }
+  eidType num_edges() const { return ne_; }
+  vidType size() const { return nv_; }
+  eidType sizeEdges() const { return ne_; }
+  vidType get_max_degree() const { return max_degree_; }
+  vidType get_degree(vidType v) const { return vidType(rowptr_[v + 1] - rowptr_[v]); }
+  eidType edge_begin(vidType v) const { return rowptr_[v]; }
+  eidType edge_end(vidType v) const { return rowptr_[v + 1]; }
+  const eidType *out_rowptr() const { return rowptr_.data(); }
+  const vidType *out_colidx() const { return colidx_.data(); }
+  std::string get_name() const { return name_; }
+  void print_meta_data() const {
+    std::cout << "|V|: " << nv_ << ", |E|: " << ne_ << ", Max Degree: " << max_degree_ << "\n";
+  }
+};
+
+// Name-only pattern descriptor (include/pattern.hh:47, is_* :58-75).
+class Pattern {
+  std::string name_;
+ public:
+  explicit Pattern(std::string name) : name_(std::move(name)) {}
+  std::string get_name() const { return name_; }
+  bool is_diamond() const { return name_ == "diamond"; }
+  bool is_rectangle() const { return name_ == "rectangle"; }
+  bool is_house() const { return name_ == "house"; }
+  bool is_pentagon() const { return name_ == "pentagon"; }
+};
+
+static const int num_possible_patterns[] = {0, 1, 1, 2, 6, 21, 112, 853, 11117, 261080};   // pattern.hh:4-15
+
+struct WallTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double seconds() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+}  // namespace gm
+
+// ---- the four solver symbols -------------------------------------------------------------------------
+inline void TCSolver(gm::Graph &g, uint64_t &total, int n_gpu, int /*chunk_size*/) {
+  gm::WallTimer t;
+  gm::die_on(gm_tc_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), n_gpu, &total), "TCSolver");
+  double s = t.seconds();
+  std::cout << "runtime [gpu_base] = " << s << " sec\n";
+  std::cout << "throughput = " << double(g.E()) / s / 1e9 << " billion Traversed Edges Per Second (TEPS)\n";
+}
+
+inline void CliqueSolver(gm::Graph &g, int k, uint64_t &total, int n_gpu, int /*chunk_size*/) {
+  gm::WallTimer t;
+  int rc = gm_kclique_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), k, n_gpu, &total);
+  if (rc == GM_EUNSUPPORTED) { std::cout << "Not supported right now\n"; total = 0; return; }   // clique/gpu_base.cu:69-71
+  gm::die_on(rc, "CliqueSolver");
+  std::cout << "runtime [gpu_base] = " << t.seconds() << " sec\n";
+}
+
+inline void SglSolver(gm::Graph &g, gm::Pattern &p, uint64_t &total, int n_gpu, int /*chunk_size*/) {
+  gm::WallTimer t;
+  int rc = gm_sgl_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), p.get_name().c_str(), n_gpu, &total);
+  if (rc == GM_EUNSUPPORTED) { std::cout << "Not implemented\n"; total = 0; return; }          // sgl/omp_base.cc:52-54
+  gm::die_on(rc, "SglSolver");
+  std::cout << "runtime [cuda_base] = " << t.seconds() << " sec\n";
+}
+
+inline void MotifSolverImpl(gm::Graph &g, int k, std::vector<uint64_t> &accum, int n_gpu, int formula) {
+  gm::WallTimer t;
+  uint64_t c[8] = {0};
+  int rc = gm_motif_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), k, formula, n_gpu, c);
+  if (rc == GM_EUNSUPPORTED) { std::cout << "Not supported right now\n"; return; }              // motif/gpu_base.cu:99-101
+  gm::die_on(rc, "MotifSolver");
+  for (size_t i = 0; i < accum.size() && i < 8; i++) accum[i] = c[i];
+  std::cout << "runtime [cuda_base] = " << t.seconds() << " sec\n";
+}
+#ifdef GM_MOTIF_FORMULA
+inline void MotifSolver(gm::Graph &g, int k, std::vector<uint64_t> &accum, int n_gpu, int) { MotifSolverImpl(g, k, accum, n_gpu, 1); }
+#else
+inline void MotifSolver(gm::Graph &g, int k, std::vector<uint64_t> &accum, int n_gpu, int) { MotifSolverImpl(g, k, accum, n_gpu, 0); }
+#endif

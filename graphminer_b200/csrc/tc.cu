@@ -1,0 +1,226 @@
+// Triangle counting on the (degree,id)-oriented DAG:  sum over edges (u,v) of |N+(u) ∩ N+(v)|
+// (reference: src/triangle/omp_base.cc:15-21 for the definition, src/triangle/gpu_base.cu:25-74 +
+// gpu_kernels/bs_warp_edge.cuh:2-18 for the GPU solver this replaces).
+//
+// Two kernels:
+//   tc_hash_kernel   -- the production path.  Vertex-centric: a thread group owns a root row, hashes
+//                       it into a shared-memory RowTable once, and streams the rows of the root's
+//                       partners (its out-neighbours, or with REVERSE its in-neighbours) from HBM,
+//                       one shared-memory probe per streamed element.  Work items (root, partner
+//                       slice) are size-classed by the root degree and handed out dynamically.
+//   tc_warp_edge_bs  -- warp-per-COO-edge with the header-only operator API (gm/set_ops.cuh); the
+//                       straightforward re-expression of the reference's kernel, kept as a second
+//                       implementation for cross-checking and as the "operator API" consumer.
+#include "gm_internal.cuh"
+#include "hash_table.cuh"
+
+namespace gm {
+
+// ------------------------------------------------------------------------------------------
+template <int GT>   // threads per group
+struct GroupCfg {
+  static constexpr int kCtaThreads = GT < 256 ? 256 : GT;
+  static constexpr int kGroupsPerCta = kCtaThreads / GT;
+  static constexpr int kWarpsPerGroup = GT / 32;
+};
+
+template <int GT>
+__device__ __forceinline__ void group_sync() {
+  if (GT == 32) __syncwarp(); else __syncthreads();
+}
+
+// Stream one aligned row and count table hits.  Warp-collective.
+__device__ __forceinline__ uint32_t stream_probe(const RowTable &tab, const vidType *list, int len, int lane) {
+  uint32_t c = 0;
+  for (int base = 0; base < len; base += 128) {
+    int i = base + lane;
+    vidType x0 = (i < len) ? __ldg(list + i) : kVidMax;
+    vidType x1 = (i + 32 < len) ? __ldg(list + i + 32) : kVidMax;
+    vidType x2 = (i + 64 < len) ? __ldg(list + i + 64) : kVidMax;
+    vidType x3 = (i + 96 < len) ? __ldg(list + i + 96) : kVidMax;
+    c += tab.contains(uint32_t(x0));
+    if (base + 32 < len) c += tab.contains(uint32_t(x1));
+    if (base + 64 < len) c += tab.contains(uint32_t(x2));
+    if (base + 96 < len) c += tab.contains(uint32_t(x3));
+  }
+  return c;
+}
+
+// Fallback when the root row does not fit the table: search it where it lies (global / L2).
+__device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, const vidType *list, int len, int lane) {
+  uint32_t c = 0;
+  for (int i = lane; i < len; i += 32) c += binary_search(root, __ldg(list + i), vidType(d));
+  return c;
+}
+
+template <int GT, int MAXB1, int CAP, bool REVERSE>
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads)
+tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
+               const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
+  using Cfg = GroupCfg<GT>;
+  extern __shared__ uint32_t smem[];
+  __shared__ int64_t s_next;
+  constexpr int kWords = RowTable::words_for_bits(MAXB1, CAP);
+  constexpr int kBatch = GT == 32 ? 4 : 1;
+  const int lane = threadIdx.x & 31;
+  const int gtid = threadIdx.x % GT;                 // rank in group
+  const int gwarp = gtid >> 5;                       // warp in group
+  uint32_t *gbase = smem + (threadIdx.x / GT) * kWords;
+  AccType acc = 0;
+
+  while (true) {
+    int64_t first;
+    if (GT == 32) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(ticket, kBatch);
+      first = int64_t(__shfl_sync(kFullMask, t, 0));
+    } else {
+      __syncthreads();                               // previous item fully done (also guards s_next)
+      if (threadIdx.x == 0) s_next = int64_t(atomicAdd(ticket, kBatch));
+      __syncthreads();
+      first = s_next;
+    }
+    if (first >= nitems) break;
+    for (int b = 0; b < kBatch && first + b < nitems; b++) {
+      WorkItem it = items[first + b];
+      uint2 ri = g.info(it.root);
+      const int d = int(ri.y);
+      const vidType *rrow = g.NA(ri);
+      RowTable tab;
+      const int b1 = RowTable::bits_for(d);
+      bool fits = b1 <= MAXB1;
+      if (fits) {
+        tab.configure(gbase, b1, CAP);
+        if (GT == 32) __syncwarp();                  // previous item's probes are done
+        tab.build(rrow, d, gtid, GT, [] { group_sync<GT>(); });
+        if (tab.overflowed()) fits = false;          // group-uniform
+      }
+      const vidType *P = REVERSE ? pcol + prow[it.root] + it.pbegin
+                                 : g.d_colidx + g.d_rowptr[it.root] + it.pbegin;
+      uint32_t c = 0;
+      for (int pb = gwarp * 32; pb < it.pcount; pb += 32 * Cfg::kWarpsPerGroup) {
+        int pi = pb + lane;
+        uint2 pv = make_uint2(0, 0);
+        if (pi < it.pcount) pv = g.info(__ldg(P + pi));
+        int np = min(32, it.pcount - pb);
+        for (int j = 0; j < np; j++) {
+          uint32_t off = __shfl_sync(kFullMask, pv.x, j);
+          int len = int(__shfl_sync(kFullMask, pv.y, j));
+          const vidType *list = g.d_acol + (size_t(off) << 2);
+          c += fits ? stream_probe(tab, list, len, lane) : stream_bsearch(rrow, d, list, len, lane);
+        }
+      }
+      acc += c;
+    }
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// warp per COO edge, operator API (the reference's schedule: bs_warp_edge.cuh:9-15)
+__global__ void __launch_bounds__(256)
+tc_warp_edge_bs(GraphGPU g, AccType *total) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  AccType count = 0;
+  for (eidType e = warp; e < g.num_tasks; e += nwarps) {
+    vidType u = g.get_src(e), v = g.get_dst(e);
+    count += intersect_num(g.N(u), g.get_degree(u), g.N(v), g.get_degree(v));
+  }
+  count = warp_reduce(count);
+  if (lane == 0 && count) atomicAdd(total, count);
+}
+
+// algorithmic bytes of TC, SURVEY.md §8(d): sum over edges 4*(d(u)+d(v)) + 8|E| + 8(|V|+1)
+__global__ void k_tc_alg_bytes(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx, unsigned long long *out) {
+  vidType u = vb + blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long s = 0;
+  if (u < ve) {
+    eidType b = rowptr[u], e = rowptr[u + 1];
+    unsigned long long du = (unsigned long long)(e - b);
+    for (eidType i = b; i < e; i++) { vidType v = colidx[i]; s += 4ull * (du + (unsigned long long)(rowptr[v + 1] - rowptr[v])) + 8ull; }
+  }
+  s = warp_reduce(s);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+template <int GT, int MAXB1, int CAP, bool REVERSE>
+static int launch_hash_class(gm_graph *g, int cls, const eidType *prow, const vidType *pcol, int *launches) {
+  const ItemList &il = g->items[REVERSE ? 1 : 0][cls];
+  if (il.n == 0) return GM_OK;
+  using Cfg = GroupCfg<GT>;
+  auto kern = tc_hash_kernel<GT, MAXB1, CAP, REVERSE>;
+  size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
+  GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int occ = 0;
+  GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::kCtaThreads, smem));
+  if (occ < 1) { set_error("tc_hash_kernel<%d,%d> does not fit on an SM (smem %zu)", GT, MAXB1, smem); return GM_ECUDA; }
+  int64_t per_cta = int64_t(Cfg::kGroupsPerCta) * (GT == 32 ? 4 : 1);
+  int64_t want = (il.n + per_cta - 1) / per_cta;
+  int grid = int(std::min<int64_t>(want, int64_t(occ) * g->num_sms));
+  kern<<<grid, Cfg::kCtaThreads, smem, g->stream>>>(g->view(0), prow, pcol, il.d_items, il.n, g->d_ticket + cls, g->d_counts);
+  (*launches)++;
+  return GM_OK;
+}
+
+template <bool REVERSE>
+static int run_tc_hash(gm_graph *g, int *launches) {
+  const eidType *prow = REVERSE ? g->d_rrowptr : g->d_rowptr;
+  const vidType *pcol = REVERSE ? g->d_rcolidx : g->d_colidx;
+  GM_TRY((launch_hash_class<32, 7, 16, REVERSE>(g, 0, prow, pcol, launches)));
+  GM_TRY((launch_hash_class<256, 11, 64, REVERSE>(g, 1, prow, pcol, launches)));
+  GM_TRY((launch_hash_class<256, 13, 64, REVERSE>(g, 2, prow, pcol, launches)));
+  GM_TRY((launch_hash_class<1024, 15, 64, REVERSE>(g, 3, prow, pcol, launches)));
+  return GM_OK;
+}
+
+static int tc_alg_bytes(gm_graph *g, uint64_t *out) {
+  vidType n = g->src_end - g->src_begin;
+  unsigned long long *d = nullptr, h = 0;
+  GM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+  GM_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), g->stream));
+  if (n > 0) k_tc_alg_bytes<<<(n + 255) / 256, 256, 0, g->stream>>>(g->src_begin, g->src_end, g->d_rowptr, g->d_colidx, d);
+  GM_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(cudaFree(d));
+  *out = h + 8ull * (uint64_t(g->nv) + 1);
+  return GM_OK;
+}
+
+int prepare_tc(gm_graph *g) {
+  const std::string &algo = options().tc_algo;
+  if (algo == "bs") return ensure_coo(g, 0);
+  GM_TRY(ensure_aligned(g));
+  return ensure_items(g, algo == "hash_rev" ? 1 : 0);
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
+  if (!g || !total) { set_error("gm_tc: null argument"); return GM_EINVAL; }
+  GM_TRY(prepare_tc(g));
+  if (g->tc_bytes_cache == 0) GM_TRY(tc_alg_bytes(g, &g->tc_bytes_cache));
+  g->last_alg_bytes = g->tc_bytes_cache;
+  const std::string &algo = options().tc_algo;
+  int launches = 0;
+  GM_TRY(begin_timed(g));
+  if (algo == "bs") {
+    if (g->nnz[0] > 0) {
+      int occ = 0;
+      GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_warp_edge_bs, 256, 0));
+      int64_t want = (g->nnz[0] + 7) / 8;
+      int grid = int(std::min<int64_t>(want, int64_t(occ) * g->num_sms * 4));
+      tc_warp_edge_bs<<<grid, 256, 0, g->stream>>>(g->view(0), g->d_counts);
+      launches++;
+    }
+  } else if (algo == "hash_rev") {
+    GM_TRY(run_tc_hash<true>(g, &launches));
+  } else {
+    GM_TRY(run_tc_hash<false>(g, &launches));
+  }
+  return end_timed(g, launches, 1, total);
+}

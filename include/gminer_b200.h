@@ -1,0 +1,183 @@
+/*
+ * gminer_b200.h -- C ABI of libgminer_b200.so, the B200-native set-intersection engine for
+ * graph pattern mining.  Plain pointers and sizes only; no C++/torch types cross this line.
+ *
+ * The reference (chenxuhao/GraphMiner) has no FFI: its boundary is the link-time solver symbol
+ * chosen by each Makefile target plus header-only device templates.  Every entry
+ * point below names the reference interface it replaces (paths relative to the reference root).
+ * The C++ shims with the reference's exact solver signatures (TCSolver, CliqueSolver, SglSolver,
+ * MotifSolver) live in graphminer_b200/csrc/solvers.h and forward to these functions; see
+ * INTEGRATION.md for the maintainer-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative GM_E* code on failure, and never calls
+ *     exit(); gm_last_error() gives the message (thread-local).  (Reference: CUDA_SAFE_CALL
+ *     prints and exit()s, include/cutil_subset.h:4-10.)
+ *   - vertex ids are int32 (vidType), CSR offsets int64 (eidType), counts uint64 (AccType)
+ *     -- include/common.h:35-40.
+ *   - adjacency lists are sorted ascending, unique and loop-free (the reference's standing
+ *     assumption, src/triangle/main.cc:13).
+ *   - a gm_graph_t is bound to one device and one stream; it is not thread-safe, distinct
+ *     handles are independent.
+ */
+#ifndef GMINER_B200_H_
+#define GMINER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK 0
+#define GM_EINVAL (-1)    /* bad argument */
+#define GM_ECUDA (-2)     /* CUDA runtime error */
+#define GM_ENOMEM (-3)    /* host or device allocation failed */
+#define GM_EUNSUPPORTED (-4) /* pattern / k not supported ("Not supported right now", clique/gpu_base.cu:69-71) */
+#define GM_EIO (-5)       /* file error */
+#define GM_ENCCL (-6)     /* NCCL error / library not loadable */
+
+typedef struct gm_graph gm_graph_t;   /* opaque device-resident graph (replaces class GraphGPU, include/graph_gpu.h:6-210) */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char *gm_last_error(void);
+int gm_version(void);                       /* 10000*major + 100*minor + patch */
+int gm_device_count(int *count);            /* cudaGetDeviceCount; 0 devices is not an error */
+/* Runtime knobs replacing the reference's compile-time macros (src/common.mk:72-114).
+ * keys: "tc.algo" = auto|hash|hash_rev|bs|merge, "clique.algo" = auto|bitmap|list,
+ *       "sched.chunk" = partners per work item.  Unknown key -> GM_EINVAL. */
+int gm_set_option(const char *key, const char *value);
+
+/* ---- host-side graph preparation (C++/OpenMP; no device needed) ---------------------------- */
+/* Graph::orientation, src/common/graph.cc:233-279.  out_colidx needs room for ne entries.
+ * Returns the oriented edge count (>=0) or a negative error. */
+int64_t gm_host_orient(int32_t nv, const int64_t *rowptr, const int32_t *colidx,
+                       int64_t *out_rowptr, int32_t *out_colidx, int32_t *out_max_degree);
+/* Graph::init_edgelist(sym_break), graph.cc:297-326.  src/dst need room for ne entries.
+ * Returns nnz written. */
+int64_t gm_host_edgelist(int32_t nv, const int64_t *rowptr, const int32_t *colidx, int sym_break,
+                         int32_t *src, int32_t *dst);
+/* PartitionedGraph::edgecut_induced_partition1D for ONE part, src/common/graph_partition.cc:24-132:
+ * vertices [begin,end) plus their 1-hop neighbours, order-preserving relabel, vertex-induced CSR.
+ * Two-call protocol: with sub_rowptr == NULL only the sizes are returned. */
+int gm_host_partition_part(int32_t nv, const int64_t *rowptr, const int32_t *colidx,
+                           int32_t begin, int32_t end,
+                           int64_t *sub_rowptr, int32_t *sub_colidx, int32_t *idx_map,
+                           int32_t *sub_nv, int64_t *sub_ne, int32_t *local_begin, int32_t *local_end);
+/* Source-vertex range boundaries for n shards.  balance=0: equal |V|/n chunks exactly as
+ * graph_partition.cc:84-86; balance=1: equal sum over sources of sum_{u in N(v)} min(d(v),d(u))
+ * (work estimate of src/common/scheduler.cc:14-19).  bounds has n+1 entries. */
+int gm_host_shard_bounds(int32_t nv, const int64_t *rowptr, const int32_t *colidx, int n, int balance,
+                         int32_t *bounds);
+/* Reference on-disk format (graph.cc:19-41, README.md:82-100): <prefix>.meta.txt / .vertex.bin / .edge.bin.
+ * gm_host_read_meta fills nv, ne, max_degree; gm_host_read_graph fills caller arrays. */
+int gm_host_read_meta(const char *prefix, int32_t *nv, int64_t *ne, int32_t *max_degree);
+int gm_host_read_graph(const char *prefix, int32_t nv, int64_t ne, int64_t *rowptr, int32_t *colidx);
+int gm_host_write_graph(const char *prefix, int32_t nv, int64_t ne, int32_t max_degree,
+                        const int64_t *rowptr, const int32_t *colidx);
+
+/* ---- device graph ------------------------------------------------------------------------- */
+/* GraphGPU::init, include/graph_gpu.h:69-122: copy a host CSR to `device`.  Host arrays are
+ * borrowed only for the duration of the call.  max_degree <= 0 means "compute it". */
+int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
+                    int32_t max_degree, int device, gm_graph_t **out);
+/* Adopt a CSR that is already resident on `device` (no copy; caller keeps ownership of the two
+ * arrays and must keep them alive).  Used when the graph was built on the GPU. */
+int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv, int64_t ne,
+                   int32_t max_degree, int device, gm_graph_t **out);
+int gm_graph_free(gm_graph_t *g);           /* GraphGPU::clean + clean_edgelist, graph_gpu.h:56-63 */
+/* Launch on this cudaStream_t (as void*); NULL = the library's own stream for the device. */
+int gm_graph_set_stream(gm_graph_t *g, void *cuda_stream);
+/* Restrict the solvers to source vertices (DFS roots) in [begin,end): the multi-GPU shard of
+ * triangle/multigpu.cu:73-75 (warp_vertex<<<>>>(local_begin, local_end, ...)).  Default [0,nv). */
+int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end);
+/* Build the auxiliary device structures a solver needs (padded 16-byte-aligned CSR, COO task list
+ * = GraphGPU::init_edgelist graph_gpu.h:124-178, degree-binned work items) ahead of the timed
+ * call.  what: "tc", "clique", "sgl:<pattern>", "motif", or "all".  Solvers call it lazily. */
+int gm_graph_prepare(gm_graph_t *g, const char *what);
+int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, int *device);
+
+/* ---- solvers on a device-resident graph (what *_gpu_base time: kernel only) ------------------ */
+/* TCSolver, src/triangle/gpu_base.cu:25-74.  g must be the (degree,id)-oriented DAG. */
+int gm_tc(gm_graph_t *g, uint64_t *total);
+/* CliqueSolver, src/clique/gpu_base.cu:16-79.  DAG input; k in 3..8 (reference GPU: 4..8, OMP: 3..5). */
+int gm_kclique(gm_graph_t *g, int k, uint64_t *total);
+/* SglSolver, src/sgl/gpu_base.cu:21-103.  Undirected input; pattern in
+ * {"diamond","rectangle","house","pentagon"} (edge-induced counts). */
+int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total);
+/* MotifSolver, src/motif/gpu_base.cu:21-111.  Undirected input; k=3 -> counts[2] = {wedge, triangle}
+ * (OMP order, motif/cpu_kernels/automine_base.h:13,18), k=4 -> counts[6] = {3-star, 4-path,
+ * tailed-triangle, 4-cycle, diamond, 4-clique} (vertex-induced). */
+int gm_motif(gm_graph_t *g, int k, uint64_t *counts);
+/* MotifSolver (formula), src/motif/gpu_formula.cu:22-110: closed forms from per-edge triangle
+ * counts, only 4-cycle / 4-clique enumerated.  Same outputs as gm_motif. */
+int gm_motif_formula(gm_graph_t *g, int k, uint64_t *counts);
+/* The closed forms divide (omp_formula.cc:42-45), so they are not additive over shards: a shard
+ * returns its RAW partial sums with _raw, the caller adds the shards and applies _finish once. */
+int gm_motif_formula_raw(gm_graph_t *g, int k, uint64_t *counts);
+int gm_motif_formula_finish(int k, uint64_t *counts);
+
+/* Device time (ms, CUDA events on the graph's stream) and number of kernel launches of the last
+ * solver call on this graph. */
+int gm_last_stats(gm_graph_t *g, float *kernel_ms, int *launches);
+/* Algorithmic bytes of the last solver call per SURVEY.md §8(d) (lists read + COO + rowptr). */
+int gm_last_alg_bytes(gm_graph_t *g, uint64_t *bytes);
+
+/* ---- end-to-end host entry points (host CSR in, counts out; upload + prepare + kernel) -------- */
+/* These are what the reference-signature shims call: Graph lives in host memory
+ * (triangle/main.cc:5 etc.); n_gpus > 1 shards by source-vertex range over devices
+ * 0..n_gpus-1 (one host thread per device, triangle/multigpu.cu:16-89) and sums the counts with one
+ * ncclAllReduce(uint64, sum) when NCCL is loadable, else on the host. */
+int gm_tc_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
+               int32_t max_degree, int n_gpus, uint64_t *total);
+int gm_kclique_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
+                    int32_t max_degree, int k, int n_gpus, uint64_t *total);
+int gm_sgl_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
+                int32_t max_degree, const char *pattern, int n_gpus, uint64_t *total);
+int gm_motif_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
+                  int32_t max_degree, int k, int use_formula, int n_gpus, uint64_t *counts);
+
+/* ---- batched set operators (unit tests + the streaming HBM microbenchmark) ----- */
+/* ops: the warp-cooperative device operators of include/set_intersect.cuh, set_difference.cuh,
+ * operations.cuh, applied to `npairs` independent (a,b) pairs whose lists live in `d_pool`
+ * (device int32 array): a_i = pool[a_off[i] .. a_off[i]+a_len[i]).  `bound` / `anc` arrays may be
+ * NULL when the op does not use them.  out[i] (device uint64) receives the count; for the
+ * materialising ops (GM_OP_*_SET) d_out_pool/out_off receive the elements as well.
+ * algo: GM_ALGO_AUTO or one specific variant (each variant is what gets an ncu capture). */
+enum {
+  GM_OP_INTERSECT_NUM = 0,        /* |a ∩ b|                       set_intersect.cuh:352-357, VertexSet.h:65-76 */
+  GM_OP_INTERSECT_NUM_BOUND = 1,  /* |{x∈a∩b : x<bound}|           set_intersect.cuh:428-433, VertexSet.h:110-122 */
+  GM_OP_INTERSECT_NUM_BOUND_EXCEPT = 2, /* ... and x != anc        set_intersect.cuh:436-468, VertexSet.h:150-163 */
+  GM_OP_INTERSECT_NUM_EXCEPT2 = 3, /* x != anc and x != anc2      set_intersect.cuh:471-503, VertexSet.h:178-189 */
+  GM_OP_DIFFERENCE_NUM = 4,       /* |a \ b \ {anc}|               set_difference.cuh:38-40, VertexSet.cc:21-43 */
+  GM_OP_DIFFERENCE_NUM_BOUND = 5, /* |{x∈a\b\{anc} : x<bound}|     set_difference.cuh:84-86, VertexSet.cc:69-89 */
+  GM_OP_INTERSECT_SET = 6,        /* a ∩ b materialised            set_intersect.cuh:109-114, VertexSet.h:53-64 */
+  GM_OP_INTERSECT_SET_BOUND = 7,  /*                               set_intersect.cuh:191-193, VertexSet.h:95-108 */
+  GM_OP_DIFFERENCE_SET = 8,       /* a \ b \ {anc} materialised    set_difference.cuh:138-140 */
+  GM_OP_DIFFERENCE_SET_BOUND = 9, /*                               set_difference.cuh:199-201, VertexSet.cc:46-67 */
+  GM_OP_COUNT_SMALLER = 10        /* #{x∈a : x<bound}              operations.cuh:61-105, VertexSet.h:240-255 */
+};
+enum {
+  GM_ALGO_AUTO = 0,
+  GM_ALGO_BSEARCH = 1,   /* warp: keys of the shorter list, pivot-cached binary search in the longer */
+  GM_ALGO_MERGE = 2,     /* warp: lists TMA-staged into shared memory, merge-path partition + serial merge */
+  GM_ALGO_HASH = 3,      /* warp: shorter list hashed into shared memory, longer list streamed (128-bit loads) */
+  GM_ALGO_GALLOP = 4     /* warp: exponential gallop from the previous hit (skewed pairs) */
+};
+int gm_intersect_batch(const int32_t *d_pool, const int64_t *d_a_off, const int32_t *d_a_len,
+                       const int64_t *d_b_off, const int32_t *d_b_len,
+                       const int32_t *d_bound, const int32_t *d_anc, const int32_t *d_anc2,
+                       int64_t npairs, int op, int algo, uint64_t *d_out,
+                       int32_t *d_out_pool, const int64_t *d_out_off,
+                       int device, void *cuda_stream);
+
+/* ---- multi-GPU reduction ------------------------------------------------------------------ */
+/* Sum `n` uint64 values across `n_gpus` device buffers with NCCL (ncclAllReduce, ncclUint64,
+ * ncclSum) -- replaces the host loop `total += h_counts[i]` (triangle/multigpu.cu:84) and
+ * MPI_Allreduce (triangle/dist_gpu.cpp:30).  d_bufs[i] lives on device devices[i]. */
+int gm_allreduce_u64(uint64_t **d_bufs, const int *devices, int n_gpus, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMINER_B200_H_ */

@@ -1,0 +1,87 @@
+"""CPU-side checks of the C ABI: the library loads, exports every declared symbol, the host-side
+graph preparation matches the oracle, and compute entry points fail loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from graphminer_b200 import capi
+from graphminer_b200.rmat import rmat_graph
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gminer_b200.h")).read()
+    declared = set(re.findall(r"\b(gm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"gm_graph_t"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    L = capi.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.gm_version() >= 100
+
+
+def test_host_orient_edgelist_match_oracle(citeseer):
+    rp, ci, _ = citeseer
+    a = capi.host_orient(rp, ci)
+    b = oracle.orient(rp, ci)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    for sb in (False, True):
+        s1, d1 = capi.host_edgelist(rp, ci, sb)
+        s2, d2 = oracle.edgelist(rp, ci, sb)
+        assert np.array_equal(s1, s2) and np.array_equal(d1, d2)
+
+
+def test_host_partition_matches_oracle_and_is_closed():
+    rp, ci = (t.numpy() for t in rmat_graph(10))
+    orp, oci, _ = oracle.orient(rp, ci)
+    nv = len(orp) - 1
+    total = 0
+    bounds = capi.host_shard_bounds(orp, oci, 3, balance=False)
+    assert list(bounds) == [0, 342, 684, 1024]                  # ceil(nv/3) chunks, graph_partition.cc:84-86
+    for b, e in zip(bounds[:-1], bounds[1:]):
+        got = capi.host_partition_part(orp, oci, int(b), int(e))
+        exp = oracle.partition_part(orp, oci, int(b), int(e))
+        for x, y in zip(got, exp):
+            assert np.array_equal(x, y)
+        srp, sci, idx, lb, le = got
+        # the shard is closed for TC: counting its local source range reproduces the global range
+        total += oracle.tc(srp, sci, (lb, le))
+        assert oracle.tc(srp, sci, (lb, le)) == oracle.tc(orp, oci, (int(b), int(e)))
+    assert total == oracle.tc(orp, oci)
+    bal = capi.host_shard_bounds(orp, oci, 4, balance=True)
+    assert bal[0] == 0 and bal[-1] == nv and np.all(np.diff(bal) >= 0)
+
+
+def test_graph_file_round_trip(tmp_path, citeseer):
+    rp, ci, md = citeseer
+    prefix = str(tmp_path / "graph")
+    capi.write_graph(prefix, rp, ci, md)
+    rp2, ci2, md2 = capi.read_graph(prefix)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and md == md2
+    with pytest.raises(capi.GMError):
+        capi.read_graph(str(tmp_path / "missing"))
+
+
+def test_compute_fails_loudly_without_gpu(citeseer):
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    rp, ci, md = citeseer
+    with pytest.raises(capi.GMError):
+        capi.DeviceGraph(rp, ci, md)
+    with pytest.raises(capi.GMError):
+        capi.tc_host(rp, ci, md)
+
+
+def test_bad_arguments_are_errors_not_exits():
+    with pytest.raises(capi.GMError):
+        capi.set_option("no.such.option", "1")
+    with pytest.raises(capi.GMError):
+        capi.set_option("tc.algo", "bogus")
+    with pytest.raises(capi.GMError):
+        capi.kclique_host(np.zeros(2, np.int64), np.zeros(0, np.int32), 9)
+    with pytest.raises(capi.GMError):
+        capi.sgl_host(np.zeros(2, np.int64), np.zeros(0, np.int32), "no-such-pattern")

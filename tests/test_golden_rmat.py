@@ -1,0 +1,71 @@
+"""The oracle (C restatement) against golden vectors produced by the UNMODIFIED reference OpenMP
+binaries on this repo's deterministic R-MAT graphs (tests/golden/rmat_counts.json, made by
+tools/make_golden.py in the build container).  Also guards the generator against drift."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from graphminer_b200.rmat import rmat_graph, shaped_graph
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rmat_counts.json")))
+
+
+def graph(name):
+    if name.startswith("rmat"):
+        rp, ci = rmat_graph(int(name[4:]))
+    else:
+        rp, ci = shaped_graph(3000, 40000, 0x5EED004C)
+    return rp.numpy(), ci.numpy()
+
+
+@pytest.mark.parametrize("name", ["rmat8", "rmat10", "rmat12", "shaped3000"])
+def test_oracle_matches_reference_binaries(name):
+    g = GOLD[name]
+    rp, ci = graph(name)
+    assert len(rp) - 1 == g["nv"] and len(ci) == g["ne"] and int(ci.astype(np.int64).sum()) == g["colidx_sum"]
+    orp, oci, _ = oracle.orient(rp, ci)
+    assert oracle.tc(orp, oci) == g["tc"]
+    assert oracle.kclique(orp, oci, 4) == g["clique4"]
+    assert oracle.kclique(orp, oci, 5) == g["clique5"]
+    for p in ("diamond", "rectangle", "house", "pentagon"):
+        assert oracle.sgl(rp, ci, p) == g[p], p
+    assert oracle.motif(rp, ci, 3) == g["motif3"]
+    assert oracle.motif(rp, ci, 4) == g["motif4"] == g["motif4_formula"]
+    assert oracle.motif_formula(rp, ci, 4) == g["motif4_formula"]
+    assert oracle.motif_formula(rp, ci, 3) == g["motif3"]
+
+
+@pytest.mark.parametrize("name", ["rmat14", "rmat16"])
+def test_oracle_matches_reference_binaries_large(name):
+    g = GOLD[name]
+    rp, ci = graph(name)
+    assert len(ci) == g["ne"] and int(ci.astype(np.int64).sum()) == g["colidx_sum"]
+    orp, oci, _ = oracle.orient(rp, ci)
+    assert oracle.tc(orp, oci) == g["tc"]
+    assert oracle.kclique(orp, oci, 4) == g["clique4"]
+    assert oracle.sgl(rp, ci, "diamond") == g["diamond"]
+    assert oracle.motif_formula(rp, ci, 4) == g["motif4_formula"]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_ref_shim_matches_oracle():
+    """oracle/_ref/libgm_ref.so (reference VertexSet code behind a range shim) == C restatement."""
+    rp, ci = graph("rmat10")
+    orp, oci, md = oracle.orient(rp, ci)
+    L = oracle.ref_lib()
+    h = L.gmr_graph_create(len(orp) - 1, orp, oci, md)
+    try:
+        assert L.gmr_tc_range(h, 0, len(orp) - 1) == GOLD["rmat10"]["tc"]
+        assert L.gmr_tc_range(h, 100, 500) == oracle.tc(orp, oci, (100, 500))
+        assert L.gmr_kclique_range(h, 4, 0, len(orp) - 1) == GOLD["rmat10"]["clique4"]
+        assert L.gmr_kclique_range(h, 5, 0, len(orp) - 1) == GOLD["rmat10"]["clique5"]
+    finally:
+        L.gmr_graph_free(h)
+    h = L.gmr_graph_create(len(rp) - 1, rp, ci, int(np.diff(rp).max()))
+    try:
+        assert L.gmr_diamond_range(h, 0, len(rp) - 1) == GOLD["rmat10"]["diamond"]
+    finally:
+        L.gmr_graph_free(h)

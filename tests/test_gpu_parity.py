@@ -1,0 +1,314 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, the reference README
+known-answer tables (citeseer, mico) and the golden vectors of the reference's own OpenMP binaries
+on generated R-MAT graphs.  Bit-exact: every quantity here is an integer count."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from graphminer_b200 import capi
+from graphminer_b200.rmat import rmat_graph, shaped_graph
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(__file__)
+KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+GOLD = json.load(open(os.path.join(HERE, "golden", "rmat_counts.json")))
+TC_ALGOS = ["hash", "hash_rev", "bs"]
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    yield
+    capi.set_option("tc.algo", "auto")
+    capi.set_option("clique.algo", "auto")
+    capi.set_option("sched.chunk", 0)
+
+
+def _graph(name):
+    if name.startswith("rmat"):
+        rp, ci = rmat_graph(int(name[4:]))
+    else:
+        rp, ci = shaped_graph(3000, 40000, 0x5EED004C)
+    return rp.numpy(), ci.numpy()
+
+
+def _dag(rp, ci):
+    return capi.host_orient(rp, ci)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", TC_ALGOS)
+@pytest.mark.parametrize("name", ["citeseer", "mico"])
+def test_tc_kat(name, algo, request):
+    rp, ci, _ = request.getfixturevalue(name)
+    orp, oci, md = _dag(rp, ci)
+    capi.set_option("tc.algo", algo)
+    with capi.DeviceGraph(orp, oci, md) as g:
+        assert g.tc() == KAT[name]["tc"]
+        ms, launches = g.last_stats()
+        assert launches >= 1 and ms > 0
+        assert g.tc() == KAT[name]["tc"]          # cached aux structures, second call
+
+
+def test_tc_alg_bytes_citeseer_mico(citeseer, mico):
+    # SURVEY.md section 8(d) sanity values (with the rowptr term)
+    for (rp, ci, _), want in ((citeseer, 127660), (mico, 280387976)):
+        orp, oci, md = _dag(rp, ci)
+        with capi.DeviceGraph(orp, oci, md) as g:
+            g.tc()
+            assert g.last_alg_bytes() == want
+
+
+@pytest.mark.parametrize("algo", TC_ALGOS)
+@pytest.mark.parametrize("name", ["rmat8", "rmat10", "rmat12", "rmat14", "rmat16", "shaped3000"])
+def test_tc_golden(name, algo):
+    rp, ci = _graph(name)
+    orp, oci, md = _dag(rp, ci)
+    capi.set_option("tc.algo", algo)
+    with capi.DeviceGraph(orp, oci, md) as g:
+        assert g.tc() == GOLD[name]["tc"]
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 1000000])
+def test_tc_chunking_is_invisible(chunk):
+    rp, ci = _graph("rmat12")
+    orp, oci, md = _dag(rp, ci)
+    capi.set_option("sched.chunk", chunk)
+    for algo in ("hash", "hash_rev"):
+        capi.set_option("tc.algo", algo)
+        with capi.DeviceGraph(orp, oci, md) as g:
+            assert g.tc() == GOLD["rmat12"]["tc"]
+
+
+def test_tc_edge_cases():
+    # empty graph, isolated vertices, a single triangle, a clique, a star (hub row much longer than the rest)
+    def csr(n, edges):
+        adj = [[] for _ in range(n)]
+        for u, v in edges:
+            adj[u].append(v); adj[v].append(u)
+        rp = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            rp[i + 1] = rp[i] + len(adj[i])
+        ci = np.array([x for a in adj for x in sorted(a)], np.int32)
+        return rp, ci
+    cases = {
+        "empty": (csr(5, []), 0),
+        "triangle": (csr(4, [(0, 1), (1, 2), (0, 2)]), 1),
+        "k6": (csr(6, [(i, j) for i in range(6) for j in range(i)]), 20),
+        "star": (csr(300, [(0, i) for i in range(1, 300)]), 0),
+        "wheel": (csr(200, [(0, i) for i in range(1, 200)] + [(i, i + 1) for i in range(1, 199)]), 198),
+    }
+    for name, ((rp, ci), want) in cases.items():
+        orp, oci, md = _dag(rp, ci)
+        assert oracle.tc(orp, oci) == want, name
+        for algo in TC_ALGOS:
+            capi.set_option("tc.algo", algo)
+            with capi.DeviceGraph(orp, oci, max(md, 1)) as g:
+                assert g.tc() == want, (name, algo)
+
+
+def test_tc_big_rows_fall_back_correctly():
+    # a row longer than the largest shared-memory table (d > 8192) exercises the global-search path
+    n = 9500
+    edges = [(0, i) for i in range(1, n)] + [(i, i + 1) for i in range(1, n - 1)]
+    rp = np.zeros(n + 1, np.int64)
+    adj = [[] for _ in range(n)]
+    for u, v in edges:
+        adj[u].append(v); adj[v].append(u)
+    for i in range(n):
+        rp[i + 1] = rp[i] + len(adj[i])
+    ci = np.array([x for a in adj for x in sorted(a)], np.int32)
+    # NOT oriented: feed the symmetric graph as if it were a DAG so row 0 keeps its 9499 entries;
+    # sum over directed entries (u,v) of |N(u) ∩ N(v)| is still well defined and the oracle computes it
+    want = oracle.tc(rp, ci)
+    for algo in TC_ALGOS:
+        capi.set_option("tc.algo", algo)
+        with capi.DeviceGraph(rp, ci, n - 1) as g:
+            assert g.tc() == want, algo
+
+
+def test_tc_source_range_shards_add_up():
+    rp, ci = _graph("rmat14")
+    orp, oci, md = _dag(rp, ci)
+    nv = len(orp) - 1
+    bounds = capi.host_shard_bounds(orp, oci, 4, balance=True)
+    for algo in TC_ALGOS:
+        capi.set_option("tc.algo", algo)
+        with capi.DeviceGraph(orp, oci, md) as g:
+            parts = []
+            for b, e in zip(bounds[:-1], bounds[1:]):
+                g.set_source_range(int(b), int(e))
+                parts.append(g.tc())
+                assert parts[-1] == oracle.tc(orp, oci, (int(b), int(e)))
+            assert sum(parts) == GOLD["rmat14"]["tc"]
+            g.set_source_range(0, nv)
+            assert g.tc() == GOLD["rmat14"]["tc"]
+
+
+def test_tc_on_induced_partition():
+    """graph_partition.cc semantics: each shard = range + 1-hop halo, relabelled; local range counted."""
+    rp, ci = _graph("rmat12")
+    orp, oci, md = _dag(rp, ci)
+    bounds = capi.host_shard_bounds(orp, oci, 3, balance=False)
+    total = 0
+    for b, e in zip(bounds[:-1], bounds[1:]):
+        srp, sci, idx, lb, le = capi.host_partition_part(orp, oci, int(b), int(e))
+        with capi.DeviceGraph(srp, sci, 0) as g:
+            g.set_source_range(lb, le)
+            total += g.tc()
+    assert total == GOLD["rmat12"]["tc"]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["list", "auto"])
+def test_kclique_kat(citeseer, mico, algo):
+    capi.set_option("clique.algo", algo)
+    rp, ci, _ = citeseer
+    orp, oci, md = _dag(rp, ci)
+    with capi.DeviceGraph(orp, oci, md) as g:
+        assert g.kclique(3) == KAT["citeseer"]["tc"]
+        assert g.kclique(4) == KAT["citeseer"]["clique4"]
+        assert g.kclique(5) == KAT["citeseer"]["clique5"]
+    rp, ci, _ = mico
+    orp, oci, md = _dag(rp, ci)
+    with capi.DeviceGraph(orp, oci, md) as g:
+        assert g.kclique(4) == KAT["mico"]["clique4"]
+        assert g.kclique(5) == KAT["mico"]["clique5"]
+
+
+@pytest.mark.parametrize("algo", ["list", "auto"])
+@pytest.mark.parametrize("name", ["rmat8", "rmat10", "rmat12", "rmat14", "shaped3000"])
+def test_kclique_golden(name, algo):
+    capi.set_option("clique.algo", algo)
+    rp, ci = _graph(name)
+    orp, oci, md = _dag(rp, ci)
+    with capi.DeviceGraph(orp, oci, md) as g:
+        assert g.kclique(4) == GOLD[name]["clique4"]
+        assert g.kclique(5) == GOLD[name]["clique5"]
+
+
+@pytest.mark.parametrize("algo", ["list", "auto"])
+def test_kclique_deep_matches_closed_form(algo):
+    # K_n contains C(n,k) k-cliques: checks k = 6, 7, 8 (the oracle stops at 5, automine_omp.h:159-183)
+    from math import comb
+    capi.set_option("clique.algo", algo)
+    n = 14
+    rp = np.arange(0, n * (n - 1) + 1, n - 1, dtype=np.int64)
+    ci = np.array([j for i in range(n) for j in range(n) if j != i], np.int32)
+    orp, oci, md = _dag(rp, ci)
+    with capi.DeviceGraph(orp, oci, md) as g:
+        for k in range(3, 9):
+            assert g.kclique(k) == comb(n, k), k
+        with pytest.raises(capi.GMError):
+            g.kclique(9)
+
+
+def test_kclique_shards_add_up():
+    rp, ci = _graph("rmat12")
+    orp, oci, md = _dag(rp, ci)
+    bounds = capi.host_shard_bounds(orp, oci, 3, balance=True)
+    for algo in ("list", "auto"):
+        capi.set_option("clique.algo", algo)
+        with capi.DeviceGraph(orp, oci, md) as g:
+            tot = 0
+            for b, e in zip(bounds[:-1], bounds[1:]):
+                g.set_source_range(int(b), int(e))
+                tot += g.kclique(4)
+            assert tot == GOLD["rmat12"]["clique4"]
+
+
+# ---------------------------------------------------------------------------------------------
+def test_sgl_kat(citeseer, mico):
+    rp, ci, md = citeseer
+    with capi.DeviceGraph(rp, ci, md) as g:
+        for p in ("diamond", "rectangle", "house", "pentagon"):
+            assert g.sgl(p) == KAT["citeseer"][p], p
+        with pytest.raises(capi.GMError):
+            g.sgl("dumbbell")
+    rp, ci, md = mico
+    with capi.DeviceGraph(rp, ci, md) as g:
+        assert g.sgl("diamond") == KAT["mico"]["diamond"]
+        assert g.sgl("rectangle") == KAT["mico"]["rectangle"]
+
+
+@pytest.mark.parametrize("name", ["rmat8", "rmat10", "rmat12", "shaped3000"])
+def test_sgl_golden(name):
+    rp, ci = _graph(name)
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        for p in ("diamond", "rectangle", "house", "pentagon"):
+            assert g.sgl(p) == GOLD[name][p], (name, p)
+
+
+def test_sgl_shards_add_up():
+    rp, ci = _graph("rmat10")
+    nv = len(rp) - 1
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        for p in ("diamond", "rectangle", "house", "pentagon"):
+            tot = 0
+            for b, e in ((0, 300), (300, 301), (301, nv)):
+                g.set_source_range(b, e)
+                got = g.sgl(p)
+                assert got == oracle.sgl(rp, ci, p, (b, e)), (p, b, e)
+                tot += got
+            assert tot == GOLD["rmat10"][p]
+
+
+# ---------------------------------------------------------------------------------------------
+def test_motif_kat(citeseer, mico):
+    rp, ci, md = citeseer
+    with capi.DeviceGraph(rp, ci, md) as g:
+        assert g.motif(3) == KAT["citeseer"]["motif3"]
+        assert g.motif(4) == KAT["citeseer"]["motif4"]
+        assert g.motif(3, formula=True) == KAT["citeseer"]["motif3"]
+        assert g.motif(4, formula=True) == KAT["citeseer"]["motif4"]
+        with pytest.raises(capi.GMError):
+            g.motif(5)
+    rp, ci, md = mico
+    with capi.DeviceGraph(rp, ci, md) as g:
+        assert g.motif(3) == KAT["mico"]["motif3"]
+        assert g.motif(4, formula=True) == KAT["mico"]["motif4"]
+        assert g.motif(4) == KAT["mico"]["motif4"]
+
+
+@pytest.mark.parametrize("name", ["rmat8", "rmat10", "rmat12", "shaped3000"])
+def test_motif_golden(name):
+    rp, ci = _graph(name)
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        assert g.motif(3) == GOLD[name]["motif3"]
+        assert g.motif(4) == GOLD[name]["motif4"]
+        assert g.motif(4, formula=True) == GOLD[name]["motif4_formula"]
+        assert g.motif(3, formula=True) == GOLD[name]["motif3"]
+
+
+def test_motif_shards_add_up():
+    rp, ci = _graph("rmat10")
+    nv = len(rp) - 1
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        base = np.zeros(6, np.uint64); raw = np.zeros(6, np.uint64)
+        for b, e in ((0, 400), (400, nv)):
+            g.set_source_range(b, e)
+            got = g.motif(4)
+            assert got == oracle.motif(rp, ci, 4, (b, e))
+            base += np.array(got, np.uint64)
+            raw += np.array(g.motif(4, formula=True, raw=True), np.uint64)
+        assert [int(x) for x in base] == GOLD["rmat10"]["motif4"]
+        assert capi.motif_formula_finish(4, raw) == GOLD["rmat10"]["motif4"]
+
+
+# ---------------------------------------------------------------------------------------------
+def test_host_entry_points(citeseer):
+    rp, ci, md = citeseer
+    orp, oci, omd = _dag(rp, ci)
+    k = KAT["citeseer"]
+    assert capi.tc_host(orp, oci, omd) == k["tc"]
+    assert capi.kclique_host(orp, oci, 4, omd) == k["clique4"]
+    assert capi.sgl_host(rp, ci, "diamond", md) == k["diamond"]
+    assert capi.motif_host(rp, ci, 4, False, md) == k["motif4"]
+    assert capi.motif_host(rp, ci, 4, True, md) == k["motif4"]
+    assert capi.motif_host(rp, ci, 3, True, md) == k["motif3"]
+    # asking for more GPUs than present clamps (triangle/multigpu.cu:28-30) and still counts right
+    assert capi.tc_host(orp, oci, omd, n_gpus=64) == k["tc"]
+    assert capi.motif_host(rp, ci, 4, True, md, n_gpus=64) == k["motif4"]
