@@ -92,6 +92,8 @@ struct gm_graph {
   int *d_ticket = nullptr;                    // dynamic work counters (8)
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // size classes of one pass run concurrently
+  cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
   float last_ms = 0.f;
   int last_launches = 0;
   uint64_t last_alg_bytes = 0;
@@ -116,5 +118,7 @@ int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int reverse);
 int ensure_scratch(gm_graph *g, size_t bytes);
 int begin_timed(gm_graph *g);
+int fork_streams(gm_graph *g);
+int join_streams(gm_graph *g);
 int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out);
 }  // namespace gm

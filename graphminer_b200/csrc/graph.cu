@@ -284,6 +284,21 @@ int begin_timed(gm_graph *g) {
   return GM_OK;
 }
 
+// side streams start after everything queued on the main stream so far ...
+int fork_streams(gm_graph *g) {
+  GM_CUDA(cudaEventRecord(g->fork_ev, g->stream));
+  for (int i = 0; i < 3; i++) GM_CUDA(cudaStreamWaitEvent(g->side[i], g->fork_ev, 0));
+  return GM_OK;
+}
+// ... and the main stream continues only when all of them are done
+int join_streams(gm_graph *g) {
+  for (int i = 0; i < 3; i++) {
+    GM_CUDA(cudaEventRecord(g->join_ev[i], g->side[i]));
+    GM_CUDA(cudaStreamWaitEvent(g->stream, g->join_ev[i], 0));
+  }
+  return GM_OK;
+}
+
 int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out) {
   GM_CUDA(cudaEventRecord(g->ev1, g->stream));
   GM_CUDA(cudaGetLastError());
@@ -316,6 +331,11 @@ static int init_common(gm_graph *g) {
   GM_CUDA(cudaMallocHost(&g->h_counts, 8 * sizeof(unsigned long long)));
   GM_CUDA(cudaEventCreate(&g->ev0));
   GM_CUDA(cudaEventCreate(&g->ev1));
+  GM_CUDA(cudaEventCreateWithFlags(&g->fork_ev, cudaEventDisableTiming));
+  for (int i = 0; i < 3; i++) {
+    GM_CUDA(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
+    GM_CUDA(cudaEventCreateWithFlags(&g->join_ev[i], cudaEventDisableTiming));
+  }
   cudaDeviceProp p;
   GM_CUDA(cudaGetDeviceProperties(&p, g->device));
   g->num_sms = p.multiProcessorCount;
@@ -413,6 +433,8 @@ int gm_graph_free(gm_graph_t *g) {
   if (g->h_counts) cudaFreeHost(g->h_counts);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->fork_ev) cudaEventDestroy(g->fork_ev);
+  for (int i = 0; i < 3; i++) { if (g->side[i]) cudaStreamDestroy(g->side[i]); if (g->join_ev[i]) cudaEventDestroy(g->join_ev[i]); }
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   cudaGetLastError();
   delete g;

@@ -83,6 +83,33 @@ struct RowTable {
   }
   __device__ __forceinline__ bool overflowed() const { return *nstash > stash_cap; }
 
+  // ---- hot-path probes --------------------------------------------------------------------
+  // The probe loop addresses the table through a 32-bit shared-window address and ld.shared, so the
+  // per-probe sequence is IMAD, SHF, LEA, LDS, LOP3, ISETP (+ISETP for the overflow flag).  Going
+  // through the generic pointers above makes nvcc re-derive the shared window base for every probe
+  // (S2UR SR_CgaCtaId / UMOV / ULEA -- seen in the round-1 ncu source page, 18 SASS per probe).
+  __device__ __forceinline__ uint32_t saddr1() const { return uint32_t(__cvta_generic_to_shared(t1)); }
+  __device__ __forceinline__ static uint32_t lds(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  }
+  // first-level probe: returns the raw slot word
+  __device__ __forceinline__ uint32_t probe1(uint32_t s1, uint32_t x) const {
+    return lds(s1 + (((x * kHashK1) >> sh1) << 2));
+  }
+  __device__ __forceinline__ static bool is_hit(uint32_t slot, uint32_t x) { return (slot & kKeyMask) == x; }
+  // a miss on a flagged slot must consult level 2 / the stash
+  __device__ __forceinline__ static bool needs_l2(uint32_t slot, uint32_t x) { return int32_t(slot) < 0 && (slot & kKeyMask) != x; }
+  __device__ __forceinline__ bool probe2(uint32_t x) const {
+    uint32_t t = t2[(x * kHashK2) >> sh2];
+    if ((t & kKeyMask) == x) return true;
+    if (!(t & kSlotFlag)) return false;
+    int n = min(*nstash, stash_cap);
+    for (int i = 0; i < n; i++) if (stash[i] == x) return true;
+    return false;
+  }
+
   // membership; may be called divergently
   __device__ __forceinline__ bool contains(uint32_t x) const {
     uint32_t t = t1[(x * kHashK1) >> sh1];

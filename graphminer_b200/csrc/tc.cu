@@ -29,19 +29,30 @@ __device__ __forceinline__ void group_sync() {
   if (GT == 32) __syncwarp(); else __syncthreads();
 }
 
-// Stream one aligned row and count table hits.  Warp-collective.
-__device__ __forceinline__ uint32_t stream_probe(const RowTable &tab, const vidType *list, int len, int lane) {
+// Stream one aligned row and count table hits.  Warp-collective.  Four coalesced 128-byte loads are
+// in flight per iteration; probes go two chunks at a time with the level-2 lookups of both deferred
+// into one (rarely taken, few-lane) branch.
+__device__ __forceinline__ uint32_t probe_pair(const RowTable &tab, uint32_t s1, uint32_t xa, uint32_t xb) {
+  uint32_t ta = tab.probe1(s1, xa), tb = tab.probe1(s1, xb);
+  uint32_t c = uint32_t(RowTable::is_hit(ta, xa)) + uint32_t(RowTable::is_hit(tb, xb));
+  bool qa = RowTable::needs_l2(ta, xa), qb = RowTable::needs_l2(tb, xb);
+  if (qa | qb) {
+    if (qa) c += tab.probe2(xa);
+    if (qb) c += tab.probe2(xb);
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint32_t stream_probe(const RowTable &tab, uint32_t s1, const vidType *list, int len, int lane) {
   uint32_t c = 0;
-  for (int base = 0; base < len; base += 128) {
-    int i = base + lane;
-    vidType x0 = (i < len) ? __ldg(list + i) : kVidMax;
-    vidType x1 = (i + 32 < len) ? __ldg(list + i + 32) : kVidMax;
-    vidType x2 = (i + 64 < len) ? __ldg(list + i + 64) : kVidMax;
-    vidType x3 = (i + 96 < len) ? __ldg(list + i + 96) : kVidMax;
-    c += tab.contains(uint32_t(x0));
-    if (base + 32 < len) c += tab.contains(uint32_t(x1));
-    if (base + 64 < len) c += tab.contains(uint32_t(x2));
-    if (base + 96 < len) c += tab.contains(uint32_t(x3));
+  const vidType *p = list + lane;
+  for (int r = len - lane; r > -lane; r -= 128, p += 128) {        // r - (-lane) = elements left in the row
+    uint32_t x0 = r > 0 ? uint32_t(__ldg(p)) : uint32_t(kVidMax);
+    uint32_t x1 = r > 32 ? uint32_t(__ldg(p + 32)) : uint32_t(kVidMax);
+    uint32_t x2 = r > 64 ? uint32_t(__ldg(p + 64)) : uint32_t(kVidMax);
+    uint32_t x3 = r > 96 ? uint32_t(__ldg(p + 96)) : uint32_t(kVidMax);
+    c += probe_pair(tab, s1, x0, x1);
+    if (r + lane > 64) c += probe_pair(tab, s1, x2, x3);           // warp-uniform
   }
   return c;
 }
@@ -97,6 +108,7 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
       }
       const vidType *P = REVERSE ? pcol + prow[it.root] + it.pbegin
                                  : g.d_colidx + g.d_rowptr[it.root] + it.pbegin;
+      const uint32_t s1 = fits ? tab.saddr1() : 0u;
       uint32_t c = 0;
       for (int pb = gwarp * 32; pb < it.pcount; pb += 32 * Cfg::kWarpsPerGroup) {
         int pi = pb + lane;
@@ -107,7 +119,7 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
           uint32_t off = __shfl_sync(kFullMask, pv.x, j);
           int len = int(__shfl_sync(kFullMask, pv.y, j));
           const vidType *list = g.d_acol + (size_t(off) << 2);
-          c += fits ? stream_probe(tab, list, len, lane) : stream_bsearch(rrow, d, list, len, lane);
+          c += fits ? stream_probe(tab, s1, list, len, lane) : stream_bsearch(rrow, d, list, len, lane);
         }
       }
       acc += c;
@@ -147,7 +159,7 @@ __global__ void k_tc_alg_bytes(vidType vb, vidType ve, const eidType *rowptr, co
 }
 
 template <int GT, int MAXB1, int CAP, bool REVERSE>
-static int launch_hash_class(gm_graph *g, int cls, const eidType *prow, const vidType *pcol, int *launches) {
+static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, const eidType *prow, const vidType *pcol, int *launches) {
   const ItemList &il = g->items[REVERSE ? 1 : 0][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
@@ -160,7 +172,7 @@ static int launch_hash_class(gm_graph *g, int cls, const eidType *prow, const vi
   int64_t per_cta = int64_t(Cfg::kGroupsPerCta) * (GT == 32 ? 4 : 1);
   int64_t want = (il.n + per_cta - 1) / per_cta;
   int grid = int(std::min<int64_t>(want, int64_t(occ) * g->num_sms));
-  kern<<<grid, Cfg::kCtaThreads, smem, g->stream>>>(g->view(0), prow, pcol, il.d_items, il.n, g->d_ticket + cls, g->d_counts);
+  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(g->view(0), prow, pcol, il.d_items, il.n, g->d_ticket + cls, g->d_counts);
   (*launches)++;
   return GM_OK;
 }
@@ -169,10 +181,13 @@ template <bool REVERSE>
 static int run_tc_hash(gm_graph *g, int *launches) {
   const eidType *prow = REVERSE ? g->d_rrowptr : g->d_rowptr;
   const vidType *pcol = REVERSE ? g->d_rcolidx : g->d_colidx;
-  GM_TRY((launch_hash_class<32, 7, 16, REVERSE>(g, 0, prow, pcol, launches)));
-  GM_TRY((launch_hash_class<256, 11, 64, REVERSE>(g, 1, prow, pcol, launches)));
-  GM_TRY((launch_hash_class<256, 13, 64, REVERSE>(g, 2, prow, pcol, launches)));
-  GM_TRY((launch_hash_class<1024, 15, 64, REVERSE>(g, 3, prow, pcol, launches)));
+  // the four size classes are independent: run them concurrently so their tails overlap
+  GM_TRY(fork_streams(g));
+  GM_TRY((launch_hash_class<256, 11, 64, REVERSE>(g, 1, g->stream, prow, pcol, launches)));
+  GM_TRY((launch_hash_class<256, 13, 64, REVERSE>(g, 2, g->side[0], prow, pcol, launches)));
+  GM_TRY((launch_hash_class<1024, 15, 64, REVERSE>(g, 3, g->side[1], prow, pcol, launches)));
+  GM_TRY((launch_hash_class<32, 7, 16, REVERSE>(g, 0, g->side[2], prow, pcol, launches)));
+  GM_TRY(join_streams(g));
   return GM_OK;
 }
 
@@ -193,7 +208,7 @@ int prepare_tc(gm_graph *g) {
   const std::string &algo = options().tc_algo;
   if (algo == "bs") return ensure_coo(g, 0);
   GM_TRY(ensure_aligned(g));
-  return ensure_items(g, algo == "hash_rev" ? 1 : 0);
+  return ensure_items(g, algo == "hash" ? 0 : 1);
 }
 
 }  // namespace gm
@@ -217,10 +232,10 @@ extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
       tc_warp_edge_bs<<<grid, 256, 0, g->stream>>>(g->view(0), g->d_counts);
       launches++;
     }
-  } else if (algo == "hash_rev") {
-    GM_TRY(run_tc_hash<true>(g, &launches));
-  } else {
+  } else if (algo == "hash") {
     GM_TRY(run_tc_hash<false>(g, &launches));
+  } else {                                   // auto = hash_rev: fewest probes (sum of d+(u)^2)
+    GM_TRY(run_tc_hash<true>(g, &launches));
   }
   return end_timed(g, launches, 1, total);
 }
