@@ -256,7 +256,7 @@ int ensure_items(gm_graph *g, int reverse) {
   for (int cls = 0; cls < 4; cls++) {
     // class 3 also absorbs the overflow class 4 (tables that do not fit shared memory: the kernel
     // falls back to searching the root row in global memory)
-    int chunk = chunk_opt > 0 ? chunk_opt : (cls == 0 ? 64 : cls == 1 ? 128 : 256);
+    int chunk = chunk_opt > 0 ? chunk_opt : (cls == 0 ? 64 : cls == 1 ? 512 : cls == 2 ? 1024 : 2048);
     GM_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t) * (size_t(n) + 1), g->stream));
     if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, g->d_rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off);
     int r = exclusive_scan_inplace(g, off, n);

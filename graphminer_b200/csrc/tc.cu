@@ -110,11 +110,16 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
                                  : g.d_colidx + g.d_rowptr[it.root] + it.pbegin;
       const uint32_t s1 = fits ? tab.saddr1() : 0u;
       uint32_t c = 0;
-      for (int pb = gwarp * 32; pb < it.pcount; pb += 32 * Cfg::kWarpsPerGroup) {
-        int pi = pb + lane;
+      // partners are dealt round-robin to the warps of the group (partner q goes to warp q % W), so
+      // every warp has work whenever the item has at least W partners; each warp fetches the row
+      // descriptors of its next 32 partners with one lane-parallel load
+      constexpr int W = Cfg::kWarpsPerGroup;
+      const int mine = (it.pcount - gwarp + W - 1) / W;          // partners owned by this warp
+      for (int pb = 0; pb < mine; pb += 32) {
+        int q = pb + lane;
         uint2 pv = make_uint2(0, 0);
-        if (pi < it.pcount) pv = g.info(__ldg(P + pi));
-        int np = min(32, it.pcount - pb);
+        if (q < mine) pv = g.info(__ldg(P + q * W + gwarp));
+        int np = min(32, mine - pb);
         for (int j = 0; j < np; j++) {
           uint32_t off = __shfl_sync(kFullMask, pv.x, j);
           int len = int(__shfl_sync(kFullMask, pv.y, j));
