@@ -83,14 +83,15 @@ struct gm_graph {
   gm::vidType *d_rcolidx = nullptr;
 
   // vertex-centric work items, by class (0: warp-sized tables, 1: CTA small, 2: CTA large, 3: fallback)
-  gm::ItemList items[2][4];
-  bool items_ready[2] = {false, false};   // [0] forward partners, [1] reverse partners
+  gm::ItemList items[3][4];
+  bool items_ready[3] = {false, false, false};   // [0] forward partners, [1] reverse partners, [2] forward whole-root
 
   // scratch + results
   unsigned long long *d_counts = nullptr;     // 8 accumulators
   unsigned long long *h_counts = nullptr;     // pinned
   int *d_ticket = nullptr;                    // dynamic work counters (8)
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
+  uint32_t *d_gmat = nullptr; size_t gmat_bytes = 0;   // global bit-matrix slabs of the k-clique kernel
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // size classes of one pass run concurrently
   cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
@@ -115,7 +116,7 @@ namespace gm {
 int ensure_aligned(gm_graph *g);
 int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
-int ensure_items(gm_graph *g, int reverse);
+int ensure_items(gm_graph *g, int mode);
 int ensure_scratch(gm_graph *g, size_t bytes);
 int begin_timed(gm_graph *g);
 int fork_streams(gm_graph *g);

@@ -243,14 +243,17 @@ int ensure_reverse(gm_graph *g) {
 // Vertex-centric work items.  reverse=0: root r probes with its own row as the table and its
 // out-neighbours as partners (roots limited to the source range).  reverse=1: partners are the
 // in-neighbours (already limited to the source range by ensure_reverse), roots are all vertices.
-int ensure_items(gm_graph *g, int reverse) {
-  if (g->items_ready[reverse]) return GM_OK;
+// mode 2: forward, ONE item per root (the whole partner row), roots with degree >= 3 -- for the
+// kernels that build a per-root structure which cannot be split (k-clique bitmap).
+int ensure_items(gm_graph *g, int mode) {
+  if (g->items_ready[mode]) return GM_OK;
   GM_CUDA(cudaSetDevice(g->device));
+  const int reverse = mode == 1;
   if (reverse) GM_TRY(ensure_reverse(g));
   const eidType *prow = reverse ? g->d_rrowptr : g->d_rowptr;
   vidType vb = reverse ? 0 : g->src_begin, ve = reverse ? g->nv : g->src_end, n = ve - vb;
-  vidType min_deg = reverse ? 1 : 2;
-  int chunk_opt = options().chunk;
+  vidType min_deg = mode == 2 ? 3 : reverse ? 1 : 2;
+  int chunk_opt = mode == 2 ? 0x7fffffff : options().chunk;
   int64_t *off = nullptr;
   GM_CUDA(cudaMalloc(&off, sizeof(int64_t) * (size_t(n) + 1)));
   for (int cls = 0; cls < 4; cls++) {
@@ -264,7 +267,7 @@ int ensure_items(gm_graph *g, int reverse) {
     int64_t total = 0;
     GM_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    ItemList &il = g->items[reverse][cls];
+    ItemList &il = g->items[mode][cls];
     il.n = total;
     GM_CUDA(cudaMalloc(&il.d_items, sizeof(WorkItem) * size_t(total > 0 ? total : 1)));
     if (n > 0 && total > 0) k_fill_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, prow, chunk, off, il.d_items);
@@ -272,7 +275,7 @@ int ensure_items(gm_graph *g, int reverse) {
   }
   GM_CUDA(cudaFree(off));
   GM_CUDA(cudaGetLastError());
-  g->items_ready[reverse] = true;
+  g->items_ready[mode] = true;
   return GM_OK;
 }
 
@@ -316,6 +319,8 @@ static void free_aux(gm_graph *g) {
     cudaFree(g->d_src[s]); g->d_src[s] = nullptr;
     if (s == 1) cudaFree(g->d_dst[s]);
     g->d_dst[s] = nullptr; g->coo_ready[s] = false; g->nnz[s] = 0;
+  }
+  for (int s = 0; s < 3; s++) {
     for (int c = 0; c < 4; c++) { cudaFree(g->items[s][c].d_items); g->items[s][c] = ItemList(); }
     g->items_ready[s] = false;
   }
@@ -429,7 +434,7 @@ int gm_graph_free(gm_graph_t *g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   free_aux(g);
   if (g->own_csr) { cudaFree(g->d_rowptr); cudaFree(g->d_colidx); }
-  cudaFree(g->d_counts); cudaFree(g->d_ticket); cudaFree(g->d_scratch);
+  cudaFree(g->d_counts); cudaFree(g->d_ticket); cudaFree(g->d_scratch); cudaFree(g->d_gmat);
   if (g->h_counts) cudaFreeHost(g->h_counts);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);

@@ -49,7 +49,7 @@ __device__ __forceinline__ void flush(AccType v, AccType *dst) {
 
 // ---- k-clique on the DAG ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-kclique_warp_edge(GraphGPU g, int k, vidType *scratch, int64_t max_deg, unsigned long long *ticket, AccType *total) {
+kclique_warp_edge(GraphGPU g, int k, vidType min_src_deg, vidType *scratch, int64_t max_deg, unsigned long long *ticket, AccType *total) {
   vidType *buf = warp_scratch(scratch, max_deg * (k > 3 ? k - 3 : 1));
   TaskFeed feed; feed.init(ticket, g.num_tasks);
   AccType cnt = 0;
@@ -57,6 +57,7 @@ kclique_warp_edge(GraphGPU g, int k, vidType *scratch, int64_t max_deg, unsigned
   const int last = k - 3;                      // level whose members are only counted against
   for (eidType e = feed.next(); e >= 0; e = feed.next()) {
     vidType v0 = g.get_src(e), v1 = g.get_dst(e);
+    if (g.get_degree(v0) <= min_src_deg) continue;       // roots handled by the bitmap kernel
     if (k == 3) { cnt += intersect_num(g.N(v0), g.get_degree(v0), g.N(v1), g.get_degree(v1)); continue; }
     n[1] = intersect(g.N(v0), g.get_degree(v0), g.N(v1), g.get_degree(v1), buf);
     S[1] = buf; idx[1] = 0;
@@ -278,15 +279,20 @@ static int pattern_grid(gm_graph *g, const void *kernel, int64_t ntasks, int64_t
 
 static unsigned long long *ticket64(gm_graph *g) { return reinterpret_cast<unsigned long long *>(g->d_ticket); }
 
-int run_kclique_list(gm_graph *g, int k, int *launches) {
+// tasks whose source has out-degree <= min_src_degree are skipped (-1: none skipped)
+int run_kclique_list_filtered(gm_graph *g, int k, vidType min_src_degree, int *launches, cudaStream_t stream) {
   GM_TRY(ensure_coo(g, 0));
   if (g->nnz[0] == 0) return GM_OK;
   int grid; vidType *scratch;
   int64_t md = std::max<int64_t>(g->max_degree, 1);
   GM_TRY(pattern_grid(g, (const void *)kclique_warp_edge, g->nnz[0], k > 3 ? md * (k - 3) : 0, &grid, &scratch));
-  kclique_warp_edge<<<grid, 256, 0, g->stream>>>(g->view(0), k, scratch, md, ticket64(g), g->d_counts);
+  kclique_warp_edge<<<grid, 256, 0, stream>>>(g->view(0), k, min_src_degree, scratch, md, ticket64(g), g->d_counts);
   (*launches)++;
   return GM_OK;
+}
+
+int run_kclique_list(gm_graph *g, int k, int *launches) {
+  return run_kclique_list_filtered(g, k, -1, launches, g->stream);
 }
 
 int run_sgl(gm_graph *g, int pattern, int *launches) {
