@@ -271,7 +271,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src, "kernel": "tc_hash_kernel (all size classes of one pass)",
+                         "peak_source": peak_src, "kernel": ("kclique_bitmap_kernel" if clique else "tc_hash_kernel<MODE=2 ranked>") + " (all size classes of one pass, run concurrently)",
                          "alg_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_total_ms / args.steps},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),

@@ -83,8 +83,16 @@ struct gm_graph {
   gm::vidType *d_rcolidx = nullptr;
 
   // vertex-centric work items, by class (0: warp-sized tables, 1: CTA small, 2: CTA large, 3: fallback)
-  gm::ItemList items[3][4];
-  bool items_ready[3] = {false, false, false};   // [0] forward partners, [1] reverse partners, [2] forward whole-root
+  gm::ItemList items[4][4];
+  bool items_ready[4] = {false, false, false, false};   // [0] forward, [1] reverse, [2] forward whole-root, [3] ranked
+
+  // rank-relabelled DAG (rank.cu): new id = position in the (total degree, id) order, so every edge
+  // goes from a lower to a higher id and rows are sorted by new id
+  bool rk_ready = false, rk_valid = false;
+  uint2 *rk_vinfo = nullptr; gm::vidType *rk_acol = nullptr;
+  gm::eidType *rk_nrow = nullptr;      // compact rowptr of the relabelled graph (nv+1)
+  gm::eidType *rk_prow = nullptr;      // per new root: offsets into rk_prec (nv+1)
+  uint2 *rk_prec = nullptr;            // partner records {element offset of the suffix, length}
 
   // scratch + results
   unsigned long long *d_counts = nullptr;     // 8 accumulators
@@ -117,6 +125,7 @@ int ensure_aligned(gm_graph *g);
 int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
+int ensure_ranked(gm_graph *g);
 int ensure_scratch(gm_graph *g, size_t bytes);
 int begin_timed(gm_graph *g);
 int fork_streams(gm_graph *g);

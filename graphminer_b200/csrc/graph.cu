@@ -250,9 +250,13 @@ int ensure_items(gm_graph *g, int mode) {
   GM_CUDA(cudaSetDevice(g->device));
   const int reverse = mode == 1;
   if (reverse) GM_TRY(ensure_reverse(g));
-  const eidType *prow = reverse ? g->d_rrowptr : g->d_rowptr;
-  vidType vb = reverse ? 0 : g->src_begin, ve = reverse ? g->nv : g->src_end, n = ve - vb;
-  vidType min_deg = mode == 2 ? 3 : reverse ? 1 : 2;
+  if (mode == 3) GM_TRY(ensure_ranked(g));
+  // mode 3 (ranked): roots are NEW ids; degrees come from the relabelled compact rowptr
+  const eidType *rowptr = mode == 3 ? g->rk_nrow : g->d_rowptr;
+  const eidType *prow = reverse ? g->d_rrowptr : mode == 3 ? g->rk_prow : g->d_rowptr;
+  const bool all_roots = reverse || mode == 3;
+  vidType vb = all_roots ? 0 : g->src_begin, ve = all_roots ? g->nv : g->src_end, n = ve - vb;
+  vidType min_deg = mode == 2 ? 3 : all_roots ? 1 : 2;
   int chunk_opt = mode == 2 ? 0x7fffffff : options().chunk;
   int64_t *off = nullptr;
   GM_CUDA(cudaMalloc(&off, sizeof(int64_t) * (size_t(n) + 1)));
@@ -261,7 +265,7 @@ int ensure_items(gm_graph *g, int mode) {
     // falls back to searching the root row in global memory)
     int chunk = chunk_opt > 0 ? chunk_opt : (cls == 0 ? 64 : cls == 1 ? 512 : cls == 2 ? 1024 : 2048);
     GM_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t) * (size_t(n) + 1), g->stream));
-    if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, g->d_rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off);
+    if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off);
     int r = exclusive_scan_inplace(g, off, n);
     if (r != GM_OK) { cudaFree(off); return r; }
     int64_t total = 0;
@@ -320,10 +324,13 @@ static void free_aux(gm_graph *g) {
     if (s == 1) cudaFree(g->d_dst[s]);
     g->d_dst[s] = nullptr; g->coo_ready[s] = false; g->nnz[s] = 0;
   }
-  for (int s = 0; s < 3; s++) {
+  for (int s = 0; s < 4; s++) {
     for (int c = 0; c < 4; c++) { cudaFree(g->items[s][c].d_items); g->items[s][c] = ItemList(); }
     g->items_ready[s] = false;
   }
+  cudaFree(g->rk_vinfo); cudaFree(g->rk_acol); cudaFree(g->rk_nrow); cudaFree(g->rk_prow); cudaFree(g->rk_prec);
+  g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
+  g->rk_ready = g->rk_valid = false;
   cudaFree(g->d_rrowptr); cudaFree(g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
 }
 
@@ -381,7 +388,7 @@ int gm_set_option(const char *key, const char *value) {
   if (!key || !value) { set_error("null option"); return GM_EINVAL; }
   std::string k(key), v(value);
   if (k == "tc.algo") {
-    if (v != "auto" && v != "hash" && v != "hash_rev" && v != "bs" && v != "merge") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
+    if (v != "auto" && v != "rank" && v != "hash" && v != "hash_rev" && v != "bs") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_algo = v;
   } else if (k == "clique.algo") {
     if (v != "auto" && v != "bitmap" && v != "list") { set_error("clique.algo: unknown value '%s'", value); return GM_EINVAL; }

@@ -64,9 +64,14 @@ __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, c
   return c;
 }
 
-template <int GT, int MAXB1, int CAP, bool REVERSE>
+// MODE 0: partners = out-neighbours of the root (rows read through g's aligned view)
+// MODE 1: partners = in-neighbours (prow/pcol = reverse adjacency)
+// MODE 2: RANKED graph (rank.cu): g's aligned view holds the rank-relabelled rows, partners are
+//         records {element offset of the row suffix to stream, its length} in prec
+template <int GT, int MAXB1, int CAP, int MODE>
 __global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads)
 tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
+               const uint2 *__restrict__ prec,
                const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
   using Cfg = GroupCfg<GT>;
   extern __shared__ uint32_t smem[];
@@ -106,8 +111,9 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
         tab.build(rrow, d, gtid, GT, [] { group_sync<GT>(); });
         if (tab.overflowed()) fits = false;          // group-uniform
       }
-      const vidType *P = REVERSE ? pcol + prow[it.root] + it.pbegin
-                                 : g.d_colidx + g.d_rowptr[it.root] + it.pbegin;
+      const vidType *P = MODE == 1 ? pcol + prow[it.root] + it.pbegin
+                                   : MODE == 0 ? g.d_colidx + g.d_rowptr[it.root] + it.pbegin : nullptr;
+      const uint2 *R = MODE == 2 ? prec + prow[it.root] + it.pbegin : nullptr;
       const uint32_t s1 = fits ? tab.saddr1() : 0u;
       uint32_t c = 0;
       // partners are dealt round-robin to the warps of the group (partner q goes to warp q % W), so
@@ -118,12 +124,12 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
       for (int pb = 0; pb < mine; pb += 32) {
         int q = pb + lane;
         uint2 pv = make_uint2(0, 0);
-        if (q < mine) pv = g.info(__ldg(P + q * W + gwarp));
+        if (q < mine) pv = MODE == 2 ? __ldg(R + q * W + gwarp) : g.info(__ldg(P + q * W + gwarp));
         int np = min(32, mine - pb);
         for (int j = 0; j < np; j++) {
           uint32_t off = __shfl_sync(kFullMask, pv.x, j);
           int len = int(__shfl_sync(kFullMask, pv.y, j));
-          const vidType *list = g.d_acol + (size_t(off) << 2);
+          const vidType *list = g.d_acol + (MODE == 2 ? size_t(off) : (size_t(off) << 2));
           c += fits ? stream_probe(tab, s1, list, len, lane) : stream_bsearch(rrow, d, list, len, lane);
         }
       }
@@ -163,12 +169,12 @@ __global__ void k_tc_alg_bytes(vidType vb, vidType ve, const eidType *rowptr, co
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
-template <int GT, int MAXB1, int CAP, bool REVERSE>
-static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, const eidType *prow, const vidType *pcol, int *launches) {
-  const ItemList &il = g->items[REVERSE ? 1 : 0][cls];
+template <int GT, int MAXB1, int CAP, int MODE>
+static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *launches) {
+  const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
-  auto kern = tc_hash_kernel<GT, MAXB1, CAP, REVERSE>;
+  auto kern = tc_hash_kernel<GT, MAXB1, CAP, MODE>;
   size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
   GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int occ = 0;
@@ -177,21 +183,23 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, const ei
   int64_t per_cta = int64_t(Cfg::kGroupsPerCta) * (GT == 32 ? 4 : 1);
   int64_t want = (il.n + per_cta - 1) / per_cta;
   int grid = int(std::min<int64_t>(want, int64_t(occ) * g->num_sms));
-  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(g->view(0), prow, pcol, il.d_items, il.n, g->d_ticket + cls, g->d_counts);
+  GraphGPU view = g->view(0);
+  const eidType *prow = g->d_rowptr; const vidType *pcol = g->d_colidx; const uint2 *prec = nullptr;
+  if (MODE == 1) { prow = g->d_rrowptr; pcol = g->d_rcolidx; }
+  if (MODE == 2) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; prow = g->rk_prow; pcol = nullptr; prec = g->rk_prec; }
+  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(view, prow, pcol, prec, il.d_items, il.n, g->d_ticket + cls, g->d_counts);
   (*launches)++;
   return GM_OK;
 }
 
-template <bool REVERSE>
+template <int MODE>
 static int run_tc_hash(gm_graph *g, int *launches) {
-  const eidType *prow = REVERSE ? g->d_rrowptr : g->d_rowptr;
-  const vidType *pcol = REVERSE ? g->d_rcolidx : g->d_colidx;
   // the four size classes are independent: run them concurrently so their tails overlap
   GM_TRY(fork_streams(g));
-  GM_TRY((launch_hash_class<256, 11, 64, REVERSE>(g, 1, g->stream, prow, pcol, launches)));
-  GM_TRY((launch_hash_class<256, 13, 64, REVERSE>(g, 2, g->side[0], prow, pcol, launches)));
-  GM_TRY((launch_hash_class<1024, 15, 64, REVERSE>(g, 3, g->side[1], prow, pcol, launches)));
-  GM_TRY((launch_hash_class<32, 7, 16, REVERSE>(g, 0, g->side[2], prow, pcol, launches)));
+  GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 1, g->stream, launches)));
+  GM_TRY((launch_hash_class<256, 13, 64, MODE>(g, 2, g->side[0], launches)));
+  GM_TRY((launch_hash_class<1024, 15, 64, MODE>(g, 3, g->side[1], launches)));
+  GM_TRY((launch_hash_class<32, 7, 16, MODE>(g, 0, g->side[2], launches)));
   GM_TRY(join_streams(g));
   return GM_OK;
 }
@@ -209,9 +217,23 @@ static int tc_alg_bytes(gm_graph *g, uint64_t *out) {
   return GM_OK;
 }
 
+// Which kernel family gm_tc runs: "bs" | "hash" | "hash_rev" | "rank".  auto = rank when the input is
+// the (degree,id) orientation (verified on device, rank.cu), else hash_rev.
+static int resolve_tc_algo(gm_graph *g, std::string *out) {
+  std::string algo = options().tc_algo;
+  if (algo == "auto" || algo == "rank") {
+    GM_TRY(ensure_ranked(g));
+    algo = g->rk_valid ? "rank" : "hash_rev";
+  }
+  *out = algo;
+  return GM_OK;
+}
+
 int prepare_tc(gm_graph *g) {
-  const std::string &algo = options().tc_algo;
+  std::string algo;
+  GM_TRY(resolve_tc_algo(g, &algo));
   if (algo == "bs") return ensure_coo(g, 0);
+  if (algo == "rank") return ensure_items(g, 3);
   GM_TRY(ensure_aligned(g));
   return ensure_items(g, algo == "hash" ? 0 : 1);
 }
@@ -225,7 +247,8 @@ extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
   GM_TRY(prepare_tc(g));
   if (g->tc_bytes_cache == 0) GM_TRY(tc_alg_bytes(g, &g->tc_bytes_cache));
   g->last_alg_bytes = g->tc_bytes_cache;
-  const std::string &algo = options().tc_algo;
+  std::string algo;
+  GM_TRY(resolve_tc_algo(g, &algo));
   int launches = 0;
   GM_TRY(begin_timed(g));
   if (algo == "bs") {
@@ -238,9 +261,11 @@ extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
       launches++;
     }
   } else if (algo == "hash") {
-    GM_TRY(run_tc_hash<false>(g, &launches));
-  } else {                                   // auto = hash_rev: fewest probes (sum of d+(u)^2)
-    GM_TRY(run_tc_hash<true>(g, &launches));
+    GM_TRY(run_tc_hash<0>(g, &launches));
+  } else if (algo == "hash_rev") {
+    GM_TRY(run_tc_hash<1>(g, &launches));
+  } else {
+    GM_TRY(run_tc_hash<2>(g, &launches));
   }
   return end_timed(g, launches, 1, total);
 }

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(__file__)
 KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
 GOLD = json.load(open(os.path.join(HERE, "golden", "rmat_counts.json")))
-TC_ALGOS = ["hash", "hash_rev", "bs"]
+TC_ALGOS = ["auto", "rank", "hash", "hash_rev", "bs"]
 
 
 @pytest.fixture(autouse=True)
@@ -77,7 +77,7 @@ def test_tc_chunking_is_invisible(chunk):
     rp, ci = _graph("rmat12")
     orp, oci, md = _dag(rp, ci)
     capi.set_option("sched.chunk", chunk)
-    for algo in ("hash", "hash_rev"):
+    for algo in ("rank", "hash", "hash_rev"):
         capi.set_option("tc.algo", algo)
         with capi.DeviceGraph(orp, oci, md) as g:
             assert g.tc() == GOLD["rmat12"]["tc"]

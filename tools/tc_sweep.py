@@ -15,7 +15,7 @@ for scale in scales:
     torch.cuda.synchronize()
     ne = ci.numel(); md = int((rp[1:] - rp[:-1]).max())
     res = {}
-    for algo in os.environ.get("GM_SWEEP_ALGOS", "hash,hash_rev,bs").split(","):
+    for algo in os.environ.get("GM_SWEEP_ALGOS", "rank,hash_rev,bs").split(","):
         for chunk in chunks:
             capi.set_option("tc.algo", algo); capi.set_option("sched.chunk", chunk)
             g = capi.DeviceGraph.adopt(rp, ci, md)
