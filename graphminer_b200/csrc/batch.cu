@@ -76,9 +76,13 @@ extern "C" int gm_intersect_batch(const int32_t *d_pool, const int64_t *d_a_off,
   BatchArgs a{d_pool, d_a_off, d_a_len, d_b_off ? d_b_off : d_a_off, d_b_len ? d_b_len : d_a_len,
               d_bound, d_anc, d_anc2, npairs,
               reinterpret_cast<unsigned long long *>(d_out), d_out_pool, d_out_off};
-  cudaDeviceProp prop;
-  GM_CUDA(cudaGetDeviceProperties(&prop, device));
-  int sms = prop.multiProcessorCount;
+  // cudaGetDeviceProperties costs milliseconds per call; the attribute query does not
+  static int sms_cache[64] = {0};
+  int sms = sms_cache[device & 63];
+  if (sms == 0) {
+    GM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    sms_cache[device & 63] = sms;
+  }
 
   if (algo == GM_ALGO_MERGE || algo == GM_ALGO_HASH || algo == GM_ALGO_GALLOP) {
     if (op != GM_OP_INTERSECT_NUM) { set_error("gm_intersect_batch: algo %d implements GM_OP_INTERSECT_NUM only", algo); return GM_EUNSUPPORTED; }

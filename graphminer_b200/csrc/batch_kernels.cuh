@@ -44,10 +44,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- MERGE ------------------------------------------------------------------------------------
-constexpr int kMergeWarps = 4;                    // warps per CTA
-constexpr int kMergeStageElems = 1792;            // int32 per stage (7 KB); 2 stages per warp
-constexpr int kMergeSmemBytes = kMergeWarps * 2 * kMergeStageElems * 4 + kMergeWarps * 2 * 8;
-
+// Two size classes share one kernel template: <1792 elements/stage, 4 warps> for ordinary pairs and
+// <4608, 3> for long ones; each instance skips the pairs of the other class.  Pairs longer than the
+// long class are intersected straight from global memory by the operator API.
 struct PairDesc {   // where a pair sits once staged
   int na, nb, head_a, head_b, units_a, units_b;   // head: elements before the list in its first 16-byte unit
 };
@@ -83,57 +82,71 @@ __device__ __forceinline__ uint32_t merge_path_count(const vidType *A, int na, c
   return c;
 }
 
-__global__ void __launch_bounds__(kMergeWarps * 32)
+template <int STAGE, int WARPS>
+struct MergeCfg {
+  static constexpr int kSmemBytes = WARPS * 2 * STAGE * 4 + WARPS * 2 * 8;
+};
+
+// lo_elems < staged size <= STAGE: staged here; size > STAGE && TAKE_OVERSIZE: global fallback here.
+template <int STAGE, int WARPS, bool TAKE_OVERSIZE>
+__global__ void __launch_bounds__(WARPS * 32)
 batch_merge_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
                    const int64_t *__restrict__ b_off, const int32_t *__restrict__ b_len, int64_t npairs,
-                   unsigned long long *__restrict__ out) {
+                   int lo_elems, unsigned long long *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  vidType *stage0 = reinterpret_cast<vidType *>(smem_raw) + size_t(w) * 2 * kMergeStageElems;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + size_t(kMergeWarps) * 2 * kMergeStageElems * 4) + w * 2;
+  vidType *stage0 = reinterpret_cast<vidType *>(smem_raw) + size_t(w) * 2 * STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + size_t(WARPS) * 2 * STAGE * 4) + w * 2;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
   __syncwarp();
 
-  const int64_t gw = int64_t(blockIdx.x) * kMergeWarps + w;
-  const int64_t nw = int64_t(gridDim.x) * kMergeWarps;
-
-  // issue the copies of pair p into stage s (lane 0 only).  Returns false if the pair does not fit
-  // (then nothing was issued and the pair is intersected straight from global memory).
-  auto issue = [&](int64_t p, int s, PairDesc &d) -> bool {
-    int64_t ao = a_off[p], bo = b_off[p];
-    d = describe_pair(ao, a_len[p], bo, b_len[p]);
-    if ((d.units_a + d.units_b) * 4 > kMergeStageElems) return false;
-    if (d.units_a + d.units_b == 0) return true;
-    if (lane == 0) {
-      vidType *dst = stage0 + s * kMergeStageElems;
-      mbar_expect_tx(&bars[s], uint32_t(d.units_a + d.units_b) * 16u);
-      if (d.units_a) tma_bulk_g2s(dst, pool + (ao - d.head_a), uint32_t(d.units_a) * 16u, &bars[s]);
-      if (d.units_b) tma_bulk_g2s(dst + d.units_a * 4, pool + (bo - d.head_b), uint32_t(d.units_b) * 16u, &bars[s]);
+  const int64_t nw = int64_t(gridDim.x) * WARPS;
+  enum { SKIP = 0, STAGED = 1, GLOBAL = 2 };
+  // first pair at or after p (stride nw) that belongs to this instance; fills d / kind
+  auto next_mine = [&](int64_t p, PairDesc &d, int &kind) -> int64_t {
+    for (; p < npairs; p += nw) {
+      d = describe_pair(a_off[p], a_len[p], b_off[p], b_len[p]);
+      int elems = (d.units_a + d.units_b) * 4;
+      kind = elems > STAGE ? (TAKE_OVERSIZE ? GLOBAL : SKIP) : (elems > lo_elems ? STAGED : SKIP);
+      if (kind != SKIP) return p;
     }
-    return true;
+    return npairs;
+  };
+  auto issue = [&](int64_t p, int s, const PairDesc &d) {
+    if (lane == 0 && d.units_a + d.units_b > 0) {
+      vidType *dst = stage0 + s * STAGE;
+      mbar_expect_tx(&bars[s], uint32_t(d.units_a + d.units_b) * 16u);
+      if (d.units_a) tma_bulk_g2s(dst, pool + (a_off[p] - d.head_a), uint32_t(d.units_a) * 16u, &bars[s]);
+      if (d.units_b) tma_bulk_g2s(dst + d.units_a * 4, pool + (b_off[p] - d.head_b), uint32_t(d.units_b) * 16u, &bars[s]);
+    }
   };
 
   uint32_t phase[2] = {0, 0};
   PairDesc cur, nxt;
-  bool cur_staged = false, nxt_staged = false;
-  int s = 0;
-  if (gw < npairs) cur_staged = issue(gw, 0, cur);
-  for (int64_t p = gw; p < npairs; p += nw) {
-    const int64_t pn = p + nw;
-    if (pn < npairs) nxt_staged = issue(pn, s ^ 1, nxt);        // prefetch the next pair
+  int ckind = SKIP, nkind = SKIP, s = 0;
+  int64_t p = next_mine(int64_t(blockIdx.x) * WARPS + w, cur, ckind);
+  if (p < npairs && ckind == STAGED) issue(p, 0, cur);
+  while (p < npairs) {
+    const int64_t pn = next_mine(p + nw, nxt, nkind);
+    if (pn < npairs && nkind == STAGED) issue(pn, s ^ 1, nxt);      // prefetch the next pair
     uint32_t c;
-    if (cur_staged) {
+    if (ckind == STAGED) {
       if (cur.units_a + cur.units_b) { mbar_wait(&bars[s], phase[s]); phase[s] ^= 1; }
-      const vidType *A = stage0 + s * kMergeStageElems + cur.head_a;
-      const vidType *B = stage0 + s * kMergeStageElems + cur.units_a * 4 + cur.head_b;
+      const vidType *A = stage0 + s * STAGE + cur.head_a;
+      const vidType *B = stage0 + s * STAGE + cur.units_a * 4 + cur.head_b;
       c = (cur.na && cur.nb) ? merge_path_count(A, cur.na, B, cur.nb, lane) : 0;
+      __syncwarp();                                                // stage s is free for re-use
+      s ^= 1;
     } else {
       c = intersect_num(pool + a_off[p], vidType(cur.na), pool + b_off[p], vidType(cur.nb));
+      if (nkind == STAGED && pn < npairs) {
+        // the prefetch above went to stage s^1 while this pair used no stage: keep stages in step
+        s ^= 1;
+      }
     }
     c = warp_reduce(c);
     if (lane == 0) out[p] = c;
-    __syncwarp();                                                // stage s is free for re-use
-    cur = nxt; cur_staged = nxt_staged; s ^= 1;
+    p = pn; cur = nxt; ckind = nkind;
   }
 }
 
@@ -224,11 +237,24 @@ static int launch_batch_variant(int algo, const vidType *pool, const int64_t *a_
                                 unsigned long long *out, int sms, cudaStream_t s) {
   if (algo == GM_ALGO_MERGE) {
     if (reinterpret_cast<uintptr_t>(pool) & 15) { set_error("GM_ALGO_MERGE needs a 16-byte aligned pool (TMA bulk copy)"); return GM_EINVAL; }
-    GM_CUDA(cudaFuncSetAttribute(batch_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeSmemBytes));
-    int occ = 0;
-    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, batch_merge_kernel, kMergeWarps * 32, kMergeSmemBytes));
-    int grid = int(std::min<int64_t>((npairs + kMergeWarps - 1) / kMergeWarps, int64_t(std::max(occ, 1)) * sms));
-    batch_merge_kernel<<<grid, kMergeWarps * 32, kMergeSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, npairs, out);
+    {
+      constexpr int ST = 1792, WP = 4;
+      auto k = batch_merge_kernel<ST, WP, false>;
+      GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, MergeCfg<ST, WP>::kSmemBytes));
+      int occ = 0;
+      GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, WP * 32, MergeCfg<ST, WP>::kSmemBytes));
+      int grid = int(std::min<int64_t>((npairs + WP - 1) / WP, int64_t(std::max(occ, 1)) * sms));
+      k<<<grid, WP * 32, MergeCfg<ST, WP>::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, npairs, -1, out);
+    }
+    {
+      constexpr int ST = 4608, WP = 3;
+      auto k = batch_merge_kernel<ST, WP, true>;
+      GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, MergeCfg<ST, WP>::kSmemBytes));
+      int occ = 0;
+      GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, WP * 32, MergeCfg<ST, WP>::kSmemBytes));
+      int grid = int(std::min<int64_t>((npairs + WP - 1) / WP, int64_t(std::max(occ, 1)) * sms));
+      k<<<grid, WP * 32, MergeCfg<ST, WP>::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, npairs, 1792, out);
+    }
   } else if (algo == GM_ALGO_GALLOP) {
     int grid = int(std::min<int64_t>((npairs + 7) / 8, int64_t(sms) * 8));
     batch_gallop_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, npairs, out);

@@ -207,9 +207,9 @@ static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream,
     size_t need = size_t(grid) * Cfg::kGlobalMatWords * 4;
     if (need > g->gmat_bytes) {
       GM_CUDA(cudaStreamSynchronize(g->stream));
-      if (g->d_gmat) GM_CUDA(cudaFree(g->d_gmat));
+      if (g->d_gmat) GM_CUDA(dfree(g, g->d_gmat));
       g->d_gmat = nullptr; g->gmat_bytes = 0;
-      if (cudaMalloc(&g->d_gmat, need) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu B bit-matrix slabs)", need); return GM_ENOMEM; }
+      if (dmalloc(g, &g->d_gmat, need) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu B bit-matrix slabs)", need); return GM_ENOMEM; }
       g->gmat_bytes = need;
     }
     gmat = g->d_gmat;

@@ -107,6 +107,7 @@ struct gm_graph {
   int last_launches = 0;
   uint64_t last_alg_bytes = 0;
   uint64_t tc_bytes_cache = 0;
+  int last_alg_kind = 0;                  // 1: TC formula (computed lazily)
   int num_sms = gm::kNumSMsB200;
   int smem_optin = 0;
 
@@ -121,11 +122,18 @@ struct gm_graph {
 };
 
 namespace gm {
+// stream-ordered allocation on the graph's stream (cudaMallocAsync pool, see device_info())
+template <typename T>
+inline cudaError_t dmalloc(gm_graph *g, T **p, size_t bytes) {
+  return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 4, g->stream);
+}
+inline cudaError_t dfree(gm_graph *g, void *p) { return p ? cudaFreeAsync(p, g->stream) : cudaSuccess; }
 int ensure_aligned(gm_graph *g);
 int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
+int tc_alg_bytes(gm_graph *g, uint64_t *out);
 int ensure_scratch(gm_graph *g, size_t bytes);
 int begin_timed(gm_graph *g);
 int fork_streams(gm_graph *g);

@@ -145,9 +145,9 @@ static int exclusive_scan_inplace(gm_graph *g, T *d_data, int64_t n) {   // d_da
 
 int ensure_scratch(gm_graph *g, size_t bytes) {
   if (bytes <= g->scratch_bytes) return GM_OK;
-  if (g->d_scratch) { GM_CUDA(cudaStreamSynchronize(g->stream)); GM_CUDA(cudaFree(g->d_scratch)); g->d_scratch = nullptr; }
+  if (g->d_scratch) { GM_CUDA(cudaStreamSynchronize(g->stream)); GM_CUDA(dfree(g, g->d_scratch)); g->d_scratch = nullptr; }
   size_t want = bytes + (bytes >> 2) + 256;
-  if (cudaMalloc(&g->d_scratch, want) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu B scratch)", want); return GM_ENOMEM; }
+  if (dmalloc(g, &g->d_scratch, want) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu B scratch)", want); return GM_ENOMEM; }
   g->scratch_bytes = want;
   return GM_OK;
 }
@@ -159,24 +159,24 @@ int ensure_aligned(gm_graph *g) {
   GM_CUDA(cudaSetDevice(g->device));
   vidType nv = g->nv;
   uint32_t *units = nullptr;
-  GM_CUDA(cudaMalloc(&units, sizeof(uint32_t) * (size_t(nv) + 1)));
+  GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * (size_t(nv) + 1)));
   GM_CUDA(cudaMemsetAsync(units, 0, sizeof(uint32_t) * (size_t(nv) + 1), g->stream));
   if (nv > 0) k_degree<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, units, nullptr);
   int r = exclusive_scan_inplace(g, units, nv);
-  if (r != GM_OK) { cudaFree(units); return r; }
+  if (r != GM_OK) { dfree(g, units); return r; }
   uint32_t total_units = 0;
   GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  if ((uint64_t(g->ne) + 3ull * uint64_t(nv)) / 4 >= (1ull << 32)) { cudaFree(units); set_error("graph too large for 32-bit aligned offsets"); return GM_EUNSUPPORTED; }
+  if ((uint64_t(g->ne) + 3ull * uint64_t(nv)) / 4 >= (1ull << 32)) { dfree(g, units); set_error("graph too large for 32-bit aligned offsets"); return GM_EUNSUPPORTED; }
   g->acol_len = int64_t(total_units) * 4;
-  GM_CUDA(cudaMalloc(&g->d_vinfo, sizeof(uint2) * size_t(nv > 0 ? nv : 1)));
-  GM_CUDA(cudaMalloc(&g->d_acol, sizeof(vidType) * size_t(g->acol_len > 0 ? g->acol_len : 4)));
+  GM_CUDA(dmalloc(g, &g->d_vinfo, sizeof(uint2) * size_t(nv > 0 ? nv : 1)));
+  GM_CUDA(dmalloc(g, &g->d_acol, sizeof(vidType) * size_t(g->acol_len > 0 ? g->acol_len : 4)));
   if (nv > 0) {
     k_make_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, units, g->d_vinfo);
     k_fill_aligned<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, g->d_vinfo, g->d_acol);
   }
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  GM_CUDA(cudaFree(units));
+  GM_CUDA(dfree(g, units));
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
@@ -193,23 +193,23 @@ int ensure_coo(gm_graph *g, int sb) {
       GM_CUDA(cudaStreamSynchronize(g->stream));
     }
     g->nnz[0] = last - base;
-    GM_CUDA(cudaMalloc(&g->d_src[0], sizeof(vidType) * size_t(g->nnz[0] > 0 ? g->nnz[0] : 1)));
+    GM_CUDA(dmalloc(g, &g->d_src[0], sizeof(vidType) * size_t(g->nnz[0] > 0 ? g->nnz[0] : 1)));
     g->d_dst[0] = g->d_colidx + base;                       // dst aliases colidx (graph_gpu.h:166)
     if (n > 0) k_fill_src_plain<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, base, g->d_src[0]);
   } else {
     eidType *off = nullptr;
-    GM_CUDA(cudaMalloc(&off, sizeof(eidType) * (size_t(n) + 1)));
+    GM_CUDA(dmalloc(g, &off, sizeof(eidType) * (size_t(n) + 1)));
     GM_CUDA(cudaMemsetAsync(off, 0, sizeof(eidType) * (size_t(n) + 1), g->stream));
     if (n > 0) k_count_lower<<<nblk(n), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, off);
     int r = exclusive_scan_inplace(g, off, n);
-    if (r != GM_OK) { cudaFree(off); return r; }
+    if (r != GM_OK) { dfree(g, off); return r; }
     GM_CUDA(cudaMemcpyAsync(&g->nnz[1], off + n, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    GM_CUDA(cudaMalloc(&g->d_src[1], sizeof(vidType) * size_t(g->nnz[1] > 0 ? g->nnz[1] : 1)));
-    GM_CUDA(cudaMalloc(&g->d_dst[1], sizeof(vidType) * size_t(g->nnz[1] > 0 ? g->nnz[1] : 1)));
+    GM_CUDA(dmalloc(g, &g->d_src[1], sizeof(vidType) * size_t(g->nnz[1] > 0 ? g->nnz[1] : 1)));
+    GM_CUDA(dmalloc(g, &g->d_dst[1], sizeof(vidType) * size_t(g->nnz[1] > 0 ? g->nnz[1] : 1)));
     if (n > 0) k_fill_lower<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, off, g->d_src[1], g->d_dst[1]);
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    GM_CUDA(cudaFree(off));
+    GM_CUDA(dfree(g, off));
   }
   GM_CUDA(cudaStreamSynchronize(g->stream));
   GM_CUDA(cudaGetLastError());
@@ -222,20 +222,20 @@ int ensure_reverse(gm_graph *g) {
   GM_CUDA(cudaSetDevice(g->device));
   vidType nv = g->nv, vb = g->src_begin, ve = g->src_end, n = ve - vb;
   unsigned long long *cursor = nullptr;
-  GM_CUDA(cudaMalloc(&g->d_rrowptr, sizeof(eidType) * (size_t(nv) + 1)));
-  GM_CUDA(cudaMalloc(&cursor, sizeof(unsigned long long) * (size_t(nv) + 1)));
+  GM_CUDA(dmalloc(g, &g->d_rrowptr, sizeof(eidType) * (size_t(nv) + 1)));
+  GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned long long) * (size_t(nv) + 1)));
   GM_CUDA(cudaMemsetAsync(g->d_rrowptr, 0, sizeof(eidType) * (size_t(nv) + 1), g->stream));
   GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
   if (n > 0) k_count_in<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, reinterpret_cast<unsigned long long *>(g->d_rrowptr));
   int r = exclusive_scan_inplace(g, g->d_rrowptr, nv);
-  if (r != GM_OK) { cudaFree(cursor); return r; }
+  if (r != GM_OK) { dfree(g, cursor); return r; }
   eidType rne = 0;
   GM_CUDA(cudaMemcpyAsync(&rne, g->d_rrowptr + nv, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  GM_CUDA(cudaMalloc(&g->d_rcolidx, sizeof(vidType) * size_t(rne > 0 ? rne : 1)));
+  GM_CUDA(dmalloc(g, &g->d_rcolidx, sizeof(vidType) * size_t(rne > 0 ? rne : 1)));
   if (n > 0) k_fill_in<<<nblk(int64_t(n) * 8), 256, 0, g->stream>>>(vb, ve, g->d_rowptr, g->d_colidx, g->d_rrowptr, cursor, g->d_rcolidx);
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  GM_CUDA(cudaFree(cursor));
+  GM_CUDA(dfree(g, cursor));
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
@@ -259,7 +259,7 @@ int ensure_items(gm_graph *g, int mode) {
   vidType min_deg = mode == 2 ? 3 : all_roots ? 1 : 2;
   int chunk_opt = mode == 2 ? 0x7fffffff : options().chunk;
   int64_t *off = nullptr;
-  GM_CUDA(cudaMalloc(&off, sizeof(int64_t) * (size_t(n) + 1)));
+  GM_CUDA(dmalloc(g, &off, sizeof(int64_t) * (size_t(n) + 1)));
   for (int cls = 0; cls < 4; cls++) {
     // class 3 also absorbs the overflow class 4 (tables that do not fit shared memory: the kernel
     // falls back to searching the root row in global memory)
@@ -267,17 +267,17 @@ int ensure_items(gm_graph *g, int mode) {
     GM_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t) * (size_t(n) + 1), g->stream));
     if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off);
     int r = exclusive_scan_inplace(g, off, n);
-    if (r != GM_OK) { cudaFree(off); return r; }
+    if (r != GM_OK) { dfree(g, off); return r; }
     int64_t total = 0;
     GM_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
     ItemList &il = g->items[mode][cls];
     il.n = total;
-    GM_CUDA(cudaMalloc(&il.d_items, sizeof(WorkItem) * size_t(total > 0 ? total : 1)));
+    GM_CUDA(dmalloc(g, &il.d_items, sizeof(WorkItem) * size_t(total > 0 ? total : 1)));
     if (n > 0 && total > 0) k_fill_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, prow, chunk, off, il.d_items);
     GM_CUDA(cudaStreamSynchronize(g->stream));
   }
-  GM_CUDA(cudaFree(off));
+  GM_CUDA(dfree(g, off));
   GM_CUDA(cudaGetLastError());
   g->items_ready[mode] = true;
   return GM_OK;
@@ -318,28 +318,56 @@ int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out) {
 }
 
 static void free_aux(gm_graph *g) {
-  cudaFree(g->d_vinfo); cudaFree(g->d_acol); g->d_vinfo = nullptr; g->d_acol = nullptr;
+  dfree(g, g->d_vinfo); dfree(g, g->d_acol); g->d_vinfo = nullptr; g->d_acol = nullptr;
   for (int s = 0; s < 2; s++) {
-    cudaFree(g->d_src[s]); g->d_src[s] = nullptr;
-    if (s == 1) cudaFree(g->d_dst[s]);
+    dfree(g, g->d_src[s]); g->d_src[s] = nullptr;
+    if (s == 1) dfree(g, g->d_dst[s]);
     g->d_dst[s] = nullptr; g->coo_ready[s] = false; g->nnz[s] = 0;
   }
   for (int s = 0; s < 4; s++) {
-    for (int c = 0; c < 4; c++) { cudaFree(g->items[s][c].d_items); g->items[s][c] = ItemList(); }
+    for (int c = 0; c < 4; c++) { dfree(g, g->items[s][c].d_items); g->items[s][c] = ItemList(); }
     g->items_ready[s] = false;
   }
-  cudaFree(g->rk_vinfo); cudaFree(g->rk_acol); cudaFree(g->rk_nrow); cudaFree(g->rk_prow); cudaFree(g->rk_prec);
+  dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec);
   g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   g->rk_ready = g->rk_valid = false;
-  cudaFree(g->d_rrowptr); cudaFree(g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
+  dfree(g, g->d_rrowptr); dfree(g, g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
+}
+
+// Per-device one-time setup: keep freed blocks in the stream-ordered pool (repeated gm_*_host calls
+// then allocate without going to the driver) and cache the slow cudaGetDeviceProperties.
+struct DeviceInfo { bool ready = false; int sms = kNumSMsB200; int smem_optin = 0; };
+static DeviceInfo &device_info(int dev) {
+  static DeviceInfo info[64];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  DeviceInfo &d = info[dev & 63];
+  if (!d.ready) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) { d.sms = p.multiProcessorCount; d.smem_optin = int(p.sharedMemPerBlockOptin); }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    d.ready = true;
+  }
+  return d;
+}
+
+static int init_stream(gm_graph *g) {
+  GM_CUDA(cudaSetDevice(g->device));
+  device_info(g->device);
+  GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  g->own_stream = true;
+  return GM_OK;
 }
 
 static int init_common(gm_graph *g) {
   GM_CUDA(cudaSetDevice(g->device));
-  GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-  g->own_stream = true;
-  GM_CUDA(cudaMalloc(&g->d_counts, 8 * sizeof(unsigned long long)));
-  GM_CUDA(cudaMalloc(&g->d_ticket, 8 * sizeof(int)));
+  GM_CUDA(dmalloc(g, &g->d_counts, 8 * sizeof(unsigned long long)));
+  GM_CUDA(dmalloc(g, &g->d_ticket, 8 * sizeof(int)));
   GM_CUDA(cudaMallocHost(&g->h_counts, 8 * sizeof(unsigned long long)));
   GM_CUDA(cudaEventCreate(&g->ev0));
   GM_CUDA(cudaEventCreate(&g->ev1));
@@ -348,20 +376,19 @@ static int init_common(gm_graph *g) {
     GM_CUDA(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
     GM_CUDA(cudaEventCreateWithFlags(&g->join_ev[i], cudaEventDisableTiming));
   }
-  cudaDeviceProp p;
-  GM_CUDA(cudaGetDeviceProperties(&p, g->device));
-  g->num_sms = p.multiProcessorCount;
-  g->smem_optin = int(p.sharedMemPerBlockOptin);
+  const DeviceInfo &di = device_info(g->device);
+  g->num_sms = di.sms;
+  g->smem_optin = di.smem_optin;
   g->src_begin = 0; g->src_end = g->nv;
   if (g->max_degree <= 0 && g->nv > 0) {
     vidType *d_md = nullptr; uint32_t *units = nullptr;
-    GM_CUDA(cudaMalloc(&d_md, sizeof(vidType)));
-    GM_CUDA(cudaMalloc(&units, sizeof(uint32_t) * size_t(g->nv)));
+    GM_CUDA(dmalloc(g, &d_md, sizeof(vidType)));
+    GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * size_t(g->nv)));
     GM_CUDA(cudaMemsetAsync(d_md, 0, sizeof(vidType), g->stream));
     k_degree<<<nblk(g->nv), 256, 0, g->stream>>>(g->nv, g->d_rowptr, units, d_md);
     GM_CUDA(cudaMemcpyAsync(&g->max_degree, d_md, sizeof(vidType), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    cudaFree(d_md); cudaFree(units);
+    dfree(g, d_md); dfree(g, units);
   }
   return GM_OK;
 }
@@ -408,12 +435,17 @@ int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, in
   gm_graph *g = new gm_graph();
   g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
   int r = [&]() -> int {
-    GM_CUDA(cudaSetDevice(device));
-    GM_CUDA(cudaMalloc(&g->d_rowptr, sizeof(eidType) * (size_t(nv) + 1)));
-    GM_CUDA(cudaMalloc(&g->d_colidx, sizeof(vidType) * size_t(ne > 0 ? ne : 1)));
-    GM_CUDA(cudaMemcpy(g->d_rowptr, rowptr, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyHostToDevice));
-    if (ne > 0) GM_CUDA(cudaMemcpy(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice));
-    return init_common(g);
+    GM_TRY(init_stream(g));
+    GM_CUDA(dmalloc(g, &g->d_rowptr, sizeof(eidType) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &g->d_colidx, sizeof(vidType) * size_t(ne > 0 ? ne : 1)));
+    // stream-ordered copies: with pinned host arrays the call returns while the DMA runs and the
+    // device-side preparation queues up behind it; the host arrays are only borrowed until the
+    // synchronisation at the end of this function
+    GM_CUDA(cudaMemcpyAsync(g->d_rowptr, rowptr, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyHostToDevice, g->stream));
+    if (ne > 0) GM_CUDA(cudaMemcpyAsync(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice, g->stream));
+    GM_TRY(init_common(g));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    return GM_OK;
   }();
   if (r != GM_OK) { gm_graph_free(g); return r; }
   *out = g;
@@ -429,7 +461,8 @@ int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv,
   g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = false;
   g->d_rowptr = const_cast<eidType *>(d_rowptr);
   g->d_colidx = const_cast<vidType *>(d_colidx);
-  int r = init_common(g);
+  int r = init_stream(g);
+  if (r == GM_OK) r = init_common(g);
   if (r != GM_OK) { gm_graph_free(g); return r; }
   *out = g;
   return GM_OK;
@@ -440,8 +473,8 @@ int gm_graph_free(gm_graph_t *g) {
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   free_aux(g);
-  if (g->own_csr) { cudaFree(g->d_rowptr); cudaFree(g->d_colidx); }
-  cudaFree(g->d_counts); cudaFree(g->d_ticket); cudaFree(g->d_scratch); cudaFree(g->d_gmat);
+  if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
+  dfree(g, g->d_counts); dfree(g, g->d_ticket); dfree(g, g->d_scratch); dfree(g, g->d_gmat);
   if (g->h_counts) cudaFreeHost(g->h_counts);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -494,6 +527,10 @@ int gm_last_stats(gm_graph_t *g, float *kernel_ms, int *launches) {
 
 int gm_last_alg_bytes(gm_graph_t *g, uint64_t *bytes) {
   if (!g || !bytes) { set_error("null argument"); return GM_EINVAL; }
+  if (g->last_alg_kind == 1) {
+    if (g->tc_bytes_cache == 0) GM_TRY(tc_alg_bytes(g, &g->tc_bytes_cache));
+    g->last_alg_bytes = g->tc_bytes_cache;
+  }
   *bytes = g->last_alg_bytes;
   return GM_OK;
 }

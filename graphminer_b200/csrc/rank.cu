@@ -118,18 +118,18 @@ int ensure_ranked(gm_graph *g) {
   unsigned *indeg = nullptr; unsigned long long *vk0 = nullptr, *vk1 = nullptr, *ek0 = nullptr, *ek1 = nullptr, *cnt = nullptr;
   vidType *rank = nullptr, *orig_of = nullptr; uint32_t *units = nullptr; int *bad = nullptr;
   auto cleanup = [&]() {
-    cudaFree(indeg); cudaFree(vk0); cudaFree(vk1); cudaFree(ek0); cudaFree(ek1); cudaFree(cnt);
-    cudaFree(rank); cudaFree(orig_of); cudaFree(units); cudaFree(bad);
+    dfree(g, indeg); dfree(g, vk0); dfree(g, vk1); dfree(g, ek0); dfree(g, ek1); dfree(g, cnt);
+    dfree(g, rank); dfree(g, orig_of); dfree(g, units); dfree(g, bad);
   };
   int rc = [&]() -> int {
-    GM_CUDA(cudaMalloc(&indeg, sizeof(unsigned) * size_t(nv)));
-    GM_CUDA(cudaMalloc(&vk0, sizeof(unsigned long long) * size_t(nv)));
-    GM_CUDA(cudaMalloc(&vk1, sizeof(unsigned long long) * size_t(nv)));
-    GM_CUDA(cudaMalloc(&rank, sizeof(vidType) * size_t(nv)));
-    GM_CUDA(cudaMalloc(&orig_of, sizeof(vidType) * size_t(nv)));
-    GM_CUDA(cudaMalloc(&units, sizeof(uint32_t) * (size_t(nv) + 1)));
-    GM_CUDA(cudaMalloc(&g->rk_nrow, sizeof(eidType) * (size_t(nv) + 1)));
-    GM_CUDA(cudaMalloc(&bad, sizeof(int)));
+    GM_CUDA(dmalloc(g, &indeg, sizeof(unsigned) * size_t(nv)));
+    GM_CUDA(dmalloc(g, &vk0, sizeof(unsigned long long) * size_t(nv)));
+    GM_CUDA(dmalloc(g, &vk1, sizeof(unsigned long long) * size_t(nv)));
+    GM_CUDA(dmalloc(g, &rank, sizeof(vidType) * size_t(nv)));
+    GM_CUDA(dmalloc(g, &orig_of, sizeof(vidType) * size_t(nv)));
+    GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &g->rk_nrow, sizeof(eidType) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &bad, sizeof(int)));
     GM_CUDA(cudaMemsetAsync(indeg, 0, sizeof(unsigned) * size_t(nv), g->stream));
     GM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), g->stream));
     GM_CUDA(cudaMemsetAsync(units, 0, sizeof(uint32_t) * (size_t(nv) + 1), g->stream));
@@ -144,21 +144,21 @@ int ensure_ranked(gm_graph *g) {
     uint32_t total_units = 0;
     GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    GM_CUDA(cudaFree(vk0)); vk0 = nullptr; GM_CUDA(cudaFree(vk1)); vk1 = nullptr; GM_CUDA(cudaFree(indeg)); indeg = nullptr;
+    GM_CUDA(dfree(g, vk0)); vk0 = nullptr; GM_CUDA(dfree(g, vk1)); vk1 = nullptr; GM_CUDA(dfree(g, indeg)); indeg = nullptr;
     if ((uint64_t(ne) + 3ull * uint64_t(nv)) >= (1ull << 32)) return GM_OK;      // element offsets must fit 32 bits
     // 2. edges by (new source, new destination)
-    GM_CUDA(cudaMalloc(&ek0, sizeof(unsigned long long) * size_t(ne)));
-    GM_CUDA(cudaMalloc(&ek1, sizeof(unsigned long long) * size_t(ne)));
+    GM_CUDA(dmalloc(g, &ek0, sizeof(unsigned long long) * size_t(ne)));
+    GM_CUDA(dmalloc(g, &ek1, sizeof(unsigned long long) * size_t(ne)));
     k_edge_keys<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, rank, ek0);
     GM_TRY(sort_keys(g, ek0, ek1, ne, 32 + bits_of(uint64_t(nv))));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    GM_CUDA(cudaFree(ek0)); ek0 = nullptr;
+    GM_CUDA(dfree(g, ek0)); ek0 = nullptr;
     // 3. aligned rows + partner records
     const int64_t acol_len = int64_t(total_units) * 4;
-    GM_CUDA(cudaMalloc(&g->rk_vinfo, sizeof(uint2) * size_t(nv)));
-    GM_CUDA(cudaMalloc(&g->rk_acol, sizeof(vidType) * size_t(acol_len > 0 ? acol_len : 4)));
-    GM_CUDA(cudaMalloc(&cnt, sizeof(unsigned long long) * (size_t(nv) + 1)));
-    GM_CUDA(cudaMalloc(&g->rk_prow, sizeof(eidType) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &g->rk_vinfo, sizeof(uint2) * size_t(nv)));
+    GM_CUDA(dmalloc(g, &g->rk_acol, sizeof(vidType) * size_t(acol_len > 0 ? acol_len : 4)));
+    GM_CUDA(dmalloc(g, &cnt, sizeof(unsigned long long) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &g->rk_prow, sizeof(eidType) * (size_t(nv) + 1)));
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
     k_ranked_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->rk_nrow, units, g->rk_vinfo);
     k_fill_u32<<<nblk(acol_len), 256, 0, g->stream>>>(acol_len, g->rk_acol, kVidMax);
@@ -171,7 +171,7 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
     if (h_bad) return GM_OK;                                                     // not the (degree,id) orientation
-    GM_CUDA(cudaMalloc(&g->rk_prec, sizeof(uint2) * size_t(nrec > 0 ? nrec : 1)));
+    GM_CUDA(dmalloc(g, &g->rk_prec, sizeof(uint2) * size_t(nrec > 0 ? nrec : 1)));
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
     k_ranked_edges<1><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end,
                                                        g->rk_acol, cnt, g->rk_prow, g->rk_prec, bad);
@@ -184,7 +184,7 @@ int ensure_ranked(gm_graph *g) {
   cudaGetLastError();
   if (rc != GM_OK) return rc;
   if (!g->rk_valid) {
-    cudaFree(g->rk_vinfo); cudaFree(g->rk_acol); cudaFree(g->rk_nrow); cudaFree(g->rk_prow); cudaFree(g->rk_prec);
+    dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec);
     g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   }
   g->rk_ready = true;

@@ -60,7 +60,7 @@ int gm_kclique(gm_graph_t *g, int k, uint64_t *total) {
   bool try_bitmap = algo != "list" && k >= 4;
   if (try_bitmap) GM_TRY(prepare_kclique_bitmap(g)); else GM_TRY(ensure_coo(g, 0));
   int launches = 0;
-  g->last_alg_bytes = 0;
+  g->last_alg_bytes = 0; g->last_alg_kind = 0;
   GM_TRY(begin_timed(g));
   bool handled = false;
   if (try_bitmap) GM_TRY(run_kclique_bitmap(g, k, &launches, &handled));
@@ -74,7 +74,7 @@ int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total) {
   if (pid < 0) { set_error("sgl: pattern '%s' not supported (diamond, rectangle, house, pentagon)", pattern ? pattern : "(null)"); return GM_EUNSUPPORTED; }
   GM_TRY(ensure_coo(g, 1));
   int launches = 0;
-  g->last_alg_bytes = 0;
+  g->last_alg_bytes = 0; g->last_alg_kind = 0;
   GM_TRY(begin_timed(g));
   GM_TRY(run_sgl(g, pid, &launches));
   return end_timed(g, launches, 1, total);
@@ -85,7 +85,7 @@ static int motif_common(gm_graph_t *g, int k, int formula, int raw, uint64_t *co
   if (k != 3 && k != 4) { set_error("motif: k=%d not supported (k in {3,4})", k); return GM_EUNSUPPORTED; }
   GM_TRY(ensure_coo(g, formula ? 1 : 0));
   int launches = 0;
-  g->last_alg_bytes = 0;
+  g->last_alg_bytes = 0; g->last_alg_kind = 0;
   GM_TRY(begin_timed(g));
   GM_TRY(run_motif(g, k, formula, &launches));
   GM_TRY(end_timed(g, launches, k == 3 ? 2 : 6, counts));

@@ -204,15 +204,15 @@ static int run_tc_hash(gm_graph *g, int *launches) {
   return GM_OK;
 }
 
-static int tc_alg_bytes(gm_graph *g, uint64_t *out) {
+int tc_alg_bytes(gm_graph *g, uint64_t *out) {
   vidType n = g->src_end - g->src_begin;
   unsigned long long *d = nullptr, h = 0;
-  GM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+  GM_CUDA(dmalloc(g, &d, sizeof(unsigned long long)));
   GM_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), g->stream));
   if (n > 0) k_tc_alg_bytes<<<(n + 255) / 256, 256, 0, g->stream>>>(g->src_begin, g->src_end, g->d_rowptr, g->d_colidx, d);
   GM_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  GM_CUDA(cudaFree(d));
+  GM_CUDA(dfree(g, d));
   *out = h + 8ull * (uint64_t(g->nv) + 1);
   return GM_OK;
 }
@@ -245,8 +245,7 @@ using namespace gm;
 extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
   if (!g || !total) { set_error("gm_tc: null argument"); return GM_EINVAL; }
   GM_TRY(prepare_tc(g));
-  if (g->tc_bytes_cache == 0) GM_TRY(tc_alg_bytes(g, &g->tc_bytes_cache));
-  g->last_alg_bytes = g->tc_bytes_cache;
+  g->last_alg_kind = 1;                       // computed on demand by gm_last_alg_bytes
   std::string algo;
   GM_TRY(resolve_tc_algo(g, &algo));
   int launches = 0;
