@@ -25,7 +25,7 @@ namespace gm {
 
 int run_kclique_list_filtered(gm_graph *g, int k, vidType min_src_degree, int *launches, cudaStream_t stream);
 
-template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD>
+template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS>
 struct CliqueCfg {
   static constexpr int kCtaThreads = GT < 256 ? 256 : GT;
   static constexpr int kGroups = kCtaThreads / GT;
@@ -34,7 +34,7 @@ struct CliqueCfg {
   static constexpr int kSlots = (1 << MAXB1) + (1 << (MAXB1 - 2 > 3 ? MAXB1 - 2 : 3)) + CAP;
   static constexpr int kPayWords = (kSlots + 1) / 2;
   static constexpr int kWMax = (MAXD + 31) / 32;
-  static constexpr int kMaskWords = kWarps * 5 * kWMax;                        // levels for k <= 8
+  static constexpr int kMaskWords = kWarps * LEVELS * kWMax;                   // per-warp mask levels (k - 4 needed)
   static constexpr int kSmemW = (SMEM_MAXD + 31) / 32;
   static constexpr int kMatWords = SMEM_MAXD * (kSmemW | 1);
   static constexpr int kGroupWords = kTabWords + kPayWords + kMaskWords + kMatWords;
@@ -45,8 +45,22 @@ struct CliqueCfg {
 template <int GT>
 __device__ __forceinline__ void cl_sync() { if (GT == 32) __syncwarp(); else __syncthreads(); }
 
+// A word array that lives either in shared memory (read with ld.shared through a 32-bit window
+// address -- no generic-address translation in the AND/POPC loops) or in global memory.
+template <bool SM>
+struct Words {
+  static constexpr bool kShared = SM;
+  const uint32_t *gp; uint32_t sa;
+  __device__ __forceinline__ explicit Words(const uint32_t *p) : gp(p), sa(SM ? uint32_t(__cvta_generic_to_shared(p)) : 0u) {}
+  __device__ __forceinline__ uint32_t operator[](int i) const { return SM ? RowTable::lds(sa + 4u * uint32_t(i)) : gp[i]; }
+  __device__ __forceinline__ Words row(size_t off) const { Words r = *this; r.gp += off; r.sa += 4u * uint32_t(off); return r; }
+};
+
 // sum over set bits j of Mp of popc(Mp & A[j]); lanes take different j.  Warp-collective.
-__device__ __forceinline__ uint32_t count_level(const uint32_t *Mp, int W, const uint32_t *M, int stride, int lane) {
+// TRI: local indices follow the DAG order (rank-relabelled graph), so A[j] only has bits above j and
+// the AND/POPC loop can start at word j/32.
+template <bool SMP, bool SMM, bool TRI>
+__device__ __forceinline__ uint32_t count_level(Words<SMP> Mp, int W, Words<SMM> M, int stride, int lane) {
   uint32_t c = 0;
   for (int wb = 0; wb < W; wb += 32) {
     const int w = wb + lane;
@@ -69,8 +83,9 @@ __device__ __forceinline__ uint32_t count_level(const uint32_t *Mp, int W, const
       const int r = t - __shfl_sync(kFullMask, excl, s);
       if (t < tot) {
         const int bit = __fns(ws, 0, r + 1);
-        const uint32_t *Aj = M + size_t((wb + s) * 32 + bit) * stride;
-        for (int w2 = 0; w2 < W; w2++) c += __popc(Mp[w2] & Aj[w2]);
+        const int j = (wb + s) * 32 + bit;
+        const Words<SMM> Aj = M.row(size_t(j) * stride);
+        for (int w2 = TRI ? (j >> 5) : 0; w2 < W; w2++) c += __popc(Mp[w2] & Aj[w2]);
       }
     }
   }
@@ -78,48 +93,52 @@ __device__ __forceinline__ uint32_t count_level(const uint32_t *Mp, int W, const
 }
 
 // cliques whose second vertex is local row i (warp-collective; masks = this warp's level buffers)
-__device__ __forceinline__ uint32_t count_row(int k, int i, int W, const uint32_t *M, int stride,
+template <bool SMM, bool TRI>
+__device__ __forceinline__ uint32_t count_row(int k, int i, int W, Words<SMM> M, int stride,
                                               uint32_t *masks, int wmax, int lane) {
-  const uint32_t *Ai = M + size_t(i) * stride;
-  if (k == 4) return count_level(Ai, W, M, stride, lane);
+  const Words<SMM> Ai = M.row(size_t(i) * stride);
+  if (k == 4) return count_level<SMM, SMM, TRI>(Ai, W, M, stride, lane);
   const int depth = k - 4;                 // serially chosen vertices below row i
-  const uint32_t *cur[6];
+  // level 0 reads the matrix row, deeper levels read this warp's masks (always shared memory)
   int wi[6]; uint32_t word[6];
   uint32_t c = 0;
   int t = 0;
-  cur[0] = Ai; wi[0] = 0; word[0] = Ai[0];
+  wi[0] = 0; word[0] = Ai[0];
+  auto cur_word = [&](int lvl, int w) -> uint32_t { return lvl == 0 ? Ai[w] : masks[(lvl - 1) * wmax + w]; };
   while (t >= 0) {
-    while (word[t] == 0 && ++wi[t] < W) word[t] = cur[t][wi[t]];
+    while (word[t] == 0 && ++wi[t] < W) word[t] = cur_word(t, wi[t]);
     if (wi[t] >= W) { t--; continue; }
     const int b = __ffs(word[t]) - 1;
     word[t] &= word[t] - 1;
     const int j = wi[t] * 32 + b;
     uint32_t *nm = masks + t * wmax;
     __syncwarp();                                         // earlier readers of nm are done
-    const uint32_t *Aj = M + size_t(j) * stride;
-    for (int w = lane; w < W; w += 32) nm[w] = cur[t][w] & Aj[w];
+    const Words<SMM> Aj = M.row(size_t(j) * stride);
+    const int w0 = TRI ? (j >> 5) : 0;
+    for (int w = lane; w < W; w += 32) nm[w] = w >= w0 ? (cur_word(t, w) & Aj[w]) : 0u;
     __syncwarp();
     if (t + 1 == depth) {
-      c += count_level(nm, W, M, stride, lane);
+      c += count_level<true, SMM, TRI>(Words<true>(nm), W, M, stride, lane);
     } else {
-      t++; cur[t] = nm; wi[t] = 0; word[t] = nm[0];
+      t++; wi[t] = 0; word[t] = nm[0];
     }
   }
   return c;
 }
 
-template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD>
-__global__ void __launch_bounds__(CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD>::kCtaThreads)
+template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS, bool TRI>
+__global__ void __launch_bounds__(CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>::kCtaThreads)
 kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int64_t nitems, int *ticket,
                       uint32_t *gmat, AccType *total) {
-  using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD>;
+  using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>;
   extern __shared__ uint32_t smem[];
   __shared__ int64_t s_next;
+  __shared__ int s_row[Cfg::kGroups];                      // dynamic row hand-out of the count phase
   const int lane = threadIdx.x & 31;
   const int gtid = threadIdx.x % GT, gwarp = gtid >> 5;
   uint32_t *gbase = smem + size_t(threadIdx.x / GT) * Cfg::kGroupWords;
   uint16_t *pay = reinterpret_cast<uint16_t *>(gbase + Cfg::kTabWords);
-  uint32_t *masks = gbase + Cfg::kTabWords + Cfg::kPayWords + gwarp * 5 * Cfg::kWMax;
+  uint32_t *masks = gbase + Cfg::kTabWords + Cfg::kPayWords + gwarp * LEVELS * Cfg::kWMax;
   uint32_t *smat = gbase + Cfg::kTabWords + Cfg::kPayWords + Cfg::kMaskWords;
   AccType acc = 0;
 
@@ -157,45 +176,91 @@ kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int
     if (hashed)
       for (int i = gtid; i < d; i += GT) pay[tab.find_slot(uint32_t(__ldg(row + i)))] = uint16_t(i);
     for (int i = gtid; i < d * stride; i += GT) M[i] = 0u;
+    if (gtid == 0) s_row[threadIdx.x / GT] = 0;
     cl_sync<GT>();
 
-    // 2. one pass over the rows of the members: A[i] |= bit(local index of x) for x in N+(R[i]) ∩ R
-    for (int i = gwarp; i < d; i += Cfg::kWarps) {
-      const uint2 pv = g.info(__ldg(row + i));
-      const vidType *list = g.NA(pv);
-      const int len = int(pv.y);
-      uint32_t *Ai = M + size_t(i) * stride;
-      for (int e = lane; e < len; e += 32) {
-        const vidType x = __ldg(list + e);
-        int j;
-        if (hashed) {
-          const int slot = tab.find_slot(uint32_t(x));
-          j = slot >= 0 ? int(pay[slot]) : -1;
-        } else {
-          const vidType p = lower_bound(row, vidType(d), x);
-          j = (p < d && __ldg(row + p) == x) ? int(p) : -1;
+    // 2. one pass over the rows of the members: A[i] |= bit(local index of x) for x in N+(R[i]) ∩ R.
+    // Rows are dealt round-robin to the warps of the group; a warp fetches the descriptors of its next
+    // 32 rows lane-parallel, then streams each row with four coalesced loads in flight and one
+    // shared-memory probe per element (the TC inner loop plus a payload lookup on hits).
+    {
+      constexpr int WG = Cfg::kWarps;
+      const uint32_t s1 = hashed ? tab.saddr1() : 0u;
+      const int mine = (d - gwarp + WG - 1) / WG;                 // rows owned by this warp
+      for (int rb = 0; rb < mine; rb += 32) {
+        const int q = rb + lane;
+        uint2 pvl = make_uint2(0, 0);
+        if (q < mine) pvl = g.info(__ldg(row + q * WG + gwarp));
+        const int nr = min(32, mine - rb);
+        for (int t = 0; t < nr; t++) {
+          const uint32_t off = __shfl_sync(kFullMask, pvl.x, t);
+          const int len = int(__shfl_sync(kFullMask, pvl.y, t));
+          const vidType *list = g.d_acol + (size_t(off) << 2);
+          uint32_t *Ai = M + size_t((rb + t) * WG + gwarp) * stride;
+          if (hashed) {
+            const vidType *p = list + lane;
+            for (int r = len - lane; r > -lane; r -= 128, p += 128) {
+              uint32_t x[4];
+              #pragma unroll
+              for (int u = 0; u < 4; u++) x[u] = r > 32 * u ? uint32_t(__ldg(p + 32 * u)) : uint32_t(kVidMax);
+              #pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const uint32_t h = (x[u] * kHashK1) >> tab.sh1;
+                const uint32_t tw = RowTable::lds(s1 + (h << 2));
+                int j = -1;
+                if ((tw & kKeyMask) == x[u]) {
+                  j = int(pay[h]);
+                } else if (int32_t(tw) < 0) {                     // overflowed slot: level 2 / stash
+                  const int slot = tab.find_slot(x[u]);
+                  if (slot >= 0) j = int(pay[slot]);
+                }
+                if (j >= 0) atomicOr(Ai + (j >> 5), 1u << (j & 31));
+              }
+            }
+          } else {
+            for (int e = lane; e < len; e += 32) {
+              const vidType x = __ldg(list + e);
+              const vidType pp = lower_bound(row, vidType(d), x);
+              if (pp < d && __ldg(row + pp) == x) atomicOr(Ai + (pp >> 5), 1u << (pp & 31));
+            }
+          }
         }
-        if (j >= 0) atomicOr(Ai + (j >> 5), 1u << (j & 31));
       }
     }
     cl_sync<GT>();
 
     // 3. count with AND + POPC
     uint32_t c = 0;
-    for (int i = gwarp; i < d; i += Cfg::kWarps) c += count_row(k, i, W, M, stride, masks, Cfg::kWMax, lane);
+    const bool in_smem = d <= SMEM_MAXD;                     // group-uniform
+    auto rows = [&](auto Mw) {
+      if (GT == 32) {
+        for (int i = 0; i < d; i++) c += count_row<decltype(Mw)::kShared, TRI>(k, i, W, Mw, stride, masks, Cfg::kWMax, lane);
+      } else {
+        // rows differ widely in popcount: warps draw them from a shared counter
+        int *rowctr = &s_row[threadIdx.x / GT];
+        while (true) {
+          int i = 0;
+          if (lane == 0) i = atomicAdd(rowctr, 1);
+          i = __shfl_sync(kFullMask, i, 0);
+          if (i >= d) break;
+          c += count_row<decltype(Mw)::kShared, TRI>(k, i, W, Mw, stride, masks, Cfg::kWMax, lane);
+        }
+      }
+    };
+    if (in_smem) rows(Words<true>(M)); else rows(Words<false>(M));
     acc += c;
   }
   acc = warp_reduce(acc);
   if (lane == 0 && acc) atomicAdd(total, acc);
 }
 
-template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD>
+template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS, bool TRI>
 static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream, int *launches) {
-  const ItemList &il = g->items[2][cls];
+  const ItemList &il = g->items[TRI ? 4 : 2][cls];
   if (il.n == 0) return GM_OK;
-  using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD>;
+  using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "k-clique bitmap class does not fit shared memory");
-  auto kern = kclique_bitmap_kernel<GT, MAXB1, CAP, MAXD, SMEM_MAXD>;
+  auto kern = kclique_bitmap_kernel<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS, TRI>;
   GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::kSmemBytes)));
   int occ = 0;
   GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::kCtaThreads, Cfg::kSmemBytes));
@@ -214,28 +279,53 @@ static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream,
     }
     gmat = g->d_gmat;
   }
-  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(g->view(0), k, il.d_items, il.n, g->d_ticket + 4 + cls, gmat, g->d_counts);
+  GraphGPU view = g->view(0);
+  if (TRI) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; }     // rank-relabelled rows
+  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, k, il.d_items, il.n, g->d_ticket + 4 + cls, gmat, g->d_counts);
   (*launches)++;
   return GM_OK;
 }
 
+// The rank-relabelled graph (rank.cu) is used when the input is the (degree,id) orientation: local
+// indices then follow the DAG order and the bit matrix is strictly upper triangular (TRI).
+static int clique_mode(gm_graph *g, bool *tri) {
+  GM_TRY(ensure_ranked(g));
+  *tri = g->rk_valid;
+  return GM_OK;
+}
+
 int prepare_kclique_bitmap(gm_graph *g) {
-  GM_TRY(ensure_aligned(g));
-  GM_TRY(ensure_items(g, 2));
-  if (g->items[2][3].n > 0) GM_TRY(ensure_coo(g, 0));
+  bool tri = false;
+  GM_TRY(clique_mode(g, &tri));
+  if (!tri) GM_TRY(ensure_aligned(g));
+  GM_TRY(ensure_items(g, tri ? 4 : 2));
+  if (g->items[tri ? 4 : 2][3].n > 0) GM_TRY(ensure_coo(g, 0));
+  return GM_OK;
+}
+
+template <bool TRI>
+static int run_bitmap_classes(gm_graph *g, int k, int *launches) {
+  GM_TRY(fork_streams(g));
+  if (k == 4) {           // no per-warp mask levels needed: the big class affords 1024 threads
+    GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));
+    GM_TRY((launch_clique_class<1024, 13, 64, 2048, 1024, 0, TRI>(g, k, 2, g->side[0], launches)));
+    GM_TRY((launch_clique_class<32, 7, 16, 32, 32, 0, TRI>(g, k, 0, g->side[1], launches)));
+  } else {
+    GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 4, TRI>(g, k, 1, g->stream, launches)));
+    GM_TRY((launch_clique_class<512, 13, 64, 2048, 1024, 4, TRI>(g, k, 2, g->side[0], launches)));
+    GM_TRY((launch_clique_class<32, 7, 16, 32, 32, 4, TRI>(g, k, 0, g->side[1], launches)));
+  }
+  // roots beyond the largest bitmap class: list DFS on the original graph (degrees are the same)
+  if (g->items[TRI ? 4 : 2][3].n > 0) GM_TRY(run_kclique_list_filtered(g, k, 2048, launches, g->side[2]));
+  GM_TRY(join_streams(g));
   return GM_OK;
 }
 
 int run_kclique_bitmap(gm_graph *g, int k, int *launches, bool *handled) {
   *handled = true;
-  // scratch for the global-matrix class must exist before the concurrent launches start
-  GM_TRY(fork_streams(g));
-  GM_TRY((launch_clique_class<256, 11, 64, 512, 512>(g, k, 1, g->stream, launches)));
-  GM_TRY((launch_clique_class<512, 13, 64, 2048, 1024>(g, k, 2, g->side[0], launches)));
-  GM_TRY((launch_clique_class<32, 7, 16, 32, 32>(g, k, 0, g->side[1], launches)));
-  if (g->items[2][3].n > 0) GM_TRY(run_kclique_list_filtered(g, k, 2048, launches, g->side[2]));
-  GM_TRY(join_streams(g));
-  return GM_OK;
+  bool tri = false;
+  GM_TRY(clique_mode(g, &tri));
+  return tri ? run_bitmap_classes<true>(g, k, launches) : run_bitmap_classes<false>(g, k, launches);
 }
 
 }  // namespace gm

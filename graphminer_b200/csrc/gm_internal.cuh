@@ -83,8 +83,8 @@ struct gm_graph {
   gm::vidType *d_rcolidx = nullptr;
 
   // vertex-centric work items, by class (0: warp-sized tables, 1: CTA small, 2: CTA large, 3: fallback)
-  gm::ItemList items[4][4];
-  bool items_ready[4] = {false, false, false, false};   // [0] forward, [1] reverse, [2] forward whole-root, [3] ranked
+  gm::ItemList items[5][4];
+  bool items_ready[5] = {false, false, false, false, false};   // [0] forward, [1] reverse, [2] forward whole-root, [3] ranked, [4] ranked whole-root
 
   // rank-relabelled DAG (rank.cu): new id = position in the (total degree, id) order, so every edge
   // goes from a lower to a higher id and rows are sorted by new id
@@ -93,6 +93,7 @@ struct gm_graph {
   gm::eidType *rk_nrow = nullptr;      // compact rowptr of the relabelled graph (nv+1)
   gm::eidType *rk_prow = nullptr;      // per new root: offsets into rk_prec (nv+1)
   uint2 *rk_prec = nullptr;            // partner records {element offset of the suffix, length}
+  gm::vidType *rk_orig = nullptr;      // new id -> original id
 
   // scratch + results
   unsigned long long *d_counts = nullptr;     // 8 accumulators

@@ -109,10 +109,13 @@ __device__ __forceinline__ int item_class(vidType d) {
   return d <= 32 ? 0 : d <= 512 ? 1 : d <= 2048 ? 2 : d <= 8192 ? 3 : 4;
 }
 // per root: number of items of class `cls` (0 when the root belongs to another class)
+// orig_of != nullptr: roots are new (ranked) ids and only count when their original id is in [fb, fe)
 __global__ void k_count_items(vidType vb, vidType ve, vidType min_deg, const eidType *rowptr,
-                              const eidType *prowptr, int cls, int merge_from, int chunk, int64_t *cnt) {
+                              const eidType *prowptr, int cls, int merge_from, int chunk, int64_t *cnt,
+                              const vidType *orig_of, vidType fb, vidType fe) {
   vidType r = vb + blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= ve) return;
+  if (orig_of) { vidType o = orig_of[r]; if (o < fb || o >= fe) { cnt[r - vb] = 0; return; } }
   vidType d = vidType(rowptr[r + 1] - rowptr[r]);
   eidType np = prowptr[r + 1] - prowptr[r];
   int c = item_class(d);
@@ -250,14 +253,17 @@ int ensure_items(gm_graph *g, int mode) {
   GM_CUDA(cudaSetDevice(g->device));
   const int reverse = mode == 1;
   if (reverse) GM_TRY(ensure_reverse(g));
-  if (mode == 3) GM_TRY(ensure_ranked(g));
-  // mode 3 (ranked): roots are NEW ids; degrees come from the relabelled compact rowptr
-  const eidType *rowptr = mode == 3 ? g->rk_nrow : g->d_rowptr;
-  const eidType *prow = reverse ? g->d_rrowptr : mode == 3 ? g->rk_prow : g->d_rowptr;
-  const bool all_roots = reverse || mode == 3;
+  if (mode >= 3) GM_TRY(ensure_ranked(g));
+  // modes 3/4 (ranked): roots are NEW ids; degrees come from the relabelled compact rowptr.
+  // mode 4 = mode 2 on the ranked graph: one item per root whose ORIGINAL id lies in the source range.
+  const bool whole = mode == 2 || mode == 4;
+  const eidType *rowptr = mode >= 3 ? g->rk_nrow : g->d_rowptr;
+  const eidType *prow = reverse ? g->d_rrowptr : mode == 3 ? g->rk_prow : mode == 4 ? g->rk_nrow : g->d_rowptr;
+  const bool all_roots = reverse || mode >= 3;
   vidType vb = all_roots ? 0 : g->src_begin, ve = all_roots ? g->nv : g->src_end, n = ve - vb;
-  vidType min_deg = mode == 2 ? 3 : all_roots ? 1 : 2;
-  int chunk_opt = mode == 2 ? 0x7fffffff : options().chunk;
+  vidType min_deg = whole ? 3 : all_roots ? 1 : 2;
+  int chunk_opt = whole ? 0x7fffffff : options().chunk;
+  const vidType *filt = mode == 4 ? g->rk_orig : nullptr;
   int64_t *off = nullptr;
   GM_CUDA(dmalloc(g, &off, sizeof(int64_t) * (size_t(n) + 1)));
   for (int cls = 0; cls < 4; cls++) {
@@ -265,7 +271,7 @@ int ensure_items(gm_graph *g, int mode) {
     // falls back to searching the root row in global memory)
     int chunk = chunk_opt > 0 ? chunk_opt : (cls == 0 ? 64 : cls == 1 ? 512 : cls == 2 ? 1024 : 2048);
     GM_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t) * (size_t(n) + 1), g->stream));
-    if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off);
+    if (n > 0) k_count_items<<<nblk(n), 256, 0, g->stream>>>(vb, ve, min_deg, rowptr, prow, cls, cls == 3 ? 3 : -1, chunk, off, filt, g->src_begin, g->src_end);
     int r = exclusive_scan_inplace(g, off, n);
     if (r != GM_OK) { dfree(g, off); return r; }
     int64_t total = 0;
@@ -324,12 +330,12 @@ static void free_aux(gm_graph *g) {
     if (s == 1) dfree(g, g->d_dst[s]);
     g->d_dst[s] = nullptr; g->coo_ready[s] = false; g->nnz[s] = 0;
   }
-  for (int s = 0; s < 4; s++) {
+  for (int s = 0; s < 5; s++) {
     for (int c = 0; c < 4; c++) { dfree(g, g->items[s][c].d_items); g->items[s][c] = ItemList(); }
     g->items_ready[s] = false;
   }
-  dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec);
-  g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
+  dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec); dfree(g, g->rk_orig);
+  g->rk_orig = nullptr; g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   g->rk_ready = g->rk_valid = false;
   dfree(g, g->d_rrowptr); dfree(g, g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
 }

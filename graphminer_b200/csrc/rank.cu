@@ -119,7 +119,7 @@ int ensure_ranked(gm_graph *g) {
   vidType *rank = nullptr, *orig_of = nullptr; uint32_t *units = nullptr; int *bad = nullptr;
   auto cleanup = [&]() {
     dfree(g, indeg); dfree(g, vk0); dfree(g, vk1); dfree(g, ek0); dfree(g, ek1); dfree(g, cnt);
-    dfree(g, rank); dfree(g, orig_of); dfree(g, units); dfree(g, bad);
+    dfree(g, rank); dfree(g, units); dfree(g, bad);
   };
   int rc = [&]() -> int {
     GM_CUDA(dmalloc(g, &indeg, sizeof(unsigned) * size_t(nv)));
@@ -178,8 +178,10 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(cudaStreamSynchronize(g->stream));
     GM_CUDA(cudaGetLastError());
     g->rk_valid = true;
+    g->rk_orig = orig_of; orig_of = nullptr;
     return GM_OK;
   }();
+  dfree(g, orig_of);
   cleanup();
   cudaGetLastError();
   if (rc != GM_OK) return rc;

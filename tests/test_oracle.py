@@ -46,8 +46,9 @@ def test_mico_slow(mico):
     rp, ci, _ = mico
     k = KAT["mico"]
     assert oracle.sgl(rp, ci, "rectangle") == k["rectangle"]
-    orp, oci, _ = oracle.orient(rp, ci)
-    assert oracle.kclique(orp, oci, 5) == k["clique5"]
+    if os.environ.get("GM_SLOW_TESTS") == "1":            # ~30 s; the GPU suite checks this KAT too
+        orp, oci, _ = oracle.orient(rp, ci)
+        assert oracle.kclique(orp, oci, 5) == k["clique5"]
 
 
 def test_range_split_is_additive(citeseer):
