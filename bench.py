@@ -287,12 +287,15 @@ def cpu_baseline(rp, ci, max_deg, clique, budget_s=12.0):
     import oracle
     nv = len(rp) - 1
     use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so"))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if use_ref:
         L = oracle.ref_lib()
+        L.gmr_set_num_threads(ncpu)            # torchrun sets OMP_NUM_THREADS=1; use every host core
         h = L.gmr_graph_create(nv, rp, ci, max_deg)
         run = (lambda a, b: L.gmr_kclique_range(h, 4, a, b)) if clique else (lambda a, b: L.gmr_tc_range(h, a, b))
         cores = L.gmr_num_threads()
     else:
+        oracle.set_num_threads(ncpu)
         run = (lambda a, b: oracle.kclique(rp, ci, 4, (a, b))) if clique else (lambda a, b: oracle.tc(rp, ci, (a, b)))
         cores = oracle.num_threads()
     # calibrate on 0.5% of the sources, then size the sample for ~budget_s (vertex ids are randomly

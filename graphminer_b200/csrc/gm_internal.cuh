@@ -108,7 +108,8 @@ struct gm_graph {
   int last_launches = 0;
   uint64_t last_alg_bytes = 0;
   uint64_t tc_bytes_cache = 0;
-  int last_alg_kind = 0;                  // 1: TC formula (computed lazily)
+  int last_alg_kind = 0;                  // 1: TC formula, 2: 4-clique formula (computed lazily)
+  uint64_t c4_bytes_cache = 0;
   int num_sms = gm::kNumSMsB200;
   int smem_optin = 0;
 
@@ -135,6 +136,7 @@ int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
 int tc_alg_bytes(gm_graph *g, uint64_t *out);
+int clique4_alg_bytes(gm_graph *g, uint64_t *out);
 int ensure_scratch(gm_graph *g, size_t bytes);
 int begin_timed(gm_graph *g);
 int fork_streams(gm_graph *g);

@@ -254,6 +254,35 @@ motif4_formula_warp_edge(GraphGPU g, vidType *scratch, int64_t max_deg, unsigned
   flush(c3, &counters[3]); flush(c4, &counters[4]); flush(c5, &counters[5]);
 }
 
+// Algorithmic bytes of 4-clique counting per SURVEY.md section 8(d): per edge (v0,v1) with S1 = N+(v0) ∩ N+(v1):
+//   4*(d0+d1) + 8 (COO)  read, 4*|S1| written, and for every v2 in S1 one more intersection 4*(|S1| + d+(v2));
+// plus 8*(|V|+1) for the row pointers.  Measurement support only (one slow operator-API pass on demand).
+__global__ void __launch_bounds__(256)
+k_clique4_alg_bytes(GraphGPU g, unsigned long long *ticket, AccType *out) {
+  TaskFeed feed; feed.init(ticket, g.num_tasks);
+  const int lane = lane_id();
+  AccType bytes = 0;
+  for (eidType e = feed.next(); e >= 0; e = feed.next()) {
+    const vidType v0 = g.get_src(e), v1 = g.get_dst(e);
+    const vidType d0 = g.get_degree(v0), d1 = g.get_degree(v1);
+    const vidType *keys = g.N(v0), *srch = g.N(v1); vidType nk = d0, ns = d1;
+    if (nk > ns) { keys = g.N(v1); srch = g.N(v0); nk = d1; ns = d0; }
+    AccType n1 = 0, degsum = 0;
+    if (nk > 0 && ns > 0) {
+      WarpIndex<vidType> idx; idx.build(srch, ns);
+      for (vidType base = 0; base < nk; base += 32) {
+        vidType i = base + lane;
+        vidType key = i < nk ? keys[i] : kVidMax;
+        bool found = idx.contains(key) && i < nk;
+        if (found) { n1++; degsum += AccType(g.get_degree(key)); }
+      }
+    }
+    n1 = warp_reduce(n1); degsum = warp_reduce(degsum);
+    if (lane == 0) bytes += 4ull * (AccType(d0) + AccType(d1)) + 8ull + 4ull * n1 + 4ull * (n1 * n1 + degsum);
+  }
+  if (lane == 0 && bytes) atomicAdd(out, bytes);
+}
+
 // ------------------------------------------------------------------------------------------------
 static int pattern_grid(gm_graph *g, const void *kernel, int64_t ntasks, int64_t per_warp_ints, int *grid, vidType **scratch) {
   int occ = 0;
@@ -293,6 +322,23 @@ int run_kclique_list_filtered(gm_graph *g, int k, vidType min_src_degree, int *l
 
 int run_kclique_list(gm_graph *g, int k, int *launches) {
   return run_kclique_list_filtered(g, k, -1, launches, g->stream);
+}
+
+int clique4_alg_bytes(gm_graph *g, uint64_t *out) {
+  GM_TRY(ensure_coo(g, 0));
+  unsigned long long *d = nullptr, h = 0;
+  GM_CUDA(dmalloc(g, &d, 2 * sizeof(unsigned long long)));
+  GM_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), g->stream));
+  if (g->nnz[0] > 0) {
+    int grid; vidType *scratch;
+    GM_TRY(pattern_grid(g, (const void *)k_clique4_alg_bytes, g->nnz[0], 0, &grid, &scratch));
+    k_clique4_alg_bytes<<<grid, 256, 0, g->stream>>>(g->view(0), d + 1, d);
+  }
+  GM_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(dfree(g, d));
+  *out = h + 8ull * (uint64_t(g->nv) + 1);
+  return GM_OK;
 }
 
 int run_sgl(gm_graph *g, int pattern, int *launches) {

@@ -60,7 +60,7 @@ int gm_kclique(gm_graph_t *g, int k, uint64_t *total) {
   bool try_bitmap = algo != "list" && k >= 4;
   if (try_bitmap) GM_TRY(prepare_kclique_bitmap(g)); else GM_TRY(ensure_coo(g, 0));
   int launches = 0;
-  g->last_alg_bytes = 0; g->last_alg_kind = 0;
+  g->last_alg_bytes = 0; g->last_alg_kind = (k == 4) ? 2 : 0;
   GM_TRY(begin_timed(g));
   bool handled = false;
   if (try_bitmap) GM_TRY(run_kclique_bitmap(g, k, &launches, &handled));

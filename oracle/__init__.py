@@ -67,6 +67,7 @@ def lib():
         L.gmo_motif_formula.restype = C.c_int
         L.gmo_motif_formula.argtypes = [v, _i64p, _i32p, C.c_int, v, _u64p]
         L.gmo_num_threads.restype = C.c_int
+        L.gmo_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -205,6 +206,10 @@ def num_threads():
     return lib().gmo_num_threads()
 
 
+def set_num_threads(n):
+    lib().gmo_set_num_threads(int(n))
+
+
 # ---- the unmodified reference (oracle/_ref) ----
 def have_ref():
     return os.path.exists(os.path.join(REF_DIR, "tc_omp_base"))
@@ -249,5 +254,6 @@ def ref_lib():
         L.gmr_diamond_range.restype = C.c_uint64
         L.gmr_diamond_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.gmr_num_threads.restype = C.c_int
+        L.gmr_set_num_threads.argtypes = [C.c_int]
         _ref = L
     return _ref

@@ -575,6 +575,15 @@ int gmo_motif_formula(vid_t nv, const eid_t *rp, const vid_t *ci, int k, vid_t m
   return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must still use the whole host */
+void gmo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int gmo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -90,5 +90,6 @@ uint64_t gmr_diamond_range(void *h, int32_t v_begin, int32_t v_end) {
   return counter;
 }
 
+void gmr_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }   // torchrun exports OMP_NUM_THREADS=1
 int gmr_num_threads() { return omp_get_max_threads(); }
 }
