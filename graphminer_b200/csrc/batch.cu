@@ -49,6 +49,18 @@ __global__ void __launch_bounds__(256) batch_bsearch_kernel(BatchArgs p) {
   }
 }
 
+int set_batch_option(const char *key, int value) {
+  BatchTuning &t = batch_tuning();
+  const std::string k(key);
+  if (k == "batch.g2048" && (value == 1 || value == 2)) t.g2048 = value;
+  else if (k == "batch.g4608" && (value == 1 || value == 2 || value == 4)) t.g4608 = value;
+  else if (k == "batch.pred_lds" && (value == 0 || value == 1)) t.pred = value;
+  else if (k == "batch.ns2048" && (value == 2 || value == 3)) t.ns2048 = value;
+  else if (k == "batch.ns1024" && (value == 2 || value == 3)) t.ns1024 = value;
+  else { set_error("bad batch option %s=%d", key, value); return GM_EINVAL; }
+  return GM_OK;
+}
+
 template <int OP>
 static void launch_bsearch(const BatchArgs &a, int grid, cudaStream_t s) { batch_bsearch_kernel<OP><<<grid, 256, 0, s>>>(a); }
 
@@ -84,7 +96,11 @@ extern "C" int gm_intersect_batch(const int32_t *d_pool, const int64_t *d_a_off,
     sms_cache[device & 63] = sms;
   }
 
-  if (algo == GM_ALGO_MERGE || algo == GM_ALGO_HASH || algo == GM_ALGO_GALLOP) {
+  // AUTO on the plain count takes the TMA pipeline with a per-pair merge/search choice when the pool
+  // can be bulk-copied; every other op (and an unaligned pool) runs the operator API
+  const bool pool_aligned = (reinterpret_cast<uintptr_t>(d_pool) & 15) == 0;
+  if (algo == GM_ALGO_MERGE || algo == GM_ALGO_HASH || algo == GM_ALGO_GALLOP ||
+      (algo == GM_ALGO_AUTO && op == GM_OP_INTERSECT_NUM && pool_aligned)) {
     if (op != GM_OP_INTERSECT_NUM) { set_error("gm_intersect_batch: algo %d implements GM_OP_INTERSECT_NUM only", algo); return GM_EUNSUPPORTED; }
     return launch_batch_variant(algo, d_pool, d_a_off, d_a_len, d_b_off, d_b_len, npairs,
                                 reinterpret_cast<unsigned long long *>(d_out), sms, s);

@@ -40,6 +40,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_addr(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -65,59 +72,153 @@ __device__ __forceinline__ vidType lds_i32(uint32_t addr) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts_i32(uint32_t addr, vidType v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
-// merge-path count of one staged pair; sA/sB = shared byte address of the first real element.
-// The caller has written the sentinels A[na] = kVidMax and B[nb] = kVidMax - 1 behind the lists: an
-// exhausted head then loses every comparison, the two sentinels never compare equal, and no step needs
-// a bounds check.  Each lane walks TWO independent merge-path segments (64 per pair) so that two
-// dependent LDS -> compare -> select chains are in flight per lane.
-__device__ __forceinline__ uint32_t merge_path_count(uint32_t sA, int na, uint32_t sB, int nb, int lane) {
+// Merge-path split of diagonal d restricted to the window [lo, hi]: the number of a-elements among the
+// first d elements of the merged sequence (a goes first on ties).  Byte-address arithmetic throughout.
+__device__ __forceinline__ int merge_path_split(uint32_t sA, uint32_t sB, int d, int lo, int hi) {
+  const uint32_t sBd = sB + 4u * uint32_t(d - 1);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const vidType av = lds_i32(sA + 4u * uint32_t(mid));
+    const vidType bv = lds_i32(sBd - 4u * uint32_t(mid));
+    const bool up = av <= bv;
+    lo = up ? mid + 1 : lo;
+    hi = up ? hi : mid;
+  }
+  return lo;
+}
+
+// One step of a serial merge chain, in PTX so that the conditional advances stay single predicated
+// instructions (nvcc's selp lowering spends 14 SASS per step).  Two flavours of the reload:
+//   PRED = true : two predicated ld.shared straight into x or y    (7 SASS, two half-populated LDS)
+//   PRED = false: select the address, one ld.shared, two selects    (9 SASS, one LDS -> fewer bank-conflict
+//                 wavefronts; the staged merge is bound by the shared-memory pipe, see profiles/)
+// Forward chain: count a match when the a-side head is consumed, advance the smaller head (a on ties).
+template <bool PRED>
+__device__ __forceinline__ void merge_step_fwd(uint32_t &c, uint32_t &pa, uint32_t &pb, vidType &x, vidType &y) {
+  if (PRED) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.le.s32 p, %3, %4;\n"
+        "setp.eq.s32 q, %3, %4;\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "@p ld.shared.s32 %3, [%1+4];\n"
+        "@!p ld.shared.s32 %4, [%2+4];\n"
+        "@p add.u32 %1, %1, 4;\n"
+        "@!p add.u32 %2, %2, 4;\n"
+        "}\n"
+        : "+r"(c), "+r"(pa), "+r"(pb), "+r"(x), "+r"(y) : : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 t, v;\n"
+        "setp.le.s32 p, %3, %4;\n"
+        "setp.eq.s32 q, %3, %4;\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "selp.b32 t, %1, %2, p;\n"
+        "ld.shared.s32 v, [t+4];\n"
+        "@p add.u32 %1, %1, 4;\n"
+        "@!p add.u32 %2, %2, 4;\n"
+        "selp.b32 %3, v, %3, p;\n"
+        "selp.b32 %4, %4, v, p;\n"
+        "}\n"
+        : "+r"(c), "+r"(pa), "+r"(pb), "+r"(x), "+r"(y) : : "memory");
+  }
+}
+// Backward chain: consume the larger tail (b on ties, since a precedes b in the merged order); a match
+// is counted when the a-side tail is consumed and equals the b consumed just before it (`lastb`).
+template <bool PRED>
+__device__ __forceinline__ void merge_step_bwd(uint32_t &c, uint32_t &qa, uint32_t &qb, vidType &xa, vidType &yb, vidType &lastb) {
+  if (PRED) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ge.s32 p, %4, %3;\n"
+        "setp.eq.and.s32 q, %3, %5, !p;\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "@p mov.b32 %5, %4;\n"
+        "@p ld.shared.s32 %4, [%2+-4];\n"
+        "@!p ld.shared.s32 %3, [%1+-4];\n"
+        "@p sub.u32 %2, %2, 4;\n"
+        "@!p sub.u32 %1, %1, 4;\n"
+        "}\n"
+        : "+r"(c), "+r"(qa), "+r"(qb), "+r"(xa), "+r"(yb), "+r"(lastb) : : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 t, v;\n"
+        "setp.ge.s32 p, %4, %3;\n"
+        "setp.eq.and.s32 q, %3, %5, !p;\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "@p mov.b32 %5, %4;\n"
+        "selp.b32 t, %2, %1, p;\n"
+        "ld.shared.s32 v, [t+-4];\n"
+        "@p sub.u32 %2, %2, 4;\n"
+        "@!p sub.u32 %1, %1, 4;\n"
+        "selp.b32 %4, v, %4, p;\n"
+        "selp.b32 %3, %3, v, p;\n"
+        "}\n"
+        : "+r"(c), "+r"(qa), "+r"(qb), "+r"(xa), "+r"(yb), "+r"(lastb) : : "memory");
+  }
+}
+
+// merge-path count of one staged pair by a group of G warps (thread gt of 32*G); sA/sB = shared byte
+// address of the first real element.  Thread t owns the S = 2L merged positions [tS, (t+1)S) and walks
+// them with TWO chains at once -- forward from its own merge-path split for L steps and backward from
+// its right neighbour's split (one shuffle away) for L steps -- so that two independent
+// LDS -> compare -> select chains are in flight per thread for ONE diagonal search per thread.
+// Sentinels make every step branch-free and bounds-check-free (the stage reserves the room):
+//   A[-1] = -1, B[-1] = -2        an exhausted backward side loses every comparison;
+//   A[na] = kVidMax, B[nb..nb+L] = kVidMax-1   likewise forward; the run of L+1 words behind B also is the
+//                                 virtual tail [n, 32*G*S) that the threads past the end walk harmlessly.
+// Every thread stores the sentinels it may read itself, so no barrier separates stores from reads.
+// L is odd: the first probes of the 32 lanes' diagonal searches then fall into distinct banks.
+template <int G, bool PRED>
+__device__ __forceinline__ uint32_t merge_path_count(uint32_t sA, int na, uint32_t sB, int nb, int gt) {
   const int n = na + nb;
-  const int L = (n + 63) >> 6;
-  int dg[2], lo[2], hi[2];
-  #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    dg[h] = min((2 * lane + h) * L, n);
-    lo[h] = max(0, dg[h] - nb); hi[h] = min(dg[h], na);
+  const int L = ((n + 64 * G - 1) / (64 * G)) | 1;
+  const int S = 2 * L;
+  const int d0 = min(gt * S, n), dn = (gt + 1) * S;
+  sts_i32(sA - 4u, -1); sts_i32(sA + 4u * uint32_t(na), kVidMax);
+  sts_i32(sB - 4u, -2); sts_i32(sB + 4u * uint32_t(nb), kVidMax - 1);
+  if (dn > n)
+    for (int k = 1; k <= L; k++) sts_i32(sB + 4u * uint32_t(nb + k), kVidMax - 1);
+  const int i0 = merge_path_split(sA, sB, d0, max(0, d0 - nb), min(d0, na));
+  int i1 = __shfl_down_sync(kFullMask, i0, 1), j1;
+  if ((gt & 31) == 31) {                                      // right neighbour sits in the next warp (or nowhere)
+    if (G == 1 || gt == 32 * G - 1 || dn >= n) i1 = na;
+    else i1 = merge_path_split(sA, sB, dn, max(0, dn - nb), min(dn, na));
   }
-  while (lo[0] < hi[0] || lo[1] < hi[1]) {                 // diagonal searches; a goes first on ties
-    #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const bool live = lo[h] < hi[h];
-      const int mid = (lo[h] + hi[h]) >> 1;
-      const vidType av = lds_i32(sA + 4u * mid);                              // mid <= na: sentinel slot at worst
-      const vidType bv = lds_i32(sB + 4u * max(dg[h] - 1 - mid, 0));
-      const bool up = av <= bv;
-      lo[h] = live && up ? mid + 1 : lo[h];
-      hi[h] = live && !up ? mid : hi[h];
-    }
-  }
-  int i[2], j[2]; vidType x[2], y[2];
-  #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    i[h] = lo[h]; j[h] = dg[h] - lo[h];
-    x[h] = lds_i32(sA + 4u * i[h]); y[h] = lds_i32(sB + 4u * j[h]);
-  }
+  if (dn > n) { i1 = na; j1 = nb + min(dn - n, L); }          // ends in the virtual tail
+  else j1 = dn - i1;
+  uint32_t pa = sA + 4u * uint32_t(i0), pb = sB + 4u * uint32_t(d0 - i0);
+  uint32_t qa = sA + 4u * uint32_t(i1) - 4u, qb = sB + 4u * uint32_t(j1) - 4u;
+  vidType x = lds_i32(pa), y = lds_i32(pb), xa = lds_i32(qa), yb = lds_i32(qb);
+  vidType lastb = lds_i32(qb + 4u);                          // the b right behind this thread's range
   uint32_t c = 0;
-  for (int s = 0; s < L; s++) {                            // branch-free: advance the smaller head, reload it
-    #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const bool ta = x[h] <= y[h];
-      c += uint32_t(x[h] == y[h]);
-      i[h] += ta;
-      j[h] = min(j[h] + !ta, nb);                          // only b can run past its sentinel
-      const vidType v = lds_i32(ta ? sA + 4u * i[h] : sB + 4u * j[h]);
-      x[h] = ta ? v : x[h];
-      y[h] = ta ? y[h] : v;
-    }
+  #pragma unroll 2
+  for (int s = 0; s < L; s++) {
+    merge_step_fwd<PRED>(c, pa, pb, x, y);
+    merge_step_bwd<PRED>(c, qa, qb, xa, yb, lastb);
   }
   return c;
 }
 
-__device__ __forceinline__ uint32_t staged_search_count(uint32_t sK, int nk, uint32_t sS, int ns, int lane) {
+// keys K (the shorter list) searched in S, both staged; 64 keys per warp iteration (two independent
+// branch-free binary searches per lane), the lower bound carried forward from block to block.  The G
+// warps of a group take key blocks round-robin.
+template <int G>
+__device__ __forceinline__ uint32_t staged_search_count(uint32_t sK, int nk, uint32_t sS, int ns, int gt) {
+  const int lane = gt & 31;
   uint32_t c = 0;
   int lo = 0;                                               // all keys from here on are >= S[lo-1]
-  for (int base = 0; base < nk; base += 64) {
+  for (int base = 64 * (gt >> 5); base < nk; base += 64 * G) {
     const int i0 = base + lane, i1 = i0 + 32;
     const vidType k0 = i0 < nk ? lds_i32(sK + 4u * i0) : kVidMax;
     const vidType k1 = i1 < nk ? lds_i32(sK + 4u * i1) : kVidMax;
@@ -170,139 +271,194 @@ batch_gallop_kernel(const vidType *__restrict__ pool, const int64_t *__restrict_
 // ---- the TMA pipeline shared by MERGE and GALLOP -------------------------------------------------------
 // Pairs are first binned by staged size (batch_classify_kernel: warp-aggregated appends into one index
 // list per class), so that every pipeline instance works through a dense list with a stage size that
-// fits its pairs.  A warp then owns blocks of 32 list entries.  The 32 pair descriptors of a block are
-// loaded lane-parallel (one round trip to HBM per 32 pairs, the NEXT block prefetched while the current
-// one is processed) and handed out by shuffles; the lists of pair k+NSTAGE-1 are in flight as 1-D TMA
-// bulk copies (cp.async.bulk -> mbarrier complete_tx) while pair k is intersected out of shared memory.
-// Nothing on the per-pair critical path waits for a dependent global load.
-//   CORE 0: merge-path diagonal split + per-lane serial merge            (GM_ALGO_MERGE)
-//   CORE 1: 64 keys per iteration, branch-free binary search carried forward chunk to chunk (GM_ALGO_GALLOP)
-constexpr int kPipeClasses = 3;
-__host__ __device__ constexpr int pipe_stage_elems(int c) { return c == 0 ? 1024 : c == 1 ? 2048 : 4608; }
+// fits its pairs and a thread-group size that fits the stage: one warp per pair up to 1024 staged
+// elements, two warps up to 2048, four up to 4608.  A group owns a ring of NSTAGE stages.  Its first
+// warp is also the feeder: it loads the descriptors of 32 list entries lane-parallel (one round trip to
+// HBM per 32 pairs, the NEXT block prefetched while the current one is consumed), and for pair k+NSTAGE-1
+// the lane that holds the descriptor posts the two 1-D TMA bulk copies (cp.async.bulk -> mbarrier
+// complete_tx) plus a 16-byte stage descriptor, while every warp of the group intersects pair k out of
+// shared memory.  Nothing on the per-pair critical path waits for a dependent global load, and the only
+// group-wide synchronisation per pair is the one that frees its stage.
+//   CORE 0: merge-path diagonal split + per-thread serial merge          (GM_ALGO_MERGE)
+//   CORE 1: 64 keys per iteration, branch-free binary search carried forward block to block (GM_ALGO_GALLOP)
+//   CORE 2: per pair whichever of the two costs fewer instructions                                  (GM_ALGO_AUTO)
+constexpr int kPipeClasses = 4;
+__host__ __device__ constexpr int pipe_stage_elems(int c) { return c == 0 ? 512 : c == 1 ? 1024 : c == 2 ? 2048 : 4608; }
 
-__global__ void __launch_bounds__(256)
+// 1024-thread blocks: class counts are aggregated in shared memory first, so the five global counters
+// see one atomic per block and class instead of one per warp (that serialisation cost 83 us per million
+// pairs in the first version).
+__global__ void __launch_bounds__(1024)
 batch_classify_kernel(const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
                       const int64_t *__restrict__ b_off, const int32_t *__restrict__ b_len, int64_t npairs,
                       int32_t *__restrict__ lists, unsigned *__restrict__ counts) {
+  __shared__ unsigned s_cnt[kPipeClasses + 1], s_base[kPipeClasses + 1];
   const int lane = threadIdx.x & 31;
-  for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) & ~31ll; base < npairs;
-       base += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t p = base + lane;
+  for (int64_t base = int64_t(blockIdx.x) * blockDim.x; base < npairs; base += int64_t(gridDim.x) * blockDim.x) {
+    if (threadIdx.x <= kPipeClasses) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t p = base + threadIdx.x;
     int cls = -1;
     if (p < npairs) {
       PairDesc d = describe_pair(a_off[p], a_len[p], b_off[p], b_len[p]);
-      const int elems = (d.units_a + d.units_b + 2) * 4;        // + one sentinel unit behind each list
-      cls = elems <= pipe_stage_elems(0) ? 0 : elems <= pipe_stage_elems(1) ? 1 : elems <= pipe_stage_elems(2) ? 2 : 3;
+      const int64_t elems = (int64_t(d.units_a) + d.units_b + 2) * 4;   // + one sentinel unit behind each list
+      cls = kPipeClasses;
+      #pragma unroll
+      for (int c = kPipeClasses - 1; c >= 0; c--) if (elems <= pipe_stage_elems(c)) cls = c;
     }
+    unsigned woff = 0, rank = 0;
     #pragma unroll
     for (int c = 0; c <= kPipeClasses; c++) {
       const unsigned m = __ballot_sync(kFullMask, cls == c);
       if (m == 0) continue;
       unsigned b = 0;
-      if (lane == __ffs(m) - 1) b = atomicAdd(&counts[c], unsigned(__popc(m)));
+      if (lane == __ffs(m) - 1) b = atomicAdd(&s_cnt[c], unsigned(__popc(m)));
       b = __shfl_sync(kFullMask, b, __ffs(m) - 1);
-      if (cls == c) lists[int64_t(c) * npairs + b + __popc(m & ((1u << lane) - 1))] = int32_t(p);
+      if (cls == c) { woff = b; rank = __popc(m & ((1u << lane) - 1)); }
     }
+    __syncthreads();
+    if (threadIdx.x <= kPipeClasses && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (cls >= 0) lists[int64_t(cls) * npairs + s_base[cls] + woff + rank] = int32_t(p);
+    __syncthreads();
   }
 }
 
-template <int STAGE, int NSTAGE, int WARPS>
+// G warps per group, NG groups per CTA.  A stage holds [pad unit | a | gap unit | b | tail]: the pad and
+// the gap take the front sentinels, the tail the run of L+1 end sentinels (merge_path_count).
+template <int STAGE, int NSTAGE, int G, int NG>
 struct PipeCfg {
-  static constexpr int kDescInts = 8;
-  static constexpr int kSmemBytes = WARPS * NSTAGE * STAGE * 4 + WARPS * NSTAGE * 8 + WARPS * NSTAGE * kDescInts * 4;
+  static constexpr int kThreads = G * NG * 32;
+  static constexpr int kTail = (((STAGE + 64 * G - 1) / (64 * G) | 1) + 1 + 3) & ~3;
+  static constexpr int kStageWords = 4 + STAGE + kTail;
+  static constexpr int kGroupBytes = NSTAGE * kStageWords * 4 + NSTAGE * 16 /*descriptors*/ + NSTAGE * 8 /*mbarriers*/ + NSTAGE * 8 /*counters*/;
+  static constexpr int kSmemBytes = NG * kGroupBytes;
+  static_assert(kGroupBytes % 16 == 0, "stages must stay 16-byte aligned");
 };
 
 struct PairRegs { int64_t ao, bo; int32_t al, bl, p; };
 
-template <int STAGE, int NSTAGE, int WARPS, int CORE>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int G>
+__device__ __forceinline__ void group_barrier(int grp) {
+  if (G == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(G * 32) : "memory");
+}
+
+template <int STAGE, int NSTAGE, int G, int NG, int CORE, bool PRED>
+__global__ void __launch_bounds__(G * NG * 32)
 batch_pipe_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
                   const int64_t *__restrict__ b_off, const int32_t *__restrict__ b_len,
                   const int32_t *__restrict__ plist, const unsigned *__restrict__ pcount,
                   unsigned long long *__restrict__ out) {
-  using Cfg = PipeCfg<STAGE, NSTAGE, WARPS>;
+  using Cfg = PipeCfg<STAGE, NSTAGE, G, NG>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  vidType *stage0 = reinterpret_cast<vidType *>(smem_raw) + size_t(w) * NSTAGE * STAGE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + size_t(WARPS) * NSTAGE * STAGE * 4) + w * NSTAGE;
-  int *desc = reinterpret_cast<int *>(smem_raw + size_t(WARPS) * NSTAGE * STAGE * 4 + size_t(WARPS) * NSTAGE * 8) + w * NSTAGE * Cfg::kDescInts;
-  if (lane == 0) { for (int i = 0; i < NSTAGE; i++) mbar_init(&bars[i], 1); fence_barrier_init(); }
-  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  const int grp = threadIdx.x / (32 * G), gt = threadIdx.x % (32 * G);
+  const bool feeder = gt < 32;                               // first warp of the group
+  unsigned char *gbase = smem_raw + size_t(grp) * Cfg::kGroupBytes;
+  constexpr int SW = Cfg::kStageWords;
+  const uint32_t sbase = smem_u32(gbase) + 16u;              // stages; +16: the pad unit in front of list a
+  const uint32_t sdesc = sbase - 16u + NSTAGE * SW * 4;      // int4 per stage: {pair, na | nb << 16, head_a | head_b << 2 | units_a << 4, -}
+  uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + NSTAGE * SW * 4 + NSTAGE * 16);
+  unsigned *cnts = reinterpret_cast<unsigned *>(gbase + NSTAGE * SW * 4 + NSTAGE * 24);
+  if (gt == 0) {
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&bars[i], 1); cnts[i] = 0; }
+    fence_barrier_init();
+  }
+  group_barrier<G>(grp);
 
-  const uint32_t sbase = smem_u32(stage0);
   const int64_t nlist = int64_t(*pcount);
-  const int64_t nblocks = (nlist + 31) >> 5;
-  const int64_t nw = int64_t(gridDim.x) * WARPS;
-  // lane-parallel load of the descriptors of list block `bid` (lane l <- entry 32*bid + l)
+  const int64_t ngroups = int64_t(gridDim.x) * NG;
+  // entries per descriptor block: 32 when the list is long, fewer when that would leave groups idle
+  const int blk = int(max(int64_t(1), min(int64_t(32), nlist / (ngroups * 2))));
+  const int64_t nblocks = (nlist + blk - 1) / blk;
+  // lane-parallel load of the descriptors of list block `bid` (lane l <- entry blk*bid + l)
   auto load_block = [&](int64_t bid, PairRegs &r) -> int {
     r.p = -1; r.al = r.bl = 0; r.ao = r.bo = 0;
     if (bid >= nblocks) return 0;
-    const int64_t e = (bid << 5) + lane;
-    if (e < nlist) {
+    const int64_t e = bid * blk + lane;
+    if (lane < blk && e < nlist) {
       r.p = plist[e];
       r.ao = a_off[r.p]; r.al = a_len[r.p]; r.bo = b_off[r.p]; r.bl = b_len[r.p];
     }
-    const int64_t left = nlist - (bid << 5);
-    return left < 32 ? int(left) : 32;
+    const int64_t left = nlist - bid * blk;
+    return left < blk ? int(left) : blk;
   };
   PairRegs cur, nxt;
-  int64_t nbid = int64_t(blockIdx.x) * WARPS + w;
-  int ccnt = load_block(nbid, cur); nbid += nw;
-  int ncnt = load_block(nbid, nxt); nbid += nw;
-  int ci = 0;
-  // start the copies of this warp's next pair into stage s; false when the warp has run out of pairs
-  auto fetch = [&](int s) -> bool {
+  int ccnt = 0, ncnt = 0, ci = 0;
+  int64_t nbid = int64_t(blockIdx.x) * NG + grp;
+  if (feeder) {
+    ccnt = load_block(nbid, cur); nbid += ngroups;
+    ncnt = load_block(nbid, nxt); nbid += ngroups;
+  }
+  // feeder warp: post the copies of the group's next pair into stage s, or the end marker
+  auto feed = [&](int s) {
     if (ci >= ccnt) {
-      if (ncnt == 0) return false;
+      if (ncnt == 0) {                                        // out of pairs
+        if (lane == 0) {
+          asm volatile("st.shared.v4.s32 [%0], {%1, %1, %1, %1};" ::"r"(sdesc + 16u * s), "r"(-1) : "memory");
+          mbar_arrive(&bars[s]);
+        }
+        return;
+      }
       cur = nxt; ccnt = ncnt; ci = 0;
-      ncnt = load_block(nbid, nxt); nbid += nw;              // prefetch: consumed 32 pairs from now
+      ncnt = load_block(nbid, nxt); nbid += ngroups;         // prefetch: consumed one block from now
     }
-    const int64_t ao = __shfl_sync(kFullMask, cur.ao, ci), bo = __shfl_sync(kFullMask, cur.bo, ci);
-    const int na = __shfl_sync(kFullMask, cur.al, ci), nb = __shfl_sync(kFullMask, cur.bl, ci);
-    const int p = __shfl_sync(kFullMask, cur.p, ci);
-    ci++;
-    if (lane == 0) {
-      PairDesc d = describe_pair(ao, na, bo, nb);
-      int *ds = desc + s * Cfg::kDescInts;
-      ds[0] = p; ds[1] = d.na; ds[2] = d.nb; ds[3] = d.head_a; ds[4] = d.head_b; ds[5] = d.units_a;
+    if (lane == ci) {
+      const PairDesc d = describe_pair(cur.ao, cur.al, cur.bo, cur.bl);
+      asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(sdesc + 16u * s), "r"(cur.p), "r"(d.na | (d.nb << 16)),
+                   "r"(d.head_a | (d.head_b << 2) | (d.units_a << 4)), "r"(0) : "memory");
       const int units = d.units_a + d.units_b;
       if (units > 0) {
-        vidType *dst = stage0 + s * STAGE;
+        const uint32_t dst = sbase + uint32_t(s) * (SW * 4);
+        // (the stage's last users fenced their sentinel stores towards the async proxy themselves; a
+        // fence here is a MEMBAR that would also wait for this warp's descriptor prefetch and result store)
         mbar_expect_tx(&bars[s], uint32_t(units) * 16u);
-        if (d.units_a) tma_bulk_g2s(dst, pool + (ao - d.head_a), uint32_t(d.units_a) * 16u, &bars[s]);
-        if (d.units_b) tma_bulk_g2s(dst + (d.units_a + 1) * 4, pool + (bo - d.head_b), uint32_t(d.units_b) * 16u, &bars[s]);
+        if (d.units_a) tma_bulk_g2s_addr(dst, pool + (cur.ao - d.head_a), uint32_t(d.units_a) * 16u, &bars[s]);
+        if (d.units_b) tma_bulk_g2s_addr(dst + uint32_t(d.units_a + 1) * 16u, pool + (cur.bo - d.head_b), uint32_t(d.units_b) * 16u, &bars[s]);
+      } else {
+        mbar_arrive(&bars[s]);
       }
     }
-    return true;
+    ci++;
   };
 
+  if (feeder) for (int s = 0; s < NSTAGE - 1; s++) feed(s);
   uint32_t phases = 0;                                       // bit s = parity to wait for on stage s
-  int inflight = 0, head = 0, tail = 0;
-  for (; inflight < NSTAGE - 1; inflight++) { if (!fetch(tail)) break; tail = (tail + 1) % NSTAGE; }
-  while (inflight > 0) {
-    if (fetch(tail)) { tail = (tail + 1) % NSTAGE; inflight++; }   // refill the stage freed last iteration
-    __syncwarp();                                                   // descriptors visible to all lanes
-    const int *ds = desc + head * Cfg::kDescInts;
-    const int p = ds[0], na = ds[1], nb = ds[2], head_a = ds[3], head_b = ds[4], units_a = ds[5];
+  for (int head = 0, tail = NSTAGE - 1;; head = head + 1 == NSTAGE ? 0 : head + 1, tail = tail + 1 == NSTAGE ? 0 : tail + 1) {
+    if (feeder) feed(tail);                                  // the stage freed by the previous iteration
+    mbar_wait(&bars[head], (phases >> head) & 1u); phases ^= 1u << head;
+    int dp, dn, dh, dz;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(dp), "=r"(dn), "=r"(dh), "=r"(dz) : "r"(sdesc + 16u * head) : "memory");
+    if (dp < 0) break;                                       // group-uniform
+    const int na = dn & 0xffff, nb = dn >> 16, head_a = dh & 3, head_b = (dh >> 2) & 3, units_a = dh >> 4;
+    const uint32_t sA = sbase + 4u * uint32_t(head * SW + head_a);
+    const uint32_t sB = sbase + 4u * uint32_t(head * SW + (units_a + 1) * 4 + head_b);
     uint32_t c = 0;
-    if (na > 0 || nb > 0) { mbar_wait(&bars[head], (phases >> head) & 1u); phases ^= 1u << head; }
-    const uint32_t sA = sbase + 4u * uint32_t(head * STAGE + head_a);
-    const uint32_t sB = sbase + 4u * uint32_t(head * STAGE + (units_a + 1) * 4 + head_b);
-    if (CORE == 0 && na > 0 && nb > 0) {                            // sentinels behind both lists
-      if (lane == 0) {
-        stage0[head * STAGE + head_a + na] = kVidMax;
-        stage0[head * STAGE + (units_a + 1) * 4 + head_b + nb] = kVidMax - 1;
-      }
-      __syncwarp();
-    }
     if (na > 0 && nb > 0) {
-      if (CORE == 0) c = merge_path_count(sA, na, sB, nb, lane);
-      else c = na <= nb ? staged_search_count(sA, na, sB, nb, lane) : staged_search_count(sB, nb, sA, na, lane);
+      bool merge = CORE == 0;
+      if (CORE == 2) {                                       // per-pair choice by instruction-count model
+        const int nk = min(na, nb), ns = max(na, nb);
+        const int search_cost = ((nk + 64 * G - 1) / (64 * G)) * (9 * (32 - __clz(ns)) + 15);
+        const int merge_cost = 170 + 15 * ((na + nb + 64 * G - 1) / (64 * G));
+        merge = merge_cost < search_cost;
+      }
+      if (merge) {
+        c = merge_path_count<G, PRED>(sA, na, sB, nb, gt);
+        fence_proxy_async();                                 // order the sentinel stores before the stage's next bulk copy
+      } else {
+        c = na <= nb ? staged_search_count<G>(sA, na, sB, nb, gt) : staged_search_count<G>(sB, nb, sA, na, gt);
+      }
     }
-    c = warp_reduce(c);
-    if (lane == 0) out[p] = c;
-    __syncwarp();                                                   // stage `head` may be overwritten now
-    head = (head + 1) % NSTAGE; inflight--;
+    c = __reduce_add_sync(kFullMask, c);
+    if (G == 1) {
+      if (lane == 0) out[dp] = c;
+      __syncwarp();                                          // stage `head` may be overwritten now
+    } else {
+      if (lane == 0 && c) atomicAdd(&cnts[head], c);
+      group_barrier<G>(grp);                                 // all warps done with the stage, counter complete
+      if (gt == 0) { out[dp] = cnts[head]; cnts[head] = 0; } // next use of cnts[head] is >= one barrier away
+    }
   }
 }
 
@@ -324,25 +480,31 @@ batch_list_bsearch_kernel(const vidType *__restrict__ pool, const int64_t *__res
   }
 }
 
-template <int STAGE, int NSTAGE, int WARPS, int CORE>
+template <int STAGE, int NSTAGE, int G, int NG, int CORE, bool PRED>
 static int launch_pipe(const vidType *pool, const int64_t *a_off, const int32_t *a_len, const int64_t *b_off,
                        const int32_t *b_len, const int32_t *plist, const unsigned *pcount, int64_t npairs,
                        unsigned long long *out, int sms, cudaStream_t s) {
-  using Cfg = PipeCfg<STAGE, NSTAGE, WARPS>;
-  auto k = batch_pipe_kernel<STAGE, NSTAGE, WARPS, CORE>;
+  using Cfg = PipeCfg<STAGE, NSTAGE, G, NG>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "pipeline class does not fit shared memory");
+  auto k = batch_pipe_kernel<STAGE, NSTAGE, G, NG, CORE, PRED>;
   static int occ = -1;                                       // per instantiation
   if (occ < 0) {
     GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, WARPS * 32, Cfg::kSmemBytes));
+    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, Cfg::kThreads, Cfg::kSmemBytes));
     if (occ < 1) occ = 1;
   }
   // the list length lives on the device; size the persistent grid by the upper bound npairs
-  int grid = int(std::min<int64_t>((npairs + 32 * WARPS - 1) / (32 * WARPS), int64_t(occ) * sms));
-  k<<<grid, WARPS * 32, Cfg::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, plist, pcount, out);
+  int grid = int(std::min<int64_t>((npairs + NG - 1) / NG, int64_t(occ) * sms));
+  k<<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, plist, pcount, out);
   return GM_OK;
 }
 
-template <int CORE>
+// Tuning knobs (gm_set_option "batch.*"): warps per pair of the two large classes and the reload
+// flavour of the merge step.  Defaults are the measured best (profiles/).
+struct BatchTuning { int g2048 = 1, g4608 = 2, pred = 1, ns2048 = 2, ns1024 = 2; };
+inline BatchTuning &batch_tuning() { static BatchTuning t; return t; }
+
+template <int CORE, bool PRED>
 static int launch_pipeline(const vidType *pool, const int64_t *a_off, const int32_t *a_len, const int64_t *b_off,
                            const int32_t *b_len, int64_t npairs, unsigned long long *out, int sms, cudaStream_t s) {
   if (npairs >= (int64_t(1) << 31)) { set_error("gm_intersect_batch: more than 2^31 pairs per call"); return GM_EUNSUPPORTED; }
@@ -350,18 +512,31 @@ static int launch_pipeline(const vidType *pool, const int64_t *a_off, const int3
   GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&lists), sizeof(int32_t) * size_t(npairs) * (kPipeClasses + 1), s));
   GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&counts), sizeof(unsigned) * (kPipeClasses + 1), s));
   GM_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * (kPipeClasses + 1), s));
-  int cgrid = int(std::min<int64_t>((npairs + 255) / 256, int64_t(sms) * 8));
-  batch_classify_kernel<<<cgrid, 256, 0, s>>>(a_off, a_len, b_off, b_len, npairs, lists, counts);
+  int cgrid = int(std::min<int64_t>((npairs + 1023) / 1024, int64_t(sms) * 2));
+  batch_classify_kernel<<<cgrid, 1024, 0, s>>>(a_off, a_len, b_off, b_len, npairs, lists, counts);
+  const BatchTuning &t = batch_tuning();
   int rc = GM_OK;
-  if (rc == GM_OK) rc = launch_pipe<pipe_stage_elems(0), 3, 4, CORE>(pool, a_off, a_len, b_off, b_len, lists, counts + 0, npairs, out, sms, s);
-  if (rc == GM_OK) rc = launch_pipe<pipe_stage_elems(1), 2, 4, CORE>(pool, a_off, a_len, b_off, b_len, lists + npairs, counts + 1, npairs, out, sms, s);
-  if (rc == GM_OK) rc = launch_pipe<pipe_stage_elems(2), 2, 3, CORE>(pool, a_off, a_len, b_off, b_len, lists + 2 * npairs, counts + 2, npairs, out, sms, s);
+#define GM_PIPE(CLS, NST, G, NG) \
+  launch_pipe<pipe_stage_elems(CLS), NST, G, NG, CORE, PRED>(pool, a_off, a_len, b_off, b_len, lists + int64_t(CLS) * npairs, counts + CLS, npairs, out, sms, s)
+  if (rc == GM_OK) rc = t.g2048 == 1 ? (t.ns2048 == 2 ? GM_PIPE(2, 2, 1, 4) : GM_PIPE(2, 3, 1, 4))
+                                     : (t.ns2048 == 2 ? GM_PIPE(2, 2, 2, 2) : GM_PIPE(2, 3, 2, 2));
+  if (rc == GM_OK) rc = t.ns1024 == 2 ? GM_PIPE(1, 2, 1, 4) : GM_PIPE(1, 3, 1, 4);
+  if (rc == GM_OK) rc = t.g4608 == 1 ? GM_PIPE(3, 2, 1, 2) : t.g4608 == 2 ? GM_PIPE(3, 2, 2, 1) : GM_PIPE(3, 2, 4, 1);
+  if (rc == GM_OK) rc = GM_PIPE(0, 4, 1, 8);
+#undef GM_PIPE
   if (rc == GM_OK) {
     int grid = int(std::min<int64_t>((npairs + 7) / 8, int64_t(sms) * 8));
-    batch_list_bsearch_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, lists + 3 * npairs, counts + 3, out);
+    batch_list_bsearch_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, lists + int64_t(kPipeClasses) * npairs, counts + kPipeClasses, out);
   }
   cudaFreeAsync(lists, s); cudaFreeAsync(counts, s);
   return rc;
+}
+
+template <int CORE>
+static int launch_pipeline(const vidType *pool, const int64_t *a_off, const int32_t *a_len, const int64_t *b_off,
+                           const int32_t *b_len, int64_t npairs, unsigned long long *out, int sms, cudaStream_t s) {
+  return batch_tuning().pred ? launch_pipeline<CORE, true>(pool, a_off, a_len, b_off, b_len, npairs, out, sms, s)
+                             : launch_pipeline<CORE, false>(pool, a_off, a_len, b_off, b_len, npairs, out, sms, s);
 }
 
 // ---- HASH -------------------------------------------------------------------------------------
@@ -421,7 +596,9 @@ static int launch_batch_variant(int algo, const vidType *pool, const int64_t *a_
                                 const int64_t *b_off, const int32_t *b_len, int64_t npairs,
                                 unsigned long long *out, int sms, cudaStream_t s) {
   const bool aligned = (reinterpret_cast<uintptr_t>(pool) & 15) == 0;          // TMA bulk copies need it
-  if (algo == GM_ALGO_MERGE) {
+  if (algo == GM_ALGO_AUTO) {
+    GM_TRY(launch_pipeline<2>(pool, a_off, a_len, b_off, b_len, npairs, out, sms, s));
+  } else if (algo == GM_ALGO_MERGE) {
     if (!aligned) { set_error("GM_ALGO_MERGE needs a 16-byte aligned pool (TMA bulk copy)"); return GM_EINVAL; }
     GM_TRY(launch_pipeline<0>(pool, a_off, a_len, b_off, b_len, npairs, out, sms, s));
   } else if (algo == GM_ALGO_GALLOP) {

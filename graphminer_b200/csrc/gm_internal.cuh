@@ -50,6 +50,7 @@ struct Options {
   int chunk = 0;   // 0 = default per kernel
 };
 Options &options();
+int set_batch_option(const char *key, int value);   // batch.cu: "batch.g2048", "batch.g4608", "batch.pred_lds"
 
 }  // namespace gm
 

@@ -428,6 +428,8 @@ int gm_set_option(const char *key, const char *value) {
     options().clique_algo = v;
   } else if (k == "sched.chunk") {
     options().chunk = atoi(value);
+  } else if (k.rfind("batch.", 0) == 0) {
+    return set_batch_option(k.c_str(), atoi(value));
   } else { set_error("unknown option '%s'", key); return GM_EINVAL; }
   return GM_OK;
 }

@@ -136,3 +136,39 @@ def test_streaming_checksum_at_scale():
         got = capi.intersect_batch(pool, ao, ln, bo, ln, op="intersect_num", algo=algo)
         torch.cuda.synchronize()
         assert torch.equal(got, want), algo
+
+
+def test_pipeline_all_size_classes_at_scale():
+    """Every stage class of the TMA pipeline (one-, two- and four-warp groups, the over-long fallback,
+    empty lists, unaligned starts) with enough pairs that every group wraps its stage ring many times:
+    merge / gallop / auto must reproduce the operator-API counts pair by pair."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    npairs = 60000
+    # lengths: mixture of tiny, small, medium, large and a few over-long lists; some empty
+    cls = torch.randint(0, 6, (npairs, 2), device=dev, generator=g)
+    hi = torch.tensor([1, 40, 300, 900, 2200, 5200], device=dev)[cls]
+    ln = (torch.rand((npairs, 2), device=dev, generator=g) * hi.float()).long()
+    gap = torch.randint(0, 4, (npairs, 2), device=dev, generator=g)              # unaligned list starts
+    seg = (ln + gap).reshape(-1)
+    off = torch.zeros(seg.numel() + 1, dtype=torch.int64, device=dev); torch.cumsum(seg, 0, out=off[1:])
+    total = int(off[-1])
+    starts = (off[:-1] + gap.reshape(-1))
+    # strictly increasing values inside every list: global cumsum of gaps in {1,2,3}, rebased per list so
+    # that a and b draw from the same range and intersect in about a third of their elements
+    vals = torch.cumsum(torch.randint(1, 4, (total + 8,), device=dev, generator=g, dtype=torch.int64), 0)
+    seg_id = torch.repeat_interleave(torch.arange(seg.numel(), device=dev), seg)
+    base = vals[off[:-1]][seg_id]
+    pool = torch.full((total + 8,), -7, dtype=torch.int32, device=dev)
+    pool[:total] = (vals[:total] - base).to(torch.int32)
+    ao, bo = starts[0::2].contiguous(), starts[1::2].contiguous()
+    al, bl = ln[:, 0].to(torch.int32).contiguous(), ln[:, 1].to(torch.int32).contiguous()
+    want = capi.intersect_batch(pool, ao, al, bo, bl, op="intersect_num", algo="bsearch")
+    torch.cuda.synchronize()
+    assert int(want.sum()) > 0
+    for algo in ("merge", "gallop", "auto", "hash"):
+        got = capi.intersect_batch(pool, ao, al, bo, bl, op="intersect_num", algo=algo)
+        torch.cuda.synchronize()
+        bad = torch.nonzero(got != want)
+        assert bad.numel() == 0, (algo, bad[:5].tolist(), got[bad[:5, 0]].tolist(), want[bad[:5, 0]].tolist(),
+                                  al[bad[:5, 0]].tolist(), bl[bad[:5, 0]].tolist())

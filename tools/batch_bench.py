@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--skew", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--json", default="")
+    ap.add_argument("--sweep", default="", help="';'-separated sets of ','-separated gm_set_option key=value pairs; every set is timed")
     a = ap.parse_args()
     dev = "cuda:0"
     pool, ao, al, bo, bl = make_batch(a.scale, a.gb, dev, skew=a.skew)
@@ -78,23 +79,28 @@ def main():
     print(f"pairs={ao.numel()} elements={nel} ({nel * 4 / 1e9:.2f} GB algorithmic) avg |a|={float(al.float().mean()):.1f} "
           f"|b|={float(bl.float().mean()):.1f} max={int(torch.maximum(al, bl).max())} pool={pool.numel() * 4 / 1e9:.2f} GB", flush=True)
     res, ref = {}, None
-    for algo in a.algos.split(","):
-        out = capi.intersect_batch(pool, ao, al, bo, bl, algo=algo); torch.cuda.synchronize()     # warm-up
-        if ref is None:
-            ref = out
-        else:
-            assert torch.equal(out, ref), f"{algo} disagrees with {a.algos.split(',')[0]}"
-        # back-to-back launches between one pair of events: host-side launch overhead overlaps the
-        # previous kernel, so the figure is device time per call
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.reps):
-            capi.intersect_batch(pool, ao, al, bo, bl, algo=algo)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / a.reps
-        gbps = nel * 4 / ms / 1e6
-        res[algo] = dict(ms=ms, alg_GBps=gbps, frac_of_peak=gbps / peak, matches=int(ref.sum()))
-        print(f"  {algo:8s} {ms:9.3f} ms  {gbps:8.1f} GB/s algorithmic = {gbps / peak * 100:5.1f}% of {peak:.0f} GB/s measured copy peak", flush=True)
+    for oset in (a.sweep.split(";") if a.sweep else [""]):
+        for kv in filter(None, oset.split(",")):
+            k, v = kv.split("="); capi.set_option(k, v)
+        if oset:
+            print(f" [{oset}]", flush=True)
+        for algo in a.algos.split(","):
+            out = capi.intersect_batch(pool, ao, al, bo, bl, algo=algo); torch.cuda.synchronize()     # warm-up
+            if ref is None:
+                ref = out
+            else:
+                assert torch.equal(out, ref), f"{algo} disagrees with {a.algos.split(',')[0]}"
+            # back-to-back launches between one pair of events: host-side launch overhead overlaps the
+            # previous kernel, so the figure is device time per call
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.reps):
+                capi.intersect_batch(pool, ao, al, bo, bl, algo=algo)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.reps
+            gbps = nel * 4 / ms / 1e6
+            res[(oset + ":" if oset else "") + algo] = dict(ms=ms, alg_GBps=gbps, frac_of_peak=gbps / peak, matches=int(ref.sum()))
+            print(f"  {algo:8s} {ms:9.3f} ms  {gbps:8.1f} GB/s algorithmic = {gbps / peak * 100:5.1f}% of {peak:.0f} GB/s measured copy peak", flush=True)
     if a.json:
         json.dump(dict(scale=a.scale, pairs=ao.numel(), elements=nel, skew=a.skew, peak_gbs=peak, results=res), open(a.json, "w"), indent=1)
 
