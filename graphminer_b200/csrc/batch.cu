@@ -55,6 +55,7 @@ int set_batch_option(const char *key, int value) {
   if (k == "batch.g2048" && (value == 1 || value == 2)) t.g2048 = value;
   else if (k == "batch.g4608" && (value == 1 || value == 2 || value == 4)) t.g4608 = value;
   else if (k == "batch.pred_lds" && (value == 0 || value == 1)) t.pred = value;
+  else if (k == "batch.ring" && (value == 0 || value == 2048 || value == 2560 || value == 3072 || value == 3584 || value == 4096)) t.ring = value;
   else if (k == "batch.ns2048" && (value == 2 || value == 3)) t.ns2048 = value;
   else if (k == "batch.ns1024" && (value == 2 || value == 3)) t.ns1024 = value;
   else { set_error("bad batch option %s=%d", key, value); return GM_EINVAL; }

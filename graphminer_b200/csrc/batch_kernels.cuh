@@ -91,80 +91,66 @@ __device__ __forceinline__ int merge_path_split(uint32_t sA, uint32_t sB, int d,
   return lo;
 }
 
-// One step of a serial merge chain, in PTX so that the conditional advances stay single predicated
-// instructions (nvcc's selp lowering spends 14 SASS per step).  Two flavours of the reload:
-//   PRED = true : two predicated ld.shared straight into x or y    (7 SASS, two half-populated LDS)
-//   PRED = false: select the address, one ld.shared, two selects    (9 SASS, one LDS -> fewer bank-conflict
-//                 wavefronts; the staged merge is bound by the shared-memory pipe, see profiles/)
-// Forward chain: count a match when the a-side head is consumed, advance the smaller head (a on ties).
+// One step of BOTH serial merge chains of a thread, in PTX so that the conditional advances stay single
+// predicated instructions (nvcc's selp lowering spends 14 SASS per chain step).
+//   forward chain : count a match when the a-side head is consumed, advance the smaller head (a on ties);
+//   backward chain: consume the larger tail (b on ties, since a precedes b in the merged order); a match is
+//                   counted when the a-side tail is consumed and equals the b consumed just before (`lastb`).
+// Two flavours of the reload:
+//   PRED = true : two predicated ld.shared straight into the head registers (7 + 8 SASS, two half-populated LDS)
+//   PRED = false: select the address, one ld.shared, two selects          (9 + 10 SASS, one LDS per chain ->
+//                 fewer bank-conflict wavefronts on the shared-memory pipe)
+// The loads use the old pointer plus an immediate offset so that the pointer update is off the critical path.
 template <bool PRED>
-__device__ __forceinline__ void merge_step_fwd(uint32_t &c, uint32_t &pa, uint32_t &pb, vidType &x, vidType &y) {
+__device__ __forceinline__ void merge_step2(uint32_t &c, uint32_t &pa, uint32_t &pb, vidType &x, vidType &y,
+                                            uint32_t &qa, uint32_t &qb, vidType &xa, vidType &yb, vidType &lastb) {
   if (PRED) {
     asm volatile(
         "{\n"
-        ".reg .pred p, q;\n"
+        ".reg .pred p, q, r, s;\n"
         "setp.le.s32 p, %3, %4;\n"
+        "setp.ge.s32 r, %8, %7;\n"
         "setp.eq.s32 q, %3, %4;\n"
-        "@q add.u32 %0, %0, 1;\n"
+        "setp.eq.and.s32 s, %7, %9, !r;\n"
         "@p ld.shared.s32 %3, [%1+4];\n"
         "@!p ld.shared.s32 %4, [%2+4];\n"
+        "@r mov.b32 %9, %8;\n"
+        "@r ld.shared.s32 %8, [%6+-4];\n"
+        "@!r ld.shared.s32 %7, [%5+-4];\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "@s add.u32 %0, %0, 1;\n"
         "@p add.u32 %1, %1, 4;\n"
         "@!p add.u32 %2, %2, 4;\n"
+        "@r sub.u32 %6, %6, 4;\n"
+        "@!r sub.u32 %5, %5, 4;\n"
         "}\n"
-        : "+r"(c), "+r"(pa), "+r"(pb), "+r"(x), "+r"(y) : : "memory");
+        : "+r"(c), "+r"(pa), "+r"(pb), "+r"(x), "+r"(y), "+r"(qa), "+r"(qb), "+r"(xa), "+r"(yb), "+r"(lastb) : : "memory");
   } else {
     asm volatile(
         "{\n"
-        ".reg .pred p, q;\n"
-        ".reg .b32 t, v;\n"
+        ".reg .pred p, q, r, s;\n"
+        ".reg .b32 t, v, u, w;\n"
         "setp.le.s32 p, %3, %4;\n"
+        "setp.ge.s32 r, %8, %7;\n"
         "setp.eq.s32 q, %3, %4;\n"
-        "@q add.u32 %0, %0, 1;\n"
+        "setp.eq.and.s32 s, %7, %9, !r;\n"
         "selp.b32 t, %1, %2, p;\n"
+        "selp.b32 u, %6, %5, r;\n"
         "ld.shared.s32 v, [t+4];\n"
+        "ld.shared.s32 w, [u+-4];\n"
+        "@r mov.b32 %9, %8;\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "@s add.u32 %0, %0, 1;\n"
         "@p add.u32 %1, %1, 4;\n"
         "@!p add.u32 %2, %2, 4;\n"
+        "@r sub.u32 %6, %6, 4;\n"
+        "@!r sub.u32 %5, %5, 4;\n"
         "selp.b32 %3, v, %3, p;\n"
         "selp.b32 %4, %4, v, p;\n"
+        "selp.b32 %8, w, %8, r;\n"
+        "selp.b32 %7, %7, w, r;\n"
         "}\n"
-        : "+r"(c), "+r"(pa), "+r"(pb), "+r"(x), "+r"(y) : : "memory");
-  }
-}
-// Backward chain: consume the larger tail (b on ties, since a precedes b in the merged order); a match
-// is counted when the a-side tail is consumed and equals the b consumed just before it (`lastb`).
-template <bool PRED>
-__device__ __forceinline__ void merge_step_bwd(uint32_t &c, uint32_t &qa, uint32_t &qb, vidType &xa, vidType &yb, vidType &lastb) {
-  if (PRED) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        "setp.ge.s32 p, %4, %3;\n"
-        "setp.eq.and.s32 q, %3, %5, !p;\n"
-        "@q add.u32 %0, %0, 1;\n"
-        "@p mov.b32 %5, %4;\n"
-        "@p ld.shared.s32 %4, [%2+-4];\n"
-        "@!p ld.shared.s32 %3, [%1+-4];\n"
-        "@p sub.u32 %2, %2, 4;\n"
-        "@!p sub.u32 %1, %1, 4;\n"
-        "}\n"
-        : "+r"(c), "+r"(qa), "+r"(qb), "+r"(xa), "+r"(yb), "+r"(lastb) : : "memory");
-  } else {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        ".reg .b32 t, v;\n"
-        "setp.ge.s32 p, %4, %3;\n"
-        "setp.eq.and.s32 q, %3, %5, !p;\n"
-        "@q add.u32 %0, %0, 1;\n"
-        "@p mov.b32 %5, %4;\n"
-        "selp.b32 t, %2, %1, p;\n"
-        "ld.shared.s32 v, [t+-4];\n"
-        "@p sub.u32 %2, %2, 4;\n"
-        "@!p sub.u32 %1, %1, 4;\n"
-        "selp.b32 %4, v, %4, p;\n"
-        "selp.b32 %3, %3, v, p;\n"
-        "}\n"
-        : "+r"(c), "+r"(qa), "+r"(qb), "+r"(xa), "+r"(yb), "+r"(lastb) : : "memory");
+        : "+r"(c), "+r"(pa), "+r"(pb), "+r"(x), "+r"(y), "+r"(qa), "+r"(qb), "+r"(xa), "+r"(yb), "+r"(lastb) : : "memory");
   }
 }
 
@@ -177,7 +163,8 @@ __device__ __forceinline__ void merge_step_bwd(uint32_t &c, uint32_t &qa, uint32
 //   A[-1] = -1, B[-1] = -2        an exhausted backward side loses every comparison;
 //   A[na] = kVidMax, B[nb..nb+L] = kVidMax-1   likewise forward; the run of L+1 words behind B also is the
 //                                 virtual tail [n, 32*G*S) that the threads past the end walk harmlessly.
-// Every thread stores the sentinels it may read itself, so no barrier separates stores from reads.
+// Every thread stores the four single sentinels it may read itself and every warp its own copy of the
+// run, so nothing stronger than a __syncwarp separates stores from reads.
 // L is odd: the first probes of the 32 lanes' diagonal searches then fall into distinct banks.
 template <int G, bool PRED>
 __device__ __forceinline__ uint32_t merge_path_count(uint32_t sA, int na, uint32_t sB, int nb, int gt) {
@@ -187,8 +174,9 @@ __device__ __forceinline__ uint32_t merge_path_count(uint32_t sA, int na, uint32
   const int d0 = min(gt * S, n), dn = (gt + 1) * S;
   sts_i32(sA - 4u, -1); sts_i32(sA + 4u * uint32_t(na), kVidMax);
   sts_i32(sB - 4u, -2); sts_i32(sB + 4u * uint32_t(nb), kVidMax - 1);
-  if (dn > n)
-    for (int k = 1; k <= L; k++) sts_i32(sB + 4u * uint32_t(nb + k), kVidMax - 1);
+  // the run behind B: written by every warp for itself, lane-parallel (same values from every warp)
+  for (int k = 1 + (gt & 31); k <= L; k += 32) sts_i32(sB + 4u * uint32_t(nb + k), kVidMax - 1);
+  __syncwarp();
   const int i0 = merge_path_split(sA, sB, d0, max(0, d0 - nb), min(d0, na));
   int i1 = __shfl_down_sync(kFullMask, i0, 1), j1;
   if ((gt & 31) == 31) {                                      // right neighbour sits in the next warp (or nowhere)
@@ -202,11 +190,8 @@ __device__ __forceinline__ uint32_t merge_path_count(uint32_t sA, int na, uint32
   vidType x = lds_i32(pa), y = lds_i32(pb), xa = lds_i32(qa), yb = lds_i32(qb);
   vidType lastb = lds_i32(qb + 4u);                          // the b right behind this thread's range
   uint32_t c = 0;
-  #pragma unroll 2
-  for (int s = 0; s < L; s++) {
-    merge_step_fwd<PRED>(c, pa, pb, x, y);
-    merge_step_bwd<PRED>(c, qa, qb, xa, yb, lastb);
-  }
+  #pragma unroll 4
+  for (int s = 0; s < L; s++) merge_step2<PRED>(c, pa, pb, x, y, qa, qb, xa, yb, lastb);
   return c;
 }
 
@@ -462,6 +447,151 @@ batch_pipe_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ 
   }
 }
 
+// ---- the ring pipeline: ONE launch for every pair that fits a warp's ring ---------------------------------
+// Each warp owns a ring of RWORDS words of shared memory and NSLOT in-flight slots.  Pairs are taken in
+// their natural order (blocks of 32 descriptors drawn from a global ticket, the next block prefetched),
+// and every pair occupies exactly the words it needs -- [pad | a | gap | b | sentinel tail] -- so the
+// number of pairs in flight adapts to their size and no shared memory is lost to size classes; the warp
+// keeps posting TMA bulk copies while there is room, then intersects the oldest slot.  Pairs that do not
+// fit the ring are appended to two overflow lists (<= 4608 staged elements: the two-warp stage pipeline
+// above; longer: operator API from global memory).
+constexpr int kRingSlots = 8;
+
+template <int RWORDS, int NW>
+struct RingCfg {
+  static constexpr int kWarpBytes = RWORDS * 4 + kRingSlots * 16 + kRingSlots * 8;
+  static constexpr int kSmemBytes = NW * kWarpBytes;
+  static_assert(kWarpBytes % 16 == 0, "rings must stay 16-byte aligned");
+};
+
+template <int RWORDS, int NW, int CORE, bool PRED>
+__global__ void __launch_bounds__(NW * 32)
+batch_ring_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
+                  const int64_t *__restrict__ b_off, const int32_t *__restrict__ b_len, int64_t npairs,
+                  unsigned *__restrict__ ticket, int32_t *__restrict__ big_lists, unsigned *__restrict__ big_counts,
+                  unsigned long long *__restrict__ out) {
+  using Cfg = RingCfg<RWORDS, NW>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + size_t(w) * Cfg::kWarpBytes;
+  const uint32_t sring = smem_u32(wbase);
+  const uint32_t sdesc = sring + RWORDS * 4;               // int4 per slot: {pair, na | nb << 16, head_a | head_b << 2 | units_a << 4, ring word offset}
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + RWORDS * 4 + kRingSlots * 16);
+  if (lane == 0) { for (int i = 0; i < kRingSlots; i++) mbar_init(&bars[i], 1); fence_barrier_init(); }
+  __syncwarp();
+
+  const int64_t nblocks = (npairs + 31) >> 5;
+  // descriptors of one block, lane-parallel; `need` = ring words of the lane's pair
+  struct Block { int64_t ao, bo; int32_t al, bl, need; int64_t first; int cnt; };
+  auto load_block = [&](Block &r) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(kFullMask, t, 0);
+    r.first = int64_t(t) << 5; r.cnt = 0; r.al = r.bl = 0; r.ao = r.bo = 0; r.need = 0;
+    if (int64_t(t) >= nblocks) return;
+    r.cnt = int(min(int64_t(32), npairs - r.first));
+    if (lane < r.cnt) {
+      const int64_t p = r.first + lane;
+      r.ao = a_off[p]; r.al = a_len[p]; r.bo = b_off[p]; r.bl = b_len[p];
+      const PairDesc d = describe_pair(r.ao, r.al, r.bo, r.bl);
+      const int L = ((r.al + r.bl + 63) >> 6) | 1;
+      r.need = 4 + (d.units_a + 1 + d.units_b) * 4 + ((L + 1 + 3) & ~3);
+      if (int64_t(d.units_a) + d.units_b + 2 > (int64_t(1) << 20)) r.need = 0x7fffffff;
+    }
+  };
+  Block cur, nxt;
+  load_block(cur);
+  load_block(nxt);
+  int ci = 0;
+  int wr = 0, rd = 0, inflight = 0, head = 0, tail = 0;   // ring state, warp-uniform
+  int slot_start = 0;                                       // lane s: ring offset of slot s
+  uint32_t phases = 0;
+
+  int need = -1;                                             // ring words of pair (cur, ci); -1: not fetched yet
+  auto try_issue = [&]() -> bool {
+    if (need < 0) {
+      if (ci >= cur.cnt) {
+        if (cur.cnt == 0) return false;                     // tickets exhausted
+        cur = nxt; ci = 0;
+        load_block(nxt);
+        if (cur.cnt == 0) return false;
+      }
+      need = __shfl_sync(kFullMask, cur.need, ci);
+    }
+    if (need > RWORDS) {                                    // does not fit: hand over to the overflow kernels
+      if (lane == ci) {
+        const PairDesc d = describe_pair(cur.ao, cur.al, cur.bo, cur.bl);
+        const int which = (int64_t(d.units_a) + d.units_b + 2) * 4 <= pipe_stage_elems(kPipeClasses - 1) ? 0 : 1;
+        const unsigned at = atomicAdd(&big_counts[which], 1u);
+        big_lists[int64_t(which) * npairs + at] = int32_t(cur.first + ci);
+      }
+      ci++; need = -1;
+      return true;
+    }
+    if (inflight == kRingSlots) return false;
+    if (inflight == 0) { wr = 0; rd = 0; }
+    int off;
+    if (wr >= rd) {
+      if (inflight > 0 && wr == rd) return false;          // full
+      if (wr + need <= RWORDS) off = wr;
+      else if (need <= rd) off = 0;                         // wrap; [wr, RWORDS) idles until rd passes it
+      else return false;
+    } else {
+      if (wr + need <= rd) off = wr; else return false;
+    }
+    wr = off + need;
+    if (lane == tail) slot_start = off;
+    if (lane == ci) {
+      const PairDesc d = describe_pair(cur.ao, cur.al, cur.bo, cur.bl);
+      asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(sdesc + 16u * tail), "r"(int32_t(cur.first + ci)),
+                   "r"(d.na | (d.nb << 16)), "r"(d.head_a | (d.head_b << 2) | (d.units_a << 4)), "r"(off) : "memory");
+      const int units = d.units_a + d.units_b;
+      if (units > 0) {
+        const uint32_t dst = sring + 4u * uint32_t(off) + 16u;                  // behind the pad unit
+        mbar_expect_tx(&bars[tail], uint32_t(units) * 16u);
+        if (d.units_a) tma_bulk_g2s_addr(dst, pool + (cur.ao - d.head_a), uint32_t(d.units_a) * 16u, &bars[tail]);
+        if (d.units_b) tma_bulk_g2s_addr(dst + uint32_t(d.units_a + 1) * 16u, pool + (cur.bo - d.head_b), uint32_t(d.units_b) * 16u, &bars[tail]);
+      } else {
+        mbar_arrive(&bars[tail]);
+      }
+    }
+    ci++; need = -1; inflight++; tail = (tail + 1) & (kRingSlots - 1);
+    return true;
+  };
+
+  while (true) {
+    while (try_issue()) {}
+    if (inflight == 0) break;                               // nothing in flight and nothing left to issue
+    mbar_wait(&bars[head], (phases >> head) & 1u); phases ^= 1u << head;
+    int dp, dn, dh, doff;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(dp), "=r"(dn), "=r"(dh), "=r"(doff) : "r"(sdesc + 16u * head) : "memory");
+    const int na = dn & 0xffff, nb = dn >> 16, head_a = dh & 3, head_b = (dh >> 2) & 3, units_a = dh >> 4;
+    const uint32_t sA = sring + 4u * uint32_t(doff + 4 + head_a);
+    const uint32_t sB = sring + 4u * uint32_t(doff + 4 + (units_a + 1) * 4 + head_b);
+    uint32_t c = 0;
+    if (na > 0 && nb > 0) {
+      bool merge = CORE == 0;
+      if (CORE == 2) {                                       // per-pair choice by instruction-count model
+        const int nk = min(na, nb), ns = max(na, nb);
+        const int search_cost = ((nk + 63) >> 6) * (9 * (32 - __clz(ns)) + 15);
+        const int merge_cost = 170 + 15 * ((na + nb + 63) >> 6);
+        merge = merge_cost < search_cost;
+      }
+      if (merge) {
+        c = merge_path_count<1, PRED>(sA, na, sB, nb, lane);
+        fence_proxy_async();                                 // sentinel stores before the ring's next bulk copy here
+      } else {
+        c = na <= nb ? staged_search_count<1>(sA, na, sB, nb, lane) : staged_search_count<1>(sB, nb, sA, na, lane);
+      }
+    }
+    c = __reduce_add_sync(kFullMask, c);
+    if (lane == 0) out[dp] = c;
+    __syncwarp();                                            // the slot may be overwritten now
+    head = (head + 1) & (kRingSlots - 1); inflight--;
+    rd = inflight > 0 ? __shfl_sync(kFullMask, slot_start, head) : wr;
+  }
+}
+
 // pairs too long for the largest stage: operator API straight from global memory
 __global__ void __launch_bounds__(256)
 batch_list_bsearch_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
@@ -499,34 +629,70 @@ static int launch_pipe(const vidType *pool, const int64_t *a_off, const int32_t 
   return GM_OK;
 }
 
-// Tuning knobs (gm_set_option "batch.*"): warps per pair of the two large classes and the reload
-// flavour of the merge step.  Defaults are the measured best (profiles/).
-struct BatchTuning { int g2048 = 1, g4608 = 2, pred = 1, ns2048 = 2, ns1024 = 2; };
+
+
+template <int RWORDS, int NW, int CORE, bool PRED>
+static int launch_ring(const vidType *pool, const int64_t *a_off, const int32_t *a_len, const int64_t *b_off,
+                       const int32_t *b_len, int64_t npairs, unsigned *ticket, int32_t *big_lists, unsigned *big_counts,
+                       unsigned long long *out, int sms, cudaStream_t s) {
+  using Cfg = RingCfg<RWORDS, NW>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "ring does not fit shared memory");
+  auto k = batch_ring_kernel<RWORDS, NW, CORE, PRED>;
+  static int occ = -1;                                       // per instantiation
+  if (occ < 0) {
+    GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NW * 32, Cfg::kSmemBytes));
+    if (occ < 1) occ = 1;
+  }
+  int grid = int(std::min<int64_t>((npairs + 32 * NW - 1) / (32 * NW), int64_t(occ) * sms));
+  k<<<grid, NW * 32, Cfg::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, npairs, ticket, big_lists, big_counts, out);
+  return GM_OK;
+}
+
+// Tuning knobs (gm_set_option "batch.*"); defaults are the measured best (profiles/).
+//   ring   : ring words per warp of the one-launch pipeline (0 = size-class pipeline instead)
+//   pred   : reload flavour of the merge step
+//   g2048, g4608, ns2048, ns1024 : warps per pair / stages of the size-class pipeline
+struct BatchTuning { int g2048 = 1, g4608 = 2, pred = 1, ns2048 = 2, ns1024 = 2, ring = 2560; };
 inline BatchTuning &batch_tuning() { static BatchTuning t; return t; }
 
 template <int CORE, bool PRED>
 static int launch_pipeline(const vidType *pool, const int64_t *a_off, const int32_t *a_len, const int64_t *b_off,
                            const int32_t *b_len, int64_t npairs, unsigned long long *out, int sms, cudaStream_t s) {
   if (npairs >= (int64_t(1) << 31)) { set_error("gm_intersect_batch: more than 2^31 pairs per call"); return GM_EUNSUPPORTED; }
-  int32_t *lists = nullptr; unsigned *counts = nullptr;
-  GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&lists), sizeof(int32_t) * size_t(npairs) * (kPipeClasses + 1), s));
-  GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&counts), sizeof(unsigned) * (kPipeClasses + 1), s));
-  GM_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * (kPipeClasses + 1), s));
-  int cgrid = int(std::min<int64_t>((npairs + 1023) / 1024, int64_t(sms) * 2));
-  batch_classify_kernel<<<cgrid, 1024, 0, s>>>(a_off, a_len, b_off, b_len, npairs, lists, counts);
   const BatchTuning &t = batch_tuning();
+  int32_t *lists = nullptr; unsigned *counts = nullptr;       // counts: [classes..., overflow, ticket]
+  const int nlists = t.ring ? 2 : kPipeClasses + 1;
+  GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&lists), sizeof(int32_t) * size_t(npairs) * nlists, s));
+  GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&counts), sizeof(unsigned) * (kPipeClasses + 2), s));
+  GM_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * (kPipeClasses + 2), s));
   int rc = GM_OK;
-#define GM_PIPE(CLS, NST, G, NG) \
-  launch_pipe<pipe_stage_elems(CLS), NST, G, NG, CORE, PRED>(pool, a_off, a_len, b_off, b_len, lists + int64_t(CLS) * npairs, counts + CLS, npairs, out, sms, s)
-  if (rc == GM_OK) rc = t.g2048 == 1 ? (t.ns2048 == 2 ? GM_PIPE(2, 2, 1, 4) : GM_PIPE(2, 3, 1, 4))
-                                     : (t.ns2048 == 2 ? GM_PIPE(2, 2, 2, 2) : GM_PIPE(2, 3, 2, 2));
-  if (rc == GM_OK) rc = t.ns1024 == 2 ? GM_PIPE(1, 2, 1, 4) : GM_PIPE(1, 3, 1, 4);
-  if (rc == GM_OK) rc = t.g4608 == 1 ? GM_PIPE(3, 2, 1, 2) : t.g4608 == 2 ? GM_PIPE(3, 2, 2, 1) : GM_PIPE(3, 2, 4, 1);
-  if (rc == GM_OK) rc = GM_PIPE(0, 4, 1, 8);
+#define GM_PIPE(CLS, NST, G, NG, LIST, CNT) \
+  launch_pipe<pipe_stage_elems(CLS), NST, G, NG, CORE, PRED>(pool, a_off, a_len, b_off, b_len, LIST, CNT, npairs, out, sms, s)
+  const int32_t *over_list; const unsigned *over_count;
+  if (t.ring) {
+    unsigned *ticket = counts + kPipeClasses + 1;
+#define GM_RING(RW, NW) launch_ring<RW, NW, CORE, PRED>(pool, a_off, a_len, b_off, b_len, npairs, ticket, lists, counts, out, sms, s)
+    rc = t.ring == 2048 ? GM_RING(2048, 4) : t.ring == 2560 ? GM_RING(2560, 4) : t.ring == 3072 ? GM_RING(3072, 4) : t.ring == 3584 ? GM_RING(3584, 4) : GM_RING(4096, 2);
+#undef GM_RING
+    if (rc == GM_OK) rc = GM_PIPE(3, 2, 2, 1, lists, counts);
+    over_list = lists + npairs; over_count = counts + 1;
+  } else {
+    int cgrid = int(std::min<int64_t>((npairs + 1023) / 1024, int64_t(sms) * 2));
+    batch_classify_kernel<<<cgrid, 1024, 0, s>>>(a_off, a_len, b_off, b_len, npairs, lists, counts);
+#define GM_CLS(CLS, NST, G, NG) GM_PIPE(CLS, NST, G, NG, lists + int64_t(CLS) * npairs, counts + CLS)
+    if (rc == GM_OK) rc = t.g2048 == 1 ? (t.ns2048 == 2 ? GM_CLS(2, 2, 1, 4) : GM_CLS(2, 3, 1, 4))
+                                       : (t.ns2048 == 2 ? GM_CLS(2, 2, 2, 2) : GM_CLS(2, 3, 2, 2));
+    if (rc == GM_OK) rc = t.ns1024 == 2 ? GM_CLS(1, 2, 1, 4) : GM_CLS(1, 3, 1, 4);
+    if (rc == GM_OK) rc = t.g4608 == 1 ? GM_CLS(3, 2, 1, 2) : t.g4608 == 2 ? GM_CLS(3, 2, 2, 1) : GM_CLS(3, 2, 4, 1);
+    if (rc == GM_OK) rc = GM_CLS(0, 4, 1, 8);
+#undef GM_CLS
+    over_list = lists + int64_t(kPipeClasses) * npairs; over_count = counts + kPipeClasses;
+  }
 #undef GM_PIPE
   if (rc == GM_OK) {
     int grid = int(std::min<int64_t>((npairs + 7) / 8, int64_t(sms) * 8));
-    batch_list_bsearch_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, lists + int64_t(kPipeClasses) * npairs, counts + kPipeClasses, out);
+    batch_list_bsearch_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, over_list, over_count, out);
   }
   cudaFreeAsync(lists, s); cudaFreeAsync(counts, s);
   return rc;
