@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the set-intersection hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tc|clique4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload tc|clique4|diamond|motif4] [--scale S] [--shape-div D]
 
-A "step" is one full pass of the solver over the synthetic graph.  Workload at N=1 (BASELINE.json
-configs[1]): triangle counting on Graph500 R-MAT scale 22 (16*2^22 sampled edges, seed 0x5EED0016,
-SURVEY.md §8d); `--workload clique4` runs configs[2] (4-clique, R-MAT scale 23).  For N>1 the global
-graph is R-MAT scale 22+log2(N), sharded by contiguous source-vertex range (work-balanced) over the N
-ranks -- one process per GPU, every rank holds the CSR, no data-path collective, one NCCL all-reduce of
-the 64-bit count per step ("weak" scaling: per-GPU shard stays about scale-22 sized).
+A "step" is one full pass of the solver over the synthetic graph.  Workload (BASELINE.json configs[1]):
+triangle counting on Graph500 R-MAT scale 22 (16*2^22 sampled edges, seed 0x5EED0016);
+`--workload clique4` runs configs[2] (4-clique, R-MAT scale 23); `--scale 24` gives the north-star size.
+For N>1 the SAME graph is sharded by contiguous source-vertex range (work-balanced) over the N ranks --
+one process per GPU, every rank holds the CSR, no data-path collective, one NCCL all-reduce of the
+64-bit count per step ("strong" scaling: total work fixed).
+`--workload diamond` = configs[3] (sgl diamond on the LiveJournal-shaped synthetic, |V|=4,847,571, 68,993,773
+samples; strong scaling: the same graph at every N); `--workload motif4` = configs[4]'s shape (Friendster-
+shaped, flatter R-MAT) divided by --shape-div (default 16; the full 1.8 B-edge graph is an 8-GPU run),
+counted with the formula solver (motif_gpu_formula semantics).
 
 Prints ONE JSON line (see the driver contract): `value` = |E+| / device-timed step (inputs resident in
 HBM), `e2e` = the same metric through gm_tc_host with pinned HOST CSR buffers (H2D + device-side
@@ -121,6 +126,79 @@ def build_graph(torch, scale, device, oriented):
     return rp, ci
 
 
+LJ_NV, LJ_SAMPLES, LJ_SEED = 4_847_571, 68_993_773, 0x5EED004C
+FR_NV, FR_SAMPLES, FR_SEED = 65_608_366, 1_806_067_135, 0x5EED00F5          # config 5
+FR_PROBS = (0.45, 0.22, 0.22, 0.11)
+
+
+class Workload:
+    """What one bench line measures.  kind: tc | clique4 | diamond | motif4."""
+
+    def __init__(self, args, n):
+        self.kind = k = args.workload
+        self.n = n
+        self.oriented = k in ("tc", "clique4")
+        self.scaling = "strong"                    # the same graph at every N, sharded by source-vertex range
+        if self.oriented:
+            self.scale = args.scale or (23 if k == "clique4" else 22)
+            self.name = f"{'kclique4' if k == 'clique4' else 'tc'}_rmat_scale{self.scale}"
+        elif k == "diamond":
+            self.div = max(1, args.shape_div or 1)
+            self.name = "sgl_diamond_livejournal_shaped" + (f"_div{self.div}" if self.div > 1 else "")
+        else:
+            self.div = max(1, args.shape_div or 16)
+            self.name = "motif4_friendster_shaped" + (f"_div{self.div}" if self.div > 1 else "")
+        self.metric = {"tc": "tc_edges_per_sec", "clique4": "kclique4_matches_per_sec",
+                       "diamond": "sgl_diamond_matches_per_sec", "motif4": "motif4_matches_per_sec"}[k]
+        self.unit = "edges/s" if k == "tc" else "matches/s"
+        self.prepare = {"tc": "tc", "clique4": "clique", "diamond": "sgl:diamond", "motif4": "motif"}[k]
+        self.ncounts = 6 if k == "motif4" else 1
+
+    def build(self, torch, device):
+        from graphminer_b200.rmat import shaped_graph
+        if self.oriented:
+            return build_graph(torch, self.scale, device, True)
+        t0 = time.time()
+        if self.kind == "diamond":
+            rp, ci = shaped_graph(LJ_NV // self.div, LJ_SAMPLES // self.div, LJ_SEED, device=device)
+        else:
+            rp, ci = shaped_graph(FR_NV // self.div, FR_SAMPLES // self.div, FR_SEED, probs=FR_PROBS, device=device)
+        if device != "cpu":
+            torch.cuda.synchronize()
+        log(f"[bench] {self.name}: nv={rp.numel() - 1} ne={ci.numel()} ({time.time() - t0:.1f}s)")
+        return rp, ci
+
+    def solve(self, g):
+        """-> list of raw per-shard counts (additive over shards)"""
+        k = self.kind
+        if k == "tc":
+            return [g.tc()]
+        if k == "clique4":
+            return [g.kclique(4)]
+        if k == "diamond":
+            return [g.sgl("diamond")]
+        return g.motif(4, formula=True, raw=True)
+
+    def finish(self, counts):
+        if self.kind == "motif4":
+            from graphminer_b200 import capi
+            return capi.motif_formula_finish(4, counts)
+        return counts
+
+    def units(self, counts, ne):
+        return ne if self.kind == "tc" else int(sum(counts))
+
+    def host_solve(self, capi, rp, ci, max_deg):
+        k = self.kind
+        if k == "tc":
+            return [capi.tc_host(rp, ci, max_deg)]
+        if k == "clique4":
+            return [capi.kclique_host(rp, ci, 4, max_deg)]
+        if k == "diamond":
+            return [capi.sgl_host(rp, ci, "diamond", max_deg)]
+        return capi.motif_host(rp, ci, 4, formula=True, max_degree=max_deg)
+
+
 def shard_bounds(torch, rp, ci, n):
     """work-balanced contiguous source ranges: weight(v) = 1 + sum_{u in N(v)} min(d(v), d(u))"""
     nv = rp.numel() - 1
@@ -134,6 +212,42 @@ def shard_bounds(torch, rp, ci, n):
     targets = cw[-1] * torch.arange(1, n, device=rp.device, dtype=torch.float64) / n
     cuts = torch.searchsorted(cw, targets).tolist()
     return [0] + [int(c) for c in cuts] + [nv]
+
+
+def stream_microbench(torch, capi, dev, gb=4.0, reps=7):
+    """The north-star's HBM-roofline claim: every streaming variant of gm_intersect_batch on independent
+    pairs drawn from the scale-24 out-degree pairs, each list read once, pool (4 GB) far beyond L2.
+    Algorithmic bytes = 4*(|a|+|b|) per pair = the DRAM traffic of a single pass."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from batch_bench import make_batch
+    pool, ao, al, bo, bl = make_batch(24, gb, dev)
+    nel = int(al.long().sum() + bl.long().sum())
+    peak, _ = measured_peak()
+    out, ref = {}, None
+    for algo in ("auto", "merge", "gallop", "bsearch", "hash"):
+        r = capi.intersect_batch(pool, ao, al, bo, bl, algo=algo); torch.cuda.synchronize()
+        if ref is None:
+            ref = r
+        assert torch.equal(r, ref), f"streaming variant {algo} disagrees"
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for e0, e1 in evs:
+            e0.record(); capi.intersect_batch(pool, ao, al, bo, bl, algo=algo); e1.record()
+        torch.cuda.synchronize()
+        ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)[reps // 2]
+        gbs = nel * 4 / ms / 1e6
+        out[algo] = {"ms": ms, "achieved": gbs, "frac": gbs / peak}
+    return {"bound": "hbm", "unit": "GB/s", "peak": peak, "pairs": int(ao.numel()), "alg_bytes": nel * 4,
+            "workload": "pairs with the (d+(u), d+(v)) of R-MAT scale-24 DAG edges, contiguous lists, pool %.1f GB > L2" % (pool.numel() * 4 / 1e9),
+            "kernel": "batch_ring_kernel (auto/merge/gallop: TMA-staged ring pipeline), batch_bsearch_kernel, batch_hash_kernel",
+            "variants": out}
+
+
+def ncu_traffic(name):
+    """DRAM bytes per step of the pass's kernels from the committed ncu --set full capture, or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -150,11 +264,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     n = max(world, 1)
-    clique = args.workload == "clique4"
-    scale = (args.scale or (23 if clique else 22)) + int(round(math.log2(n)))
-    name = f"{'kclique4' if clique else 'tc'}_rmat_scale{scale}"
+    wl = Workload(args, n)
 
-    rp, ci = build_graph(torch, scale, dev, oriented=True)
+    rp, ci = wl.build(torch, dev)
     nv, ne = rp.numel() - 1, ci.numel()
     max_deg = int((rp[1:] - rp[:-1]).max())
     bounds = shard_bounds(torch, rp, ci, n)
@@ -164,17 +276,18 @@ def run_ours(args):
     g = capi.DeviceGraph.adopt(rp, ci, max_deg)
     g.set_stream(stream.cuda_stream)
     g.set_source_range(b, e)
-    g.prepare("clique" if clique else "tc")
-    solve = (lambda: g.kclique(4)) if clique else g.tc
-    cnt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    g.prepare(wl.prepare)
+    cnt_dev = torch.zeros(wl.ncounts, dtype=torch.int64, device=dev)
+
+    def reduce_counts(c):
+        if world > 1:
+            cnt_dev.copy_(torch.tensor(c, dtype=torch.int64))
+            dist.all_reduce(cnt_dev)                   # the only collective: 1 (or 6) 64-bit counts
+            c = [int(x) for x in cnt_dev.tolist()]
+        return wl.finish(c)
 
     def step():
-        c = solve()
-        if world > 1:
-            cnt_dev.fill_(c)
-            dist.all_reduce(cnt_dev)                   # the only collective: one 64-bit count
-            return int(cnt_dev.item())
-        return c
+        return reduce_counts(wl.solve(g))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -183,14 +296,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        total = step()
+        counts = step()
     kern_ms, launches = [], 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     with ClockSampler(local) as clk:
         ev0.record(stream)
         for _ in range(args.steps):
-            total = step()
+            counts = step()
             ms, nl = g.last_stats()
             kern_ms.append(ms); launches += nl
         ev1.record(stream)
@@ -205,19 +318,19 @@ def run_ours(args):
         dist.all_reduce(alg_bytes)
     alg_bytes = int(alg_bytes.item())
 
-    units = total if clique else ne                    # matches/s for k-CL, edges/s for TC
+    units = wl.units(counts, ne)                       # matches/s for k-CL / SgL / k-MC, edges/s for TC
     value = units / (elapsed_ms / args.steps / 1e3)
 
     # ---- parity guard (outside the timed region): a second implementation must agree -------------
     check = None
-    if not clique:
+    if wl.kind == "tc":
         capi.set_option("tc.algo", "bs")
         c2 = torch.tensor([g.tc()], dtype=torch.int64, device=dev)
         capi.set_option("tc.algo", "auto")
         if world > 1:
             dist.all_reduce(c2)
         check = int(c2.item())
-        assert check == total, f"parity failure: hash path {total} != operator path {check}"
+        assert check == counts[0], f"parity failure: hash path {counts[0]} != operator path {check}"
 
     # ---- end to end through the host entry point (pinned host CSR in, count out) ----------------
     h_rp = torch.empty(rp.shape, dtype=rp.dtype, pin_memory=True); h_rp.copy_(rp)
@@ -227,19 +340,18 @@ def run_ours(args):
 
     def e2e_step():
         if world == 1:
-            return capi.kclique_host(n_rp, n_ci, 4, max_deg) if clique else capi.tc_host(n_rp, n_ci, max_deg)
+            return wl.host_solve(capi, n_rp, n_ci, max_deg)
         with capi.DeviceGraph(n_rp, n_ci, max_deg, device=local) as gg:
             gg.set_source_range(b, e)
-            c = gg.kclique(4) if clique else gg.tc()
-        cnt_dev.fill_(c); dist.all_reduce(cnt_dev)
-        return int(cnt_dev.item())
+            c = wl.solve(gg)
+        return reduce_counts(c)
 
     e2e_steps = max(1, min(args.steps, 5))
-    assert e2e_step() == total
+    assert e2e_step() == counts
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        assert e2e_step() == total
+        assert e2e_step() == counts
     sync_all()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
@@ -249,30 +361,40 @@ def run_ours(args):
     # ---- CPU baseline: the reference's own OpenMP code on a bounded sample (rank 0, N=1) ---------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(n_rp, n_ci, max_deg, clique, budget_s=args.cpu_seconds)
+        cpu = cpu_baseline(n_rp, n_ci, max_deg, wl.kind, budget_s=args.cpu_seconds)
 
     g.close()
+    del g, rp, ci
+    torch.cuda.empty_cache()
+    stream_rf = None
+    if rank == 0 and world == 1 and not args.no_stream:
+        stream_rf = stream_microbench(torch, capi, dev)
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = alg_bytes / (kern_total_ms / args.steps / 1e3) / 1e9 if alg_bytes else None
+        kernel = {"tc": "tc_hash_kernel<MODE=2 ranked>", "clique4": "kclique_bitmap_kernel",
+                  "diamond": "sgl_warp_edge<diamond>", "motif4": "motif formula kernels"}[wl.kind]
         out = {
-            "metric": "kclique4_matches_per_sec" if clique else "tc_edges_per_sec",
-            "value": value, "unit": "matches/s" if clique else "edges/s",
+            "metric": wl.metric, "value": value, "unit": wl.unit,
             "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": wl.scaling,
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": name, "nv": nv, "oriented_edges": ne, "max_out_degree": max_deg,
-                       "count": total, "parity_check_count": check,
-                       "l2": "inputs (CSR %.0f MB) larger than the 126 MB L2; no flush" % ((rp.numel() * 8 + ne * 4) / 1e6),
-                       "sharding": "contiguous source-vertex ranges, work-balanced; CSR replicated; 1 NCCL all-reduce of a u64 per step"},
-            "e2e": {"value": e2e_value, "unit": "matches/s" if clique else "edges/s",
-                    "h2d_bytes_per_step": int(rp.numel() * 8 + ne * 4), "d2h_bytes_per_step": 8,
+            "config": {"workload": wl.name, "nv": nv, "edges": ne, "oriented": wl.oriented, "max_degree": max_deg,
+                       "count": counts[0] if len(counts) == 1 else counts, "parity_check_count": check,
+                       "l2": "inputs (CSR %.0f MB) larger than the 126 MB L2; no flush" % ((nv * 8 + ne * 4) / 1e6),
+                       "sharding": "contiguous source-vertex ranges, work-balanced; CSR replicated; 1 NCCL all-reduce of %d u64 per step" % wl.ncounts},
+            "e2e": {"value": e2e_value, "unit": wl.unit,
+                    "h2d_bytes_per_step": int((nv + 1) * 8 + ne * 4), "d2h_bytes_per_step": 8 * wl.ncounts,
                     "steps": e2e_steps, "note": "gm_*_host: pinned host CSR -> upload + device-side prepare + kernels + count"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src, "kernel": ("kclique_bitmap_kernel" if clique else "tc_hash_kernel<MODE=2 ranked>") + " (all size classes of one pass, run concurrently)",
-                         "alg_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_total_ms / args.steps},
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(wl.name),
+                         "peak_source": peak_src, "kernel": kernel + " (all size classes of one pass, run concurrently)",
+                         "alg_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_total_ms / args.steps,
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes / device time; rows are re-read out of the 126 MB L2 and the "
+                                 "ranked kernel streams row suffixes only, so it may exceed the DRAM peak; traffic = ncu dram bytes per step; "
+                                 "the single-pass HBM roofline of the intersection kernels is in stream_roofline"},
+            "stream_roofline": stream_rf,
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
         }
@@ -282,35 +404,45 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(rp, ci, max_deg, clique, budget_s=12.0):
-    """oracle/_ref/libgm_ref.so = the reference's VertexSet code + its loop nest over a source range."""
+def cpu_baseline(rp, ci, max_deg, kind, budget_s=12.0):
+    """oracle/_ref/libgm_ref.so = the reference's VertexSet code + its loop nest over a source range
+    (tc / 4-clique / diamond); 4-motif: the oracle port of automine_4motif (kind "port")."""
     import oracle
     nv = len(rp) - 1
-    use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so"))
+    use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so")) and kind != "motif4"
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if use_ref:
         L = oracle.ref_lib()
         L.gmr_set_num_threads(ncpu)            # torchrun sets OMP_NUM_THREADS=1; use every host core
         h = L.gmr_graph_create(nv, rp, ci, max_deg)
-        run = (lambda a, b: L.gmr_kclique_range(h, 4, a, b)) if clique else (lambda a, b: L.gmr_tc_range(h, a, b))
+        run = {"tc": lambda a, b: L.gmr_tc_range(h, a, b), "clique4": lambda a, b: L.gmr_kclique_range(h, 4, a, b),
+               "diamond": lambda a, b: L.gmr_diamond_range(h, a, b)}[kind]
         cores = L.gmr_num_threads()
     else:
         oracle.set_num_threads(ncpu)
-        run = (lambda a, b: oracle.kclique(rp, ci, 4, (a, b))) if clique else (lambda a, b: oracle.tc(rp, ci, (a, b)))
+        run = {"tc": lambda a, b: oracle.tc(rp, ci, (a, b)), "clique4": lambda a, b: oracle.kclique(rp, ci, 4, (a, b)),
+               "diamond": lambda a, b: oracle.sgl(rp, ci, "diamond", (a, b)),
+               "motif4": lambda a, b: sum(oracle.motif(rp, ci, 4, (a, b)))}[kind]
         cores = oracle.num_threads()
-    # calibrate on 0.5% of the sources, then size the sample for ~budget_s (vertex ids are randomly
-    # permuted, so a prefix of the id range is an unbiased sample of the workload)
-    n0 = max(1, nv // 200)
-    t0 = time.perf_counter(); run(0, n0); dt = time.perf_counter() - t0
-    n1 = int(min(nv, max(n0, n0 * budget_s / max(dt, 1e-6))))
-    t0 = time.perf_counter(); cnt = run(0, n1); dt = time.perf_counter() - t0
+    # consecutive source ranges of growing size until ~budget_s of CPU time is spent (vertex ids are
+    # randomly permuted, so a prefix of the id range is an unbiased sample of the workload); each next
+    # range is sized from the rate seen so far so that the total stays bounded
+    done, cnt, dt = 0, 0, 0.0
+    step = max(1, nv // (200 if kind in ("tc", "clique4") else 50000))
+    while done < nv and dt < 0.8 * budget_s:
+        hi = min(nv, done + step)
+        t0 = time.perf_counter(); cnt += run(done, hi); dt += time.perf_counter() - t0
+        done = hi
+        rate = done / max(dt, 1e-6)                                   # sources per second so far
+        step = int(max(1, min(2 * done, rate * max(budget_s - dt, 0.0))))
+    n1 = done
     edges = int(rp[n1] - rp[0])
-    units = cnt if clique else edges
+    units = edges if kind == "tc" else cnt
     if use_ref:
         L.gmr_graph_free(h)
-    return {"value": units / dt, "unit": "matches/s" if clique else "edges/s", "cores": cores,
+    return {"value": units / dt, "unit": "edges/s" if kind == "tc" else "matches/s", "cores": cores,
             "kind": "reference" if use_ref else "port",
-            "sample": f"source vertices [0,{n1}) of {nv} ({edges} oriented edges), {dt:.2f} s"}
+            "sample": f"source vertices [0,{n1}) of {nv} ({edges} CSR entries), {dt:.2f} s"}
 
 
 def run_reference(args):
@@ -321,30 +453,27 @@ def run_reference(args):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = max(world, 1)
-    clique = args.workload == "clique4"
-    scale = (args.scale or (23 if clique else 22)) + int(round(math.log2(n)))
+    wl = Workload(args, n)
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    rp, ci = build_graph(torch, scale, dev, oriented=True)
+    rp, ci = wl.build(torch, dev)
     rp, ci = rp.cpu().numpy(), ci.cpu().numpy()
     max_deg = int(np.diff(rp).max())
     vals, last = [], None
     per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(rp, ci, max_deg, clique, budget_s=per_step)
+        last = cpu_baseline(rp, ci, max_deg, wl.kind, budget_s=per_step)
         if i >= args.warmup:
             vals.append(last["value"])
     v = statistics.mean(vals)
-    unit = "matches/s" if clique else "edges/s"
     last["value"] = v
     print(json.dumps({
-        "impl": "reference", "metric": "kclique4_matches_per_sec" if clique else "tc_edges_per_sec",
-        "value": v, "unit": unit, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": wl.metric,
+        "value": v, "unit": wl.unit, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"{'kclique4' if clique else 'tc'}_rmat_scale{scale}", "nv": len(rp) - 1,
-                   "oriented_edges": int(len(ci))},
+        "config": {"workload": wl.name, "nv": len(rp) - 1, "edges": int(len(ci)), "oriented": wl.oriented},
         "cpu_baseline": last,
-        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
@@ -354,7 +483,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tc", choices=["tc", "clique4"])
+    ap.add_argument("--workload", default="tc", choices=["tc", "clique4", "diamond", "motif4"])
+    ap.add_argument("--shape-div", type=int, default=0, help="divide the shaped graphs (|V|, samples) by this (default: diamond 1, motif4 16)")
+    ap.add_argument("--no-stream", action="store_true", help="skip the streaming-intersection roofline leg")
     ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale at N=1 (default 22 / 23)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -109,7 +109,8 @@ struct gm_graph {
   int last_launches = 0;
   uint64_t last_alg_bytes = 0;
   uint64_t tc_bytes_cache = 0;
-  int last_alg_kind = 0;                  // 1: TC formula, 2: 4-clique formula (computed lazily)
+  int last_alg_kind = 0;                  // 1: TC formula, 2: 4-clique formula, 3: diamond count form (computed lazily)
+  uint64_t dia_bytes_cache = 0;
   uint64_t c4_bytes_cache = 0;
   int num_sms = gm::kNumSMsB200;
   int smem_optin = 0;
@@ -136,7 +137,7 @@ int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
-int tc_alg_bytes(gm_graph *g, uint64_t *out);
+int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break = 0);
 int clique4_alg_bytes(gm_graph *g, uint64_t *out);
 int ensure_scratch(gm_graph *g, size_t bytes);
 int begin_timed(gm_graph *g);

@@ -513,7 +513,7 @@ int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end) {
   uint2 *vi = g->d_vinfo; vidType *ac = g->d_acol; g->d_vinfo = nullptr; g->d_acol = nullptr;
   free_aux(g);
   g->d_vinfo = vi; g->d_acol = ac;
-  g->src_begin = begin; g->src_end = end; g->tc_bytes_cache = 0; g->c4_bytes_cache = 0;
+  g->src_begin = begin; g->src_end = end; g->tc_bytes_cache = 0; g->c4_bytes_cache = 0; g->dia_bytes_cache = 0;
   return GM_OK;
 }
 
@@ -541,6 +541,9 @@ int gm_last_alg_bytes(gm_graph_t *g, uint64_t *bytes) {
   } else if (g->last_alg_kind == 2) {
     if (g->c4_bytes_cache == 0) GM_TRY(clique4_alg_bytes(g, &g->c4_bytes_cache));
     g->last_alg_bytes = g->c4_bytes_cache;
+  } else if (g->last_alg_kind == 3) {
+    if (g->dia_bytes_cache == 0) GM_TRY(tc_alg_bytes(g, &g->dia_bytes_cache, 1));
+    g->last_alg_bytes = g->dia_bytes_cache;
   }
   *bytes = g->last_alg_bytes;
   return GM_OK;

@@ -74,7 +74,7 @@ int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total) {
   if (pid < 0) { set_error("sgl: pattern '%s' not supported (diamond, rectangle, house, pentagon)", pattern ? pattern : "(null)"); return GM_EUNSUPPORTED; }
   GM_TRY(ensure_coo(g, 1));
   int launches = 0;
-  g->last_alg_bytes = 0; g->last_alg_kind = 0;
+  g->last_alg_bytes = 0; g->last_alg_kind = pid == 0 ? 3 : 0;
   GM_TRY(begin_timed(g));
   GM_TRY(run_sgl(g, pid, &launches));
   return end_timed(g, launches, 1, total);

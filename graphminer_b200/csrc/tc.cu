@@ -157,13 +157,18 @@ tc_warp_edge_bs(GraphGPU g, AccType *total) {
 }
 
 // algorithmic bytes of TC, SURVEY.md §8(d): sum over edges 4*(d(u)+d(v)) + 8|E| + 8(|V|+1)
-__global__ void k_tc_alg_bytes(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx, unsigned long long *out) {
+// sym_break: only the tasks v < u (the COO of the sgl solvers, diamond: SURVEY.md §8(d) "count form")
+__global__ void k_tc_alg_bytes(vidType vb, vidType ve, const eidType *rowptr, const vidType *colidx, int sym_break, unsigned long long *out) {
   vidType u = vb + blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long s = 0;
   if (u < ve) {
     eidType b = rowptr[u], e = rowptr[u + 1];
     unsigned long long du = (unsigned long long)(e - b);
-    for (eidType i = b; i < e; i++) { vidType v = colidx[i]; s += 4ull * (du + (unsigned long long)(rowptr[v + 1] - rowptr[v])) + 8ull; }
+    for (eidType i = b; i < e; i++) {
+      vidType v = colidx[i];
+      if (sym_break && v >= u) break;
+      s += 4ull * (du + (unsigned long long)(rowptr[v + 1] - rowptr[v])) + 8ull;
+    }
   }
   s = warp_reduce(s);
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
@@ -204,12 +209,12 @@ static int run_tc_hash(gm_graph *g, int *launches) {
   return GM_OK;
 }
 
-int tc_alg_bytes(gm_graph *g, uint64_t *out) {
+int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break) {
   vidType n = g->src_end - g->src_begin;
   unsigned long long *d = nullptr, h = 0;
   GM_CUDA(dmalloc(g, &d, sizeof(unsigned long long)));
   GM_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), g->stream));
-  if (n > 0) k_tc_alg_bytes<<<(n + 255) / 256, 256, 0, g->stream>>>(g->src_begin, g->src_end, g->d_rowptr, g->d_colidx, d);
+  if (n > 0) k_tc_alg_bytes<<<(n + 255) / 256, 256, 0, g->stream>>>(g->src_begin, g->src_end, g->d_rowptr, g->d_colidx, sym_break, d);
   GM_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
   GM_CUDA(dfree(g, d));
