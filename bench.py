@@ -278,6 +278,7 @@ def run_ours(args):
     g.set_source_range(b, e)
     g.prepare(wl.prepare)
     cnt_dev = torch.zeros(wl.ncounts, dtype=torch.int64, device=dev)
+    res_dev = torch.zeros(8, dtype=torch.int64, device=dev)
 
     def reduce_counts(c):
         if world > 1:
@@ -286,8 +287,18 @@ def run_ours(args):
             c = [int(x) for x in cnt_dev.tolist()]
         return wl.finish(c)
 
+    if world > 1:
+        # device-side results: kernels -> count in res_dev -> NCCL all-reduce on the same stream -> ONE
+        # device->host read per step (no host round trip between the pass and its collective)
+        g.set_result_buffer(res_dev)
+
     def step():
-        return reduce_counts(wl.solve(g))
+        if world == 1:
+            return wl.finish(wl.solve(g))
+        wl.solve(g)
+        red = res_dev[:wl.ncounts]
+        dist.all_reduce(red)
+        return wl.finish([int(x) for x in red.tolist()])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -324,6 +335,7 @@ def run_ours(args):
     # ---- parity guard (outside the timed region): a second implementation must agree -------------
     check = None
     if wl.kind == "tc":
+        g.set_result_buffer(None)
         capi.set_option("tc.algo", "bs")
         c2 = torch.tensor([g.tc()], dtype=torch.int64, device=dev)
         capi.set_option("tc.algo", "auto")

@@ -29,7 +29,7 @@ SYMBOLS = [
     "gm_last_error", "gm_version", "gm_device_count", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
     "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph",
-    "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream",
+    "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
     "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
     "gm_motif_formula_finish", "gm_last_stats", "gm_last_alg_bytes",
@@ -77,6 +77,7 @@ def lib():
     L.gm_graph_adopt.argtypes = [vp, vp, i32, i64, i32, C.c_int, C.POINTER(vp)]
     L.gm_graph_free.argtypes = [vp]
     L.gm_graph_set_stream.argtypes = [vp, vp]
+    L.gm_graph_set_result_buffer.argtypes = [vp, vp]
     L.gm_graph_set_source_range.argtypes = [vp, i32, i32]
     L.gm_graph_prepare.argtypes = [vp, C.c_char_p]
     L.gm_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_int)]
@@ -230,6 +231,13 @@ class DeviceGraph:
 
     def set_stream(self, stream_ptr):
         check(lib().gm_graph_set_stream(self._h, stream_ptr))
+
+    def set_result_buffer(self, d_out):
+        """torch int64/uint64 CUDA tensor of >= 6 elements, or None: asynchronous device-side results."""
+        if d_out is not None:
+            assert d_out.is_cuda and d_out.dtype.itemsize == 8 and d_out.numel() >= 6
+            self._result = d_out
+        check(lib().gm_graph_set_result_buffer(self._h, d_out.data_ptr() if d_out is not None else None))
 
     def set_source_range(self, begin, end):
         check(lib().gm_graph_set_source_range(self._h, begin, end))

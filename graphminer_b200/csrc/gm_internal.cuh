@@ -106,6 +106,8 @@ struct gm_graph {
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // size classes of one pass run concurrently
   cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
   float last_ms = 0.f;
+  unsigned long long *d_result = nullptr;   // caller-owned device result buffer (asynchronous mode)
+  bool stats_pending = false;
   int last_launches = 0;
   uint64_t last_alg_bytes = 0;
   uint64_t tc_bytes_cache = 0;

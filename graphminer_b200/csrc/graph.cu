@@ -315,6 +315,12 @@ int join_streams(gm_graph *g) {
 int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out) {
   GM_CUDA(cudaEventRecord(g->ev1, g->stream));
   GM_CUDA(cudaGetLastError());
+  g->last_launches = launches;
+  if (g->d_result) {                                      // asynchronous mode: results stay on the device
+    GM_CUDA(cudaMemcpyAsync(g->d_result, g->d_counts, size_t(ncounts) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, g->stream));
+    g->stats_pending = true;
+    return GM_OK;
+  }
   GM_CUDA(cudaMemcpyAsync(g->h_counts, g->d_counts, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
   GM_CUDA(cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1));
@@ -504,6 +510,13 @@ int gm_graph_set_stream(gm_graph_t *g, void *cuda_stream) {
   return GM_OK;
 }
 
+int gm_graph_set_result_buffer(gm_graph_t *g, uint64_t *d_out) {
+  if (!g) { set_error("null graph"); return GM_EINVAL; }
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  g->d_result = reinterpret_cast<unsigned long long *>(d_out);
+  return GM_OK;
+}
+
 int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end) {
   if (!g || begin < 0 || end > g->nv || begin > end) { set_error("gm_graph_set_source_range: bad range"); return GM_EINVAL; }
   if (begin == g->src_begin && end == g->src_end) return GM_OK;
@@ -528,6 +541,11 @@ int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, 
 
 int gm_last_stats(gm_graph_t *g, float *kernel_ms, int *launches) {
   if (!g) { set_error("null graph"); return GM_EINVAL; }
+  if (g->stats_pending) {
+    GM_CUDA(cudaEventSynchronize(g->ev1));
+    GM_CUDA(cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1));
+    g->stats_pending = false;
+  }
   if (kernel_ms) *kernel_ms = g->last_ms;
   if (launches) *launches = g->last_launches;
   return GM_OK;

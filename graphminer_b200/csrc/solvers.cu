@@ -83,6 +83,7 @@ int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total) {
 static int motif_common(gm_graph_t *g, int k, int formula, int raw, uint64_t *counts) {
   if (!g || !counts) { set_error("gm_motif: null argument"); return GM_EINVAL; }
   if (k != 3 && k != 4) { set_error("motif: k=%d not supported (k in {3,4})", k); return GM_EUNSUPPORTED; }
+  if (g->d_result && formula && !raw) { set_error("gm_motif_formula: device-side results need gm_motif_formula_raw + gm_motif_formula_finish"); return GM_EUNSUPPORTED; }
   GM_TRY(ensure_coo(g, formula ? 1 : 0));
   int launches = 0;
   g->last_alg_bytes = 0; g->last_alg_kind = 0;

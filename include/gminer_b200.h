@@ -88,6 +88,12 @@ int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv,
 int gm_graph_free(gm_graph_t *g);           /* GraphGPU::clean + clean_edgelist, graph_gpu.h:56-63 */
 /* Launch on this cudaStream_t (as void*); NULL = the library's own stream for the device. */
 int gm_graph_set_stream(gm_graph_t *g, void *cuda_stream);
+/* Device-side results: with a non-NULL d_out (device uint64[>= 6], same device) the solvers become
+ * asynchronous -- the counts land in d_out in stream order, the host `total`/`counts` argument is left
+ * untouched and nothing synchronises, so the caller can chain its collective on the same stream
+ * (one ncclAllReduce of the count replaces the host loop of triangle/multigpu.cu:82-84).  NULL restores
+ * the synchronous behaviour.  gm_last_stats then waits for the pass to finish. */
+int gm_graph_set_result_buffer(gm_graph_t *g, uint64_t *d_out);
 /* Restrict the solvers to source vertices (DFS roots) in [begin,end): the multi-GPU shard of
  * triangle/multigpu.cu:73-75 (warp_vertex<<<>>>(local_begin, local_end, ...)).  Default [0,nv). */
 int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end);

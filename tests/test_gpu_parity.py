@@ -312,3 +312,31 @@ def test_host_entry_points(citeseer):
     # asking for more GPUs than present clamps (triangle/multigpu.cu:28-30) and still counts right
     assert capi.tc_host(orp, oci, omd, n_gpus=64) == k["tc"]
     assert capi.motif_host(rp, ci, 4, True, md, n_gpus=64) == k["motif4"]
+
+
+def test_device_side_results(citeseer):
+    """gm_graph_set_result_buffer: asynchronous solvers leave their counts on the device in stream order
+    (what bench.py --gpus N chains its NCCL all-reduce on); NULL restores the synchronous path."""
+    import torch
+    rp, ci, _ = citeseer
+    orp, oci, md = _dag(rp, ci)
+    k = KAT["citeseer"]
+    res = torch.full((8,), -1, dtype=torch.int64, device="cuda:0")
+    with capi.DeviceGraph(orp, oci, md) as g:
+        g.set_result_buffer(res)
+        assert g.tc() == 0                         # host result untouched in asynchronous mode
+        g.kclique(4)                               # second pass queued behind the first, no sync in between
+        torch.cuda.synchronize()
+        assert int(res[0]) == k["clique4"]
+        g.tc(); torch.cuda.synchronize()
+        assert int(res[0]) == k["tc"]
+        ms, launches = g.last_stats()
+        assert ms > 0 and launches >= 1
+        g.set_result_buffer(None)
+        assert g.tc() == k["tc"]
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        g.set_result_buffer(res)
+        g.motif(4, formula=True, raw=True); torch.cuda.synchronize()
+        assert capi.motif_formula_finish(4, [int(x) for x in res[:6].tolist()]) == k["motif4"]
+        with pytest.raises(capi.GMError):
+            g.motif(4, formula=True)
