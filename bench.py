@@ -199,15 +199,22 @@ class Workload:
         return capi.motif_host(rp, ci, 4, formula=True, max_degree=max_deg)
 
 
-def shard_bounds(torch, rp, ci, n):
-    """work-balanced contiguous source ranges: weight(v) = 1 + sum_{u in N(v)} min(d(v), d(u))"""
+def shard_bounds(torch, rp, ci, n, kind="tc"):
+    """work-balanced contiguous source ranges.  tc (ranked kernel): the pass streams C(d+(v),2) elements for
+    source v; others: weight(v) = 1 + sum_{u in N(v)} min(d(v), d(u)) (the estimate of scheduler.cc:14-19)"""
     nv = rp.numel() - 1
     if n == 1:
         return [0, nv]
     deg = rp[1:] - rp[:-1]
-    src = torch.repeat_interleave(torch.arange(nv, device=rp.device), deg)
-    w = torch.minimum(deg[src], deg[ci.long()]).to(torch.float64)
-    wv = torch.zeros(nv, dtype=torch.float64, device=rp.device).index_add_(0, src, w) + 1.0
+    if kind == "tc":
+        # destination sharding of the ranked kernel: edge a->b streams on average (d+(a)-1)/2 elements at root b
+        src = torch.repeat_interleave(torch.arange(nv, device=rp.device), deg)
+        w = (deg[src].to(torch.float64) - 1) / 2 + 2
+        wv = torch.zeros(nv, dtype=torch.float64, device=rp.device).index_add_(0, ci.long(), w) + 1.0
+    else:
+        src = torch.repeat_interleave(torch.arange(nv, device=rp.device), deg)
+        w = torch.minimum(deg[src], deg[ci.long()]).to(torch.float64)
+        wv = torch.zeros(nv, dtype=torch.float64, device=rp.device).index_add_(0, src, w) + 1.0
     cw = torch.cumsum(wv, 0)
     targets = cw[-1] * torch.arange(1, n, device=rp.device, dtype=torch.float64) / n
     cuts = torch.searchsorted(cw, targets).tolist()
@@ -269,10 +276,17 @@ def run_ours(args):
     rp, ci = wl.build(torch, dev)
     nv, ne = rp.numel() - 1, ci.numel()
     max_deg = int((rp[1:] - rp[:-1]).max())
-    bounds = shard_bounds(torch, rp, ci, n)
+    bounds = shard_bounds(torch, rp, ci, n, wl.kind)
     b, e = bounds[rank], bounds[rank + 1]
 
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream shared by torch, NCCL's stream dependencies and the library: a NULL
+    # stream handle would make the library create its own stream, unordered against torch's
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    if wl.kind == "tc" and world > 1:
+        capi.set_option("tc.shard", "dest")        # shard the edge set by destination: one table build per root overall
     g = capi.DeviceGraph.adopt(rp, ci, max_deg)
     g.set_stream(stream.cuda_stream)
     g.set_source_range(b, e)
@@ -400,7 +414,7 @@ def run_ours(args):
                     "steps": e2e_steps, "note": "gm_*_host: pinned host CSR -> upload + device-side prepare + kernels + count"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(wl.name),
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(wl.name) if n == 1 else None,
                          "peak_source": peak_src, "kernel": kernel + " (all size classes of one pass, run concurrently)",
                          "alg_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_total_ms / args.steps,
                          "note": "achieved = SURVEY 8(d) algorithmic bytes / device time; rows are re-read out of the 126 MB L2 and the "

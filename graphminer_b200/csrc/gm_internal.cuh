@@ -47,6 +47,7 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
+  std::string tc_shard = "source";   // which endpoint of an edge the source range of a shard refers to (ranked TC kernel)
   int chunk = 0;   // 0 = default per kernel
 };
 Options &options();

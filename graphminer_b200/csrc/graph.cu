@@ -429,6 +429,9 @@ int gm_set_option(const char *key, const char *value) {
   if (k == "tc.algo") {
     if (v != "auto" && v != "rank" && v != "hash" && v != "hash_rev" && v != "bs") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_algo = v;
+  } else if (k == "tc.shard") {
+    if (v != "source" && v != "dest") { set_error("tc.shard: unknown value '%s'", value); return GM_EINVAL; }
+    options().tc_shard = v;
   } else if (k == "clique.algo") {
     if (v != "auto" && v != "bitmap" && v != "list") { set_error("clique.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().clique_algo = v;

@@ -66,7 +66,7 @@ __global__ void k_ranked_vinfo(vidType nv, const eidType *nrow, const uint32_t *
 // PASS 1: write the partner records.
 template <int PASS>
 __global__ void k_ranked_edges(eidType ne, const unsigned long long *ekeys, const eidType *nrow, const uint2 *vinfo,
-                               const vidType *orig_of, vidType src_begin, vidType src_end,
+                               const vidType *orig_of, vidType src_begin, vidType src_end, int by_dest,
                                vidType *acol, unsigned long long *cnt, const eidType *prow, uint2 *prec, int *bad) {
   eidType e = eidType(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= ne) return;
@@ -79,7 +79,10 @@ __global__ void k_ranked_edges(eidType ne, const unsigned long long *ekeys, cons
     acol[(size_t(va.x) << 2) + i] = b;
     if (b <= a) atomicOr(bad, 1);
   }
-  vidType oa = orig_of[a];
+  // the shard owns the edges whose source (reference semantics, triangle/multigpu.cu:73-75) or -- with
+  // tc.shard=dest -- whose destination lies in the range; the latter keeps every root (= destination)
+  // and its shared-memory table on exactly one shard
+  vidType oa = orig_of[by_dest ? b : a];
   if (rem == 0 || oa < src_begin || oa >= src_end) return;
   if (PASS == 0) {
     atomicAdd(&cnt[b], 1ull);
@@ -162,7 +165,8 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
     k_ranked_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->rk_nrow, units, g->rk_vinfo);
     k_fill_u32<<<nblk(acol_len), 256, 0, g->stream>>>(acol_len, g->rk_acol, kVidMax);
-    k_ranked_edges<0><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end,
+    const int by_dest = options().tc_shard == "dest";
+    k_ranked_edges<0><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end, by_dest,
                                                        g->rk_acol, cnt, nullptr, nullptr, bad);
     GM_CUDA(cudaMemcpyAsync(g->rk_prow, cnt, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, g->stream));
     GM_TRY(scan_inplace(g, g->rk_prow, nv));
@@ -173,7 +177,7 @@ int ensure_ranked(gm_graph *g) {
     if (h_bad) return GM_OK;                                                     // not the (degree,id) orientation
     GM_CUDA(dmalloc(g, &g->rk_prec, sizeof(uint2) * size_t(nrec > 0 ? nrec : 1)));
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
-    k_ranked_edges<1><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end,
+    k_ranked_edges<1><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end, by_dest,
                                                        g->rk_acol, cnt, g->rk_prow, g->rk_prec, bad);
     GM_CUDA(cudaStreamSynchronize(g->stream));
     GM_CUDA(cudaGetLastError());

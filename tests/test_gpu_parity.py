@@ -25,6 +25,7 @@ def _reset_options():
     capi.set_option("tc.algo", "auto")
     capi.set_option("clique.algo", "auto")
     capi.set_option("sched.chunk", 0)
+    capi.set_option("tc.shard", "source")
 
 
 def _graph(name):
@@ -340,3 +341,20 @@ def test_device_side_results(citeseer):
         assert capi.motif_formula_finish(4, [int(x) for x in res[:6].tolist()]) == k["motif4"]
         with pytest.raises(capi.GMError):
             g.motif(4, formula=True)
+
+
+def test_tc_destination_sharding_adds_up():
+    """tc.shard=dest: a shard owns the edges whose DESTINATION lies in its range (each root's table is then
+    built on one shard only); over a partition of the vertex set the shards still add up to the oracle."""
+    rp, ci = _graph("rmat14")
+    orp, oci, md = _dag(rp, ci)
+    want = oracle.tc(orp, oci)
+    nv = len(orp) - 1
+    capi.set_option("tc.shard", "dest")
+    cuts = [0, nv // 5, nv // 2, nv - 7, nv]
+    total = 0
+    with capi.DeviceGraph(orp, oci, md) as g:
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            g.set_source_range(b, e)
+            total += g.tc()
+    assert total == want
