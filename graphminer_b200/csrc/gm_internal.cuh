@@ -51,7 +51,9 @@ struct Options {
   int chunk = 0;   // 0 = default per kernel
 };
 Options &options();
-int set_batch_option(const char *key, int value);   // batch.cu: "batch.g2048", "batch.g4608", "batch.pred_lds"
+int set_batch_option(const char *key, int value);
+// GM_TRACE=1: print "[gm] <phase> <ms>" to stderr at phase boundaries (synchronises the stream; off by default)
+void trace_phase(cudaStream_t s, const char *name);   // batch.cu: "batch.g2048", "batch.g4608", "batch.pred_lds"
 
 }  // namespace gm
 

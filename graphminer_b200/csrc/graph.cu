@@ -5,6 +5,8 @@
 // Everything after the initial H2D copy is built ON THE DEVICE: the reference
 // builds the COO list in a single host thread (src/common/graph.cc:308-321).
 #include "gm_internal.cuh"
+#include <chrono>
+#include <cstdlib>
 
 #include <cub/cub.cuh>
 #include <mutex>
@@ -18,6 +20,16 @@ void set_error(const char *fmt, ...) {
   g_err = buf;
 }
 Options &options() { static Options o; return o; }
+
+void trace_phase(cudaStream_t s, const char *name) {
+  static const bool on = [] { const char *e = getenv("GM_TRACE"); return e && *e && *e != '0'; }();
+  if (!on) return;
+  static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  cudaStreamSynchronize(s);
+  auto now = std::chrono::steady_clock::now();
+  if (name) fprintf(stderr, "[gm] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - last).count());
+  last = now;
+}
 
 // ------------------------------------------------------------------------------------------
 // small device helpers
@@ -286,6 +298,7 @@ int ensure_items(gm_graph *g, int mode) {
   GM_CUDA(dfree(g, off));
   GM_CUDA(cudaGetLastError());
   g->items_ready[mode] = true;
+  trace_phase(g->stream, "work items");
   return GM_OK;
 }
 
@@ -323,6 +336,7 @@ int end_timed(gm_graph *g, int launches, int ncounts, uint64_t *out) {
   }
   GM_CUDA(cudaMemcpyAsync(g->h_counts, g->d_counts, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
+  trace_phase(g->stream, "solver kernels + D2H");
   GM_CUDA(cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1));
   g->last_launches = launches;
   for (int i = 0; i < ncounts; i++) out[i] = g->h_counts[i];
@@ -449,6 +463,7 @@ int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, in
   if (rowptr[nv] != ne) { set_error("gm_graph_upload: rowptr[nv]=%lld != ne=%lld", (long long)rowptr[nv], (long long)ne); return GM_EINVAL; }
   int ndev = 0; gm_device_count(&ndev);
   if (device < 0 || device >= ndev) { set_error("gm_graph_upload: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
+  trace_phase(nullptr, nullptr);
   gm_graph *g = new gm_graph();
   g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
   int r = [&]() -> int {
@@ -462,6 +477,7 @@ int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, in
     if (ne > 0) GM_CUDA(cudaMemcpyAsync(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice, g->stream));
     GM_TRY(init_common(g));
     GM_CUDA(cudaStreamSynchronize(g->stream));
+    trace_phase(g->stream, "upload (H2D CSR)");
     return GM_OK;
   }();
   if (r != GM_OK) { gm_graph_free(g); return r; }
@@ -486,6 +502,7 @@ int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv,
 }
 
 int gm_graph_free(gm_graph_t *g) {
+  if (g) trace_phase(g->stream, nullptr);
   if (!g) return GM_OK;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);

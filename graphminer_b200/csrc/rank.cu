@@ -147,6 +147,7 @@ int ensure_ranked(gm_graph *g) {
     uint32_t total_units = 0;
     GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
+    trace_phase(g->stream, "rank: vertex order");
     GM_CUDA(dfree(g, vk0)); vk0 = nullptr; GM_CUDA(dfree(g, vk1)); vk1 = nullptr; GM_CUDA(dfree(g, indeg)); indeg = nullptr;
     if ((uint64_t(ne) + 3ull * uint64_t(nv)) >= (1ull << 32)) return GM_OK;      // element offsets must fit 32 bits
     // 2. edges by (new source, new destination)
@@ -155,6 +156,7 @@ int ensure_ranked(gm_graph *g) {
     k_edge_keys<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, rank, ek0);
     GM_TRY(sort_keys(g, ek0, ek1, ne, 32 + bits_of(uint64_t(nv))));
     GM_CUDA(cudaStreamSynchronize(g->stream));
+    trace_phase(g->stream, "rank: edge sort");
     GM_CUDA(dfree(g, ek0)); ek0 = nullptr;
     // 3. aligned rows + partner records
     const int64_t acol_len = int64_t(total_units) * 4;
@@ -174,6 +176,7 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(cudaMemcpyAsync(&nrec, g->rk_prow + nv, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
+    trace_phase(g->stream, "rank: rows + count");
     if (h_bad) return GM_OK;                                                     // not the (degree,id) orientation
     GM_CUDA(dmalloc(g, &g->rk_prec, sizeof(uint2) * size_t(nrec > 0 ? nrec : 1)));
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
@@ -181,6 +184,7 @@ int ensure_ranked(gm_graph *g) {
                                                        g->rk_acol, cnt, g->rk_prow, g->rk_prec, bad);
     GM_CUDA(cudaStreamSynchronize(g->stream));
     GM_CUDA(cudaGetLastError());
+    trace_phase(g->stream, "rank: partner records");
     g->rk_valid = true;
     g->rk_orig = orig_of; orig_of = nullptr;
     return GM_OK;
