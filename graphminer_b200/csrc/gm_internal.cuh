@@ -47,6 +47,7 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
+  std::string sgl_algo = "auto";     // diamond: auto|support (DAG triangle supports) | list (operator-API warp-per-edge kernel)
   std::string tc_shard = "source";   // which endpoint of an edge the source range of a shard refers to (ranked TC kernel)
   int chunk = 0;   // 0 = default per kernel
 };
@@ -98,6 +99,13 @@ struct gm_graph {
   gm::eidType *rk_prow = nullptr;      // per new root: offsets into rk_prec (nv+1)
   uint2 *rk_prec = nullptr;            // partner records {element offset of the suffix, length}
   gm::vidType *rk_orig = nullptr;      // new id -> original id
+  int64_t rk_acol_len = 0;             // elements of rk_acol (aligned, padded)
+
+  // undirected input: device-side (degree,id) orientation kept in a child handle (support.cu), and the
+  // per-edge triangle supports of the diamond solver (indexed like the child's rk_acol)
+  gm_graph *dag_child = nullptr;
+  gm::eidType *dag_rowptr = nullptr; gm::vidType *dag_colidx = nullptr;
+  uint32_t *d_support = nullptr; int64_t support_len = 0;
 
   // scratch + results
   unsigned long long *d_counts = nullptr;     // 8 accumulators
@@ -142,6 +150,9 @@ int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
+int ensure_dag_child(gm_graph *g);
+int prepare_diamond_support(gm_graph *g, bool *ok);
+int run_diamond_support(gm_graph *g, int *launches);
 int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break = 0);
 int clique4_alg_bytes(gm_graph *g, uint64_t *out);
 int ensure_scratch(gm_graph *g, size_t bytes);

@@ -443,6 +443,9 @@ int gm_set_option(const char *key, const char *value) {
   if (k == "tc.algo") {
     if (v != "auto" && v != "rank" && v != "hash" && v != "hash_rev" && v != "bs") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_algo = v;
+  } else if (k == "sgl.algo") {
+    if (v != "auto" && v != "support" && v != "list") { set_error("sgl.algo: unknown value '%s'", value); return GM_EINVAL; }
+    options().sgl_algo = v;
   } else if (k == "tc.shard") {
     if (v != "source" && v != "dest") { set_error("tc.shard: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_shard = v;
@@ -507,6 +510,8 @@ int gm_graph_free(gm_graph_t *g) {
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   free_aux(g);
+  if (g->dag_child) { gm_graph_free(g->dag_child); g->dag_child = nullptr; }
+  dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support);
   if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
   dfree(g, g->d_counts); dfree(g, g->d_ticket); dfree(g, g->d_scratch); dfree(g, g->d_gmat);
   if (g->h_counts) cudaFreeHost(g->h_counts);
@@ -527,6 +532,7 @@ int gm_graph_set_stream(gm_graph_t *g, void *cuda_stream) {
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   if (cuda_stream) { g->stream = static_cast<cudaStream_t>(cuda_stream); g->own_stream = false; }
   else { GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)); g->own_stream = true; }
+  if (g->dag_child) GM_TRY(gm_graph_set_stream(g->dag_child, g->stream));
   return GM_OK;
 }
 

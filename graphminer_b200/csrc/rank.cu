@@ -160,6 +160,7 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(dfree(g, ek0)); ek0 = nullptr;
     // 3. aligned rows + partner records
     const int64_t acol_len = int64_t(total_units) * 4;
+    g->rk_acol_len = acol_len;
     GM_CUDA(dmalloc(g, &g->rk_vinfo, sizeof(uint2) * size_t(nv)));
     GM_CUDA(dmalloc(g, &g->rk_acol, sizeof(vidType) * size_t(acol_len > 0 ? acol_len : 4)));
     GM_CUDA(dmalloc(g, &cnt, sizeof(unsigned long long) * (size_t(nv) + 1)));

@@ -45,7 +45,8 @@ int gm_version(void);                       /* 10000*major + 100*minor + patch *
 int gm_device_count(int *count);            /* cudaGetDeviceCount; 0 devices is not an error */
 /* Runtime knobs replacing the reference's compile-time macros (src/common.mk:72-114).
  * keys: "tc.algo" = auto|hash|hash_rev|bs|merge, "clique.algo" = auto|bitmap|list,
- *       "sched.chunk" = partners per work item,
+ *       "sgl.algo" = auto|support|list (diamond: per-edge triangle supports on the DAG, or the
+ *       warp-per-edge operator-API kernel), "sched.chunk" = partners per work item,
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source
  *       (the reference's semantics, default) or by their destination (same total over a partition of
  *       the vertex set; keeps each root's table on one shard -- set before gm_graph_prepare),

@@ -26,6 +26,7 @@ def _reset_options():
     capi.set_option("clique.algo", "auto")
     capi.set_option("sched.chunk", 0)
     capi.set_option("tc.shard", "source")
+    capi.set_option("sgl.algo", "auto")
 
 
 def _graph(name):
@@ -255,6 +256,44 @@ def test_sgl_shards_add_up():
                 assert got == oracle.sgl(rp, ci, p, (b, e)), (p, b, e)
                 tot += got
             assert tot == GOLD["rmat10"][p]
+
+
+@pytest.mark.parametrize("algo", ["support", "list"])
+def test_diamond_both_algorithms(algo, citeseer, mico):
+    """diamond by per-edge triangle supports on the device-oriented DAG (support.cu) and by the
+    warp-per-edge operator-API kernel: KATs, golden R-MAT / shaped counts, per-shard oracle equality,
+    degenerate graphs."""
+    capi.set_option("sgl.algo", algo)
+    for (rp, ci, md), name in ((citeseer, "citeseer"), (mico, "mico")):
+        with capi.DeviceGraph(rp, ci, md) as g:
+            assert g.sgl("diamond") == KAT[name]["diamond"]
+            assert g.sgl("diamond") == KAT[name]["diamond"]       # cached structures, second call
+    for name in ("rmat8", "rmat12", "rmat14", "shaped3000"):
+        rp, ci = _graph(name)
+        with capi.DeviceGraph(rp, ci, 0) as g:
+            want = GOLD[name]["diamond"] if name in GOLD else oracle.sgl(rp, ci, "diamond")
+            assert g.sgl("diamond") == want, name
+    rp, ci = _graph("rmat10")
+    nv = len(rp) - 1
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        tot = 0
+        for b, e in ((0, 300), (300, 301), (301, nv)):
+            g.set_source_range(b, e)
+            got = g.sgl("diamond")
+            assert got == oracle.sgl(rp, ci, "diamond", (b, e)), (b, e)
+            tot += got
+        assert tot == GOLD["rmat10"]["diamond"]
+    # K_n: every edge lies in n-2 triangles -> C(n,2) * C(n-2,2) diamonds; star / empty graph: none
+    n = 40
+    rp = np.arange(0, n * (n - 1) + 1, n - 1, dtype=np.int64)
+    ci = np.concatenate([np.delete(np.arange(n, dtype=np.int32), i) for i in range(n)])
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        assert g.sgl("diamond") == (n * (n - 1) // 2) * ((n - 2) * (n - 3) // 2)
+    m = 50
+    rp = np.concatenate([[0], np.arange(m, 2 * m + 1)]).astype(np.int64)
+    ci = np.concatenate([np.arange(1, m + 1), np.zeros(m)]).astype(np.int32)
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        assert g.sgl("diamond") == 0
 
 
 # ---------------------------------------------------------------------------------------------
