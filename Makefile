@@ -6,7 +6,7 @@ NVFLAGS  = $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(CCBIN) -Xcompiler -fPIC,-fo
            --expt-relaxed-constexpr --expt-extended-lambda -Iinclude $(EXTRA_NVFLAGS)
 CSRC     = graphminer_b200/csrc
 LIB      = graphminer_b200/libgminer_b200.so
-CU_SRCS  = $(CSRC)/graph.cu $(CSRC)/rank.cu $(CSRC)/tc.cu $(CSRC)/batch.cu $(CSRC)/patterns.cu $(CSRC)/clique_bitmap.cu $(CSRC)/support.cu $(CSRC)/solvers.cu
+CU_SRCS  = $(CSRC)/graph.cu $(CSRC)/rank.cu $(CSRC)/tc.cu $(CSRC)/batch.cu $(CSRC)/patterns.cu $(CSRC)/clique_bitmap.cu $(CSRC)/support.cu $(CSRC)/cycle4.cu $(CSRC)/solvers.cu
 CC_SRCS  = $(CSRC)/host_graph.cc
 OBJS     = $(CU_SRCS:.cu=.o) $(CC_SRCS:.cc=.o)
 HDRS     = $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h include/*.h include/gm/*.cuh)

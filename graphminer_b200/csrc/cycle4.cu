@@ -1,0 +1,383 @@
+// 4-motif counting, formula form, on the rank-relabelled DAG (the fast path behind gm_motif_formula*).
+//
+// Reference: src/motif/gpu_formula.cu:22-110 + gpu_kernels/motif4_rest.cuh:1-35, cycle4_edge_warp.cuh:2-44,
+// clique4_edge_warp.cuh:2-32; CPU: src/motif/omp_formula.cc:8-46 + cpu_kernels/automine_formula.h:21-56.
+// The formula solver needs, per undirected edge, its triangle count (closed forms for 3-star, 4-path,
+// tailed triangle and diamond), plus the number of 4-cycles and of 4-cliques, each counted once:
+//   raw[0,1,2,4]  closed forms of tri(e), d(u), d(v)   <- per-edge triangle SUPPORTS (support.cu), one pass
+//   raw[5]        4-cliques                              <- the bit-matrix kernel (clique_bitmap.cu) on the DAG
+//   raw[3]        4-cycles                               <- this file
+// The reference enumerates the 4-cycles of every edge by intersecting undirected rows (hub rows again and
+// again).  Here every 4-cycle is counted at its HIGHEST-RANKED vertex u (rank = (degree, id) order):
+//     for v in N-(u) (lower-ranked neighbours), for w in N(v) with w < u, w != u:  L[w] += 1
+//     cycles(u) = sum_w C(L[w], 2)
+// i.e. pairs of wedges u-v-w that share both end points; only wedges whose maximum is an END point are
+// used, so each cycle is found exactly once (at the diagonal through its maximum).  With the degree order
+// the wedge count is O(m * arboricity).  N(v) ∩ {< u} = N-(v) (all of it) ∪ the prefix of the rank-sorted
+// out-row of v before u, so all that is needed on top of rank.cu are the in-rows with, per in-edge, the
+// position of u in v's out-row.  sum_w C(L[w],2) is accumulated on the fly as the sum of the values the
+// atomic increments return.  Three tiers by wedge count W(u):
+//   small (W <= 512)  warp per root, shared-memory open-addressing table;
+//   mid               CTA per root, a dense u32 array per CTA in global memory, second pass clears it;
+//   heavy (W > 2^21)  one root at a time on the whole grid, one dense array, cudaMemset clears it.
+#include "gm_internal.cuh"
+
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+namespace gm {
+
+int run_kclique_bitmap(gm_graph *g, int k, int *launches, bool *handled);
+int prepare_kclique_bitmap(gm_graph *g);
+
+static inline unsigned nblk(int64_t n, int per = 256) { return unsigned((n + per - 1) / per); }
+
+constexpr uint64_t kC4SmallMax = 512;
+constexpr uint64_t kC4MidMaxDefault = uint64_t(1) << 21;
+constexpr int kC4SmallSlots = 1024;          // per warp, >= 2 * kC4SmallMax
+constexpr int kC4MidThreads = 512;
+
+// ---- in-rows of the ranked DAG: incol[inrow[u] + k] = {v, position of u in the out-row of v} -------------
+template <int PASS>
+__global__ void k_c4_inrows(vidType nv, const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol,
+                            unsigned long long *__restrict__ cnt, const eidType *__restrict__ inrow, uint2 *__restrict__ incol) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType a = vidType(t >> 3); const int sub = int(t & 7);
+  if (a >= nv) return;
+  const uint2 vi = vinfo[a];
+  const size_t base = size_t(vi.x) << 2;
+  for (uint32_t i = sub; i < vi.y; i += 8) {
+    const vidType b = acol[base + i];
+    const unsigned long long p = atomicAdd(&cnt[b], 1ull);
+    if (PASS == 1) incol[inrow[b] + eidType(p)] = make_uint2(uint32_t(a), i);
+  }
+}
+
+// W(u) = sum over in-edges (v, pos) of indeg(v) + pos; class 1 small / 2 mid / 3 heavy / 0 nothing to do
+__global__ void k_c4_classify(vidType nv, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+                              const vidType *__restrict__ orig_of, vidType fb, vidType fe, unsigned long long small_max,
+                              unsigned long long mid_max, unsigned long long *__restrict__ W, unsigned char *__restrict__ cls) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType u = vidType(t >> 3); const int sub = int(t & 7);
+  unsigned long long w = 0;
+  if (u < nv) {
+    for (eidType e = inrow[u] + sub; e < inrow[u + 1]; e += 8) {
+      const uint2 r = incol[e];
+      w += (unsigned long long)(inrow[r.x + 1] - inrow[r.x]) + r.y;
+    }
+  }
+  w += __shfl_xor_sync(kFullMask, w, 1); w += __shfl_xor_sync(kFullMask, w, 2); w += __shfl_xor_sync(kFullMask, w, 4);
+  if (u < nv && sub == 0) {
+    const vidType o = orig_of[u];
+    const bool mine = o >= fb && o < fe && (inrow[u + 1] - inrow[u]) >= 2 && w >= 2;
+    W[u] = w;
+    cls[u] = !mine ? 0 : w <= small_max ? 1 : w <= mid_max ? 2 : 3;
+  }
+}
+
+struct ClsIs { const unsigned char *cls; unsigned char k; __device__ bool operator()(const vidType &u) const { return cls[u] == k; } };
+
+// ---- tier 1: warp per root, shared-memory table -------------------------------------------------------
+__global__ void __launch_bounds__(128)
+c4_small_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
+                const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+                const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, int *ticket, AccType *total) {
+  __shared__ uint32_t s_keys[4][kC4SmallSlots];             // 4 warps x (4 + 4) KB
+  __shared__ uint32_t s_cnts[4][kC4SmallSlots];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t *keys = s_keys[w], *cnts = s_cnts[w];
+  AccType acc = 0;
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 4);
+    const int64_t first = int64_t(__shfl_sync(kFullMask, t, 0));
+    if (first >= nroots) break;
+    for (int64_t idx = first; idx < min(first + 4, nroots); idx++) {
+      const vidType u = roots[idx];
+      const uint32_t need = uint32_t(W[u]) * 2u;
+      const int bits = max(5, 32 - __clz(int(need) - 1));           // slots = 2^bits >= 2 W, at least 32
+      const uint32_t mask = (1u << bits) - 1u;
+      __syncwarp();
+      for (uint32_t i = lane; i <= mask; i += 32) { keys[i] = 0xffffffffu; cnts[i] = 0u; }
+      __syncwarp();
+      auto insert = [&](uint32_t x) {
+        uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+        while (true) {
+          const uint32_t old = atomicCAS(&keys[h], 0xffffffffu, x);
+          if (old == 0xffffffffu || old == x) { acc += atomicAdd(&cnts[h], 1u); break; }
+          h = (h + 1) & mask;
+        }
+      };
+      for (eidType e = inrow[u]; e < inrow[u + 1]; e++) {
+        const uint2 r = incol[e];                                   // warp-uniform
+        const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+        for (int i = lane; i < nin; i += 32) insert(incol[vb + i].x);
+        const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
+        for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
+      }
+    }
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+// ---- tiers 2 and 3: dense counting array in global memory -------------------------------------------------
+// PHASE 0: L[w]++ and accumulate the old values; PHASE 1: L[w] = 0.  `nwarps` warps share the in-edges of u.
+template <int PHASE>
+__device__ __forceinline__ AccType c4_dense_pass(vidType u, int wid, int nwarps, int lane, uint32_t *L,
+                                                 const eidType *inrow, const uint2 *incol, const uint2 *vinfo, const vidType *acol) {
+  AccType acc = 0;
+  for (eidType e = inrow[u] + wid; e < inrow[u + 1]; e += nwarps) {
+    const uint2 r = incol[e];
+    const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+    for (int i = lane; i < nin; i += 32) {
+      const uint32_t x = incol[vb + i].x;
+      if (PHASE == 0) acc += atomicAdd(&L[x], 1u); else L[x] = 0u;
+    }
+    const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
+    for (int i = lane; i < int(r.y); i += 32) {
+      const uint32_t x = uint32_t(row[i]);
+      if (PHASE == 0) acc += atomicAdd(&L[x], 1u); else L[x] = 0u;
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kC4MidThreads)
+c4_mid_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+              const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *dense, size_t stride,
+              int *ticket, AccType *total) {
+  __shared__ int64_t s_next;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t *L = dense + size_t(blockIdx.x) * stride;
+  AccType acc = 0;
+  while (true) {
+    __syncthreads();                                                // previous root cleared
+    if (threadIdx.x == 0) s_next = int64_t(atomicAdd(ticket, 1));
+    __syncthreads();
+    const int64_t idx = s_next;
+    if (idx >= nroots) break;
+    const vidType u = roots[idx];
+    acc += c4_dense_pass<0>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol);
+    __syncthreads();
+    c4_dense_pass<1>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol);
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+__global__ void __launch_bounds__(256)
+c4_heavy_kernel(vidType u, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+                const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *L, AccType *total) {
+  const int lane = threadIdx.x & 31;
+  const int wid = int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = int((int64_t(gridDim.x) * blockDim.x) >> 5);
+  AccType acc = c4_dense_pass<0>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol);
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+// ---- closed forms from the supports (motif4_rest.cuh:16-28) ------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_motif4_closed(vidType nv, const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, const vidType *__restrict__ orig_of,
+                const uint32_t *__restrict__ sup, const eidType *__restrict__ urowptr, vidType fb, vidType fe, AccType *counters) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType a = vidType(t >> 3); const int sub = int(t & 7);
+  AccType c0 = 0, c1 = 0, c2 = 0, c4 = 0;
+  if (a < nv) {
+    const uint2 vi = vinfo[a];
+    const size_t base = size_t(vi.x) << 2;
+    const vidType oa = orig_of[a];
+    const AccType da = AccType(urowptr[oa + 1] - urowptr[oa]);
+    for (uint32_t i = sub; i < vi.y; i += 8) {
+      const vidType ob = orig_of[acol[base + i]];
+      const vidType v0 = oa > ob ? oa : ob;
+      if (v0 < fb || v0 >= fe) continue;
+      const AccType tri = sup[base + i], db = AccType(urowptr[ob + 1] - urowptr[ob]);
+      const AccType su = da - tri - 1, sv = db - tri - 1;
+      c4 += tri * (tri - 1);
+      c2 += tri * (su + sv);
+      c1 += su * sv;
+      c0 += su * (su - 1) + sv * (sv - 1);
+    }
+  }
+  c0 = warp_reduce(c0); c1 = warp_reduce(c1); c2 = warp_reduce(c2); c4 = warp_reduce(c4);
+  if ((threadIdx.x & 31) == 0) {
+    if (c0) atomicAdd(&counters[0], c0);
+    if (c1) atomicAdd(&counters[1], c1);
+    if (c2) atomicAdd(&counters[2], c2);
+    if (c4) atomicAdd(&counters[4], c4);
+  }
+}
+
+__global__ void k_motif4_induced_cycles(AccType *counters) {
+  counters[3] = counters[3] + 3ull * counters[5] - counters[4] / 2ull;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static void free_c4_lists(gm_graph *c) {
+  dfree(c, c->c4_small); dfree(c, c->c4_mid); dfree(c, c->c4_W);
+  c->c4_small = c->c4_mid = nullptr; c->c4_W = nullptr;
+  c->c4_nsmall = c->c4_nmid = 0; c->c4_heavy.clear();
+  c->c4_lists_ready = false;
+}
+
+void invalidate_range_structures_of_child(gm_graph *c) {
+  if (!c) return;
+  cudaStreamSynchronize(c->stream);
+  free_c4_lists(c);
+  for (int cl = 0; cl < 4; cl++) { dfree(c, c->items[4][cl].d_items); c->items[4][cl] = ItemList(); }
+  c->items_ready[4] = false;
+  for (int sb = 0; sb < 2; sb++) {                                  // COO task lists are per range too
+    dfree(c, c->d_src[sb]); c->d_src[sb] = nullptr;
+    if (sb == 1) dfree(c, c->d_dst[sb]);
+    c->d_dst[sb] = nullptr; c->coo_ready[sb] = false; c->nnz[sb] = 0;
+  }
+}
+
+void free_c4(gm_graph *c) {
+  free_c4_lists(c);
+  dfree(c, c->c4_inrow); dfree(c, c->c4_incol); dfree(c, c->c4_dense);
+  c->c4_inrow = nullptr; c->c4_incol = nullptr; c->c4_dense = nullptr;
+}
+
+// c = the DAG child (ranked, full range); [fb, fe) = the parent's source range (original ids)
+static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
+  GM_CUDA(cudaSetDevice(c->device));
+  const vidType nv = c->nv; const eidType ne = c->ne;
+  if (!c->c4_inrow) {
+    unsigned long long *cnt = nullptr;
+    GM_CUDA(dmalloc(c, &cnt, sizeof(unsigned long long) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(c, &c->c4_inrow, sizeof(eidType) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(c, &c->c4_incol, sizeof(uint2) * size_t(ne > 0 ? ne : 1)));
+    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), c->stream));
+    k_c4_inrows<0><<<nblk(int64_t(nv) * 8), 256, 0, c->stream>>>(nv, c->rk_vinfo, c->rk_acol, cnt, nullptr, nullptr);
+    GM_CUDA(cudaMemcpyAsync(c->c4_inrow, cnt, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, c->stream));
+    size_t tmp = 0;
+    GM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->c4_inrow, c->c4_inrow, int64_t(nv) + 1, c->stream));
+    GM_TRY(ensure_scratch(c, tmp));
+    GM_CUDA(cub::DeviceScan::ExclusiveSum(c->d_scratch, tmp, c->c4_inrow, c->c4_inrow, int64_t(nv) + 1, c->stream));
+    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), c->stream));
+    k_c4_inrows<1><<<nblk(int64_t(nv) * 8), 256, 0, c->stream>>>(nv, c->rk_vinfo, c->rk_acol, cnt, c->c4_inrow, c->c4_incol);
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+    GM_CUDA(dfree(c, cnt));
+    trace_phase(c->stream, "4-cycle: in-rows");
+  }
+  if (c->c4_lists_ready && c->c4_fb == fb && c->c4_fe == fe) return GM_OK;
+  free_c4_lists(c);
+  unsigned char *cls = nullptr; int64_t *d_num = nullptr; vidType *heavy = nullptr;
+  GM_CUDA(dmalloc(c, &c->c4_W, sizeof(unsigned long long) * size_t(nv)));
+  GM_CUDA(dmalloc(c, &cls, size_t(nv)));
+  GM_CUDA(dmalloc(c, &d_num, sizeof(int64_t)));
+  GM_CUDA(dmalloc(c, &c->c4_small, sizeof(vidType) * size_t(nv)));
+  GM_CUDA(dmalloc(c, &c->c4_mid, sizeof(vidType) * size_t(nv)));
+  GM_CUDA(dmalloc(c, &heavy, sizeof(vidType) * size_t(nv)));
+  // tier thresholds ("c4.small_max" <= 512, "c4.mid_max": test hooks that force roots into the larger tiers)
+  const unsigned long long small_max = std::min<unsigned long long>(kC4SmallMax, options().c4_small_max >= 0 ? options().c4_small_max : kC4SmallMax);
+  const unsigned long long mid_max = options().c4_mid_max >= 0 ? (unsigned long long)options().c4_mid_max : kC4MidMaxDefault;
+  k_c4_classify<<<nblk(int64_t(nv) * 8), 256, 0, c->stream>>>(nv, c->c4_inrow, c->c4_incol, c->rk_orig, fb, fe, small_max, mid_max, c->c4_W, cls);
+  vidType *outs[3] = {c->c4_small, c->c4_mid, heavy};
+  int64_t nums[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) {
+    thrust::counting_iterator<vidType> ids(0);
+    ClsIs pred{cls, (unsigned char)(k + 1)};
+    size_t tmp = 0;
+    GM_CUDA(cub::DeviceSelect::If(nullptr, tmp, ids, outs[k], d_num, int64_t(nv), pred, c->stream));
+    GM_TRY(ensure_scratch(c, tmp));
+    GM_CUDA(cub::DeviceSelect::If(c->d_scratch, tmp, ids, outs[k], d_num, int64_t(nv), pred, c->stream));
+    GM_CUDA(cudaMemcpyAsync(&nums[k], d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  c->c4_nsmall = nums[0]; c->c4_nmid = nums[1];
+  c->c4_heavy.resize(size_t(nums[2]));
+  if (nums[2] > 0) GM_CUDA(cudaMemcpyAsync(c->c4_heavy.data(), heavy, sizeof(vidType) * size_t(nums[2]), cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  GM_CUDA(dfree(c, cls)); GM_CUDA(dfree(c, d_num)); GM_CUDA(dfree(c, heavy));
+  // dense arrays: one per resident CTA of the mid kernel (array 0 also serves the heavy roots)
+  if (!c->c4_dense && (nums[1] > 0 || nums[2] > 0)) {
+    int occ = 0;
+    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c4_mid_kernel, kC4MidThreads, 0));
+    if (occ < 1) occ = 1;
+    c->c4_dense_stride = (size_t(nv) + 31) & ~size_t(31);
+    size_t free_b = 0, total_b = 0;
+    GM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int64_t ctas = std::min<int64_t>(int64_t(occ) * c->num_sms, std::max<int64_t>(1, int64_t(double(free_b) * 0.5) / int64_t(c->c4_dense_stride * 4)));
+    c->c4_dense_ctas = int(ctas);
+    if (dmalloc(c, &c->c4_dense, c->c4_dense_stride * 4 * size_t(ctas)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle counting arrays)"); return GM_ENOMEM; }
+    GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, c->c4_dense_stride * 4 * size_t(ctas), c->stream));
+  }
+  c->c4_fb = fb; c->c4_fe = fe; c->c4_lists_ready = true;
+  trace_phase(c->stream, "4-cycle: root tiers");
+  return GM_OK;
+}
+
+// everything the fast formula pass needs; *ok = false -> the caller keeps the operator-API kernel
+int prepare_motif4_fast(gm_graph *g, bool *ok) {
+  *ok = false;
+  bool sup = false;
+  GM_TRY(prepare_diamond_support(g, &sup));
+  if (!sup) return GM_OK;
+  gm_graph *c = g->dag_child;
+  GM_TRY(ensure_c4(c, g->src_begin, g->src_end));
+  // 4-clique work items of the child for the parent's source range (roots by original id)
+  if (!c->items_ready[4]) {
+    c->src_begin = g->src_begin; c->src_end = g->src_end;
+    int r = prepare_kclique_bitmap(c);
+    c->src_begin = 0; c->src_end = c->nv;
+    GM_TRY(r);
+  }
+  *ok = true;
+  return GM_OK;
+}
+
+int run_motif4_fast(gm_graph *g, int *launches) {
+  gm_graph *c = g->dag_child;
+  // 1. supports (full graph) -> closed forms over the owned edges
+  GM_TRY(run_support_pass(g, launches));
+  GM_CUDA(cudaMemsetAsync(g->d_ticket, 0, 8 * sizeof(int), g->stream));        // tickets are reused below
+  if (c->nv > 0) {
+    k_motif4_closed<<<nblk(int64_t(c->nv) * 8), 256, 0, g->stream>>>(c->nv, c->rk_vinfo, c->rk_acol, c->rk_orig, g->d_support,
+                                                                     g->d_rowptr, g->src_begin, g->src_end, g->d_counts);
+    (*launches)++;
+  }
+  // 2. 4-cycles
+  if (c->c4_nsmall > 0) {
+    int grid = int(std::min<int64_t>((c->c4_nsmall + 15) / 16, int64_t(c->num_sms) * 6));
+    c4_small_kernel<<<grid, 128, 0, g->stream>>>(c->c4_small, c->c4_nsmall, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                 g->d_ticket + 0, g->d_counts + 3);
+    (*launches)++;
+  }
+  if (c->c4_nmid > 0) {
+    int grid = int(std::min<int64_t>(c->c4_nmid, int64_t(c->c4_dense_ctas)));
+    c4_mid_kernel<<<grid, kC4MidThreads, 0, g->stream>>>(c->c4_mid, c->c4_nmid, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                         c->c4_dense, c->c4_dense_stride, g->d_ticket + 1, g->d_counts + 3);
+    (*launches)++;
+  }
+  for (vidType u : c->c4_heavy) {
+    c4_heavy_kernel<<<c->num_sms * 8, 256, 0, g->stream>>>(u, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol, c->c4_dense, g->d_counts + 3);
+    GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, c->c4_dense_stride * 4, g->stream));
+    (*launches)++;
+  }
+  // 3. 4-cliques: the bit-matrix kernel on the child, accumulating straight into counters[5]
+  {
+    unsigned long long *save = c->d_counts;
+    c->d_counts = g->d_counts + 5;
+    GM_CUDA(cudaMemsetAsync(c->d_ticket, 0, 8 * sizeof(int), g->stream));
+    c->src_begin = g->src_begin; c->src_end = g->src_end;
+    bool handled = false;
+    int r = run_kclique_bitmap(c, 4, launches, &handled);
+    c->src_begin = 0; c->src_end = c->nv;
+    c->d_counts = save;
+    GM_TRY(r);
+  }
+  // 4. the wedge pairs count EVERY 4-cycle; the formula wants the chordless ones: a diamond holds one
+  // 4-cycle, a 4-clique three, and (vertex-induced) diamonds = raw[4]/2 - 6 raw[5] (gpu_formula.cu:86-93).
+  // Shard-wise the three terms are partitioned differently, so a shard's value may wrap; the sum over the
+  // shards (mod 2^64) is exact.
+  k_motif4_induced_cycles<<<1, 1, 0, g->stream>>>(g->d_counts);
+  (*launches)++;
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+}  // namespace gm

@@ -47,6 +47,8 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
+  long long c4_small_max = -1, c4_mid_max = -1;   // 4-cycle tier thresholds (wedges per root); -1 = defaults
+  std::string motif_algo = "auto";   // 4-motif formula: auto|fast (supports + wedge-pair 4-cycles + bit-matrix 4-cliques) | list
   std::string sgl_algo = "auto";     // diamond: auto|support (DAG triangle supports) | list (operator-API warp-per-edge kernel)
   std::string tc_shard = "source";   // which endpoint of an edge the source range of a shard refers to (ranked TC kernel)
   int chunk = 0;   // 0 = default per kernel
@@ -106,6 +108,13 @@ struct gm_graph {
   gm_graph *dag_child = nullptr;
   gm::eidType *dag_rowptr = nullptr; gm::vidType *dag_colidx = nullptr;
   uint32_t *d_support = nullptr; int64_t support_len = 0;
+  // 4-cycle counting on the ranked DAG (cycle4.cu; lives in the child handle)
+  gm::eidType *c4_inrow = nullptr; uint2 *c4_incol = nullptr;        // in-rows {v, position of u in v's out-row}
+  unsigned long long *c4_W = nullptr;                               // wedges per root
+  gm::vidType *c4_small = nullptr, *c4_mid = nullptr; int64_t c4_nsmall = 0, c4_nmid = 0;
+  std::vector<gm::vidType> c4_heavy;
+  uint32_t *c4_dense = nullptr; size_t c4_dense_stride = 0; int c4_dense_ctas = 0;
+  bool c4_lists_ready = false; gm::vidType c4_fb = 0, c4_fe = 0;
 
   // scratch + results
   unsigned long long *d_counts = nullptr;     // 8 accumulators
@@ -153,6 +162,11 @@ int ensure_ranked(gm_graph *g);
 int ensure_dag_child(gm_graph *g);
 int prepare_diamond_support(gm_graph *g, bool *ok);
 int run_diamond_support(gm_graph *g, int *launches);
+int run_support_pass(gm_graph *g, int *launches);
+int prepare_motif4_fast(gm_graph *g, bool *ok);
+int run_motif4_fast(gm_graph *g, int *launches);
+void invalidate_range_structures_of_child(gm_graph *c);
+void free_c4(gm_graph *c);
 int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break = 0);
 int clique4_alg_bytes(gm_graph *g, uint64_t *out);
 int ensure_scratch(gm_graph *g, size_t bytes);

@@ -443,6 +443,13 @@ int gm_set_option(const char *key, const char *value) {
   if (k == "tc.algo") {
     if (v != "auto" && v != "rank" && v != "hash" && v != "hash_rev" && v != "bs") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_algo = v;
+  } else if (k == "c4.small_max") {
+    options().c4_small_max = atoll(value);
+  } else if (k == "c4.mid_max") {
+    options().c4_mid_max = atoll(value);
+  } else if (k == "motif.algo") {
+    if (v != "auto" && v != "fast" && v != "list") { set_error("motif.algo: unknown value '%s'", value); return GM_EINVAL; }
+    options().motif_algo = v;
   } else if (k == "sgl.algo") {
     if (v != "auto" && v != "support" && v != "list") { set_error("sgl.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().sgl_algo = v;
@@ -510,6 +517,7 @@ int gm_graph_free(gm_graph_t *g) {
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   free_aux(g);
+  free_c4(g);
   if (g->dag_child) { gm_graph_free(g->dag_child); g->dag_child = nullptr; }
   dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support);
   if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
@@ -552,6 +560,7 @@ int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end) {
   uint2 *vi = g->d_vinfo; vidType *ac = g->d_acol; g->d_vinfo = nullptr; g->d_acol = nullptr;
   free_aux(g);
   g->d_vinfo = vi; g->d_acol = ac;
+  invalidate_range_structures_of_child(g->dag_child);
   g->src_begin = begin; g->src_end = end; g->tc_bytes_cache = 0; g->c4_bytes_cache = 0; g->dia_bytes_cache = 0;
   return GM_OK;
 }

@@ -88,11 +88,14 @@ static int motif_common(gm_graph_t *g, int k, int formula, int raw, uint64_t *co
   if (!g || !counts) { set_error("gm_motif: null argument"); return GM_EINVAL; }
   if (k != 3 && k != 4) { set_error("motif: k=%d not supported (k in {3,4})", k); return GM_EUNSUPPORTED; }
   if (g->d_result && formula && !raw) { set_error("gm_motif_formula: device-side results need gm_motif_formula_raw + gm_motif_formula_finish"); return GM_EUNSUPPORTED; }
-  GM_TRY(ensure_coo(g, formula ? 1 : 0));
+  bool fast = false;
+  if (k == 4 && formula && options().motif_algo != "list") GM_TRY(prepare_motif4_fast(g, &fast));
+  if (!fast) GM_TRY(ensure_coo(g, formula ? 1 : 0));
   int launches = 0;
   g->last_alg_bytes = 0; g->last_alg_kind = 0;
   GM_TRY(begin_timed(g));
-  GM_TRY(run_motif(g, k, formula, &launches));
+  if (fast) GM_TRY(run_motif4_fast(g, &launches));
+  else GM_TRY(run_motif(g, k, formula, &launches));
   GM_TRY(end_timed(g, launches, k == 3 ? 2 : 6, counts));
   if (formula && !raw) formula_fixup(k, counts);
   return GM_OK;

@@ -249,7 +249,8 @@ int prepare_diamond_support(gm_graph *g, bool *ok) {
   return GM_OK;
 }
 
-int run_diamond_support(gm_graph *g, int *launches) {
+// zero the supports and enumerate every triangle of the DAG once (all four size classes concurrently)
+int run_support_pass(gm_graph *g, int *launches) {
   gm_graph *c = g->dag_child;
   GM_CUDA(cudaMemsetAsync(g->d_support, 0, sizeof(uint32_t) * size_t(g->support_len), g->stream));
   GM_TRY(fork_streams(g));
@@ -258,6 +259,12 @@ int run_diamond_support(gm_graph *g, int *launches) {
   GM_TRY((launch_support_class<1024, 14, 64>(g, c, 3, g->side[1], launches)));
   GM_TRY((launch_support_class<32, 7, 16>(g, c, 0, g->side[2], launches)));
   GM_TRY(join_streams(g));
+  return GM_OK;
+}
+
+int run_diamond_support(gm_graph *g, int *launches) {
+  gm_graph *c = g->dag_child;
+  GM_TRY(run_support_pass(g, launches));
   if (c->nv > 0) {
     k_diamond_sum<<<nblk(int64_t(c->nv) * 8), 256, 0, g->stream>>>(c->nv, c->rk_vinfo, c->rk_acol, c->rk_orig, g->d_support,
                                                                    g->src_begin, g->src_end, g->d_counts);

@@ -45,6 +45,8 @@ int gm_version(void);                       /* 10000*major + 100*minor + patch *
 int gm_device_count(int *count);            /* cudaGetDeviceCount; 0 devices is not an error */
 /* Runtime knobs replacing the reference's compile-time macros (src/common.mk:72-114).
  * keys: "tc.algo" = auto|hash|hash_rev|bs|merge, "clique.algo" = auto|bitmap|list,
+ *       "motif.algo" = auto|fast|list (4-motif formula: supports + wedge-pair 4-cycles + bit-matrix
+ *       4-cliques on the DAG, or the warp-per-edge operator-API kernel),
  *       "sgl.algo" = auto|support|list (diamond: per-edge triangle supports on the DAG, or the
  *       warp-per-edge operator-API kernel), "sched.chunk" = partners per work item,
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source

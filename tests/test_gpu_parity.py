@@ -27,6 +27,9 @@ def _reset_options():
     capi.set_option("sched.chunk", 0)
     capi.set_option("tc.shard", "source")
     capi.set_option("sgl.algo", "auto")
+    capi.set_option("motif.algo", "auto")
+    capi.set_option("c4.small_max", -1)
+    capi.set_option("c4.mid_max", -1)
 
 
 def _graph(name):
@@ -397,3 +400,55 @@ def test_tc_destination_sharding_adds_up():
             g.set_source_range(b, e)
             total += g.tc()
     assert total == want
+
+
+@pytest.mark.parametrize("algo", ["fast", "list"])
+def test_motif4_formula_both_algorithms(algo, citeseer, mico):
+    """4-motif formula: supports + wedge-pair 4-cycles + bit-matrix 4-cliques on the DAG (cycle4.cu) and the
+    warp-per-edge operator-API kernel; KATs, golden graphs, shards (raw sums add up before the fix-up),
+    4-cycle-only graphs that exercise the chord correction."""
+    capi.set_option("motif.algo", algo)
+    for (rp, ci, md), name in ((citeseer, "citeseer"), (mico, "mico")):
+        with capi.DeviceGraph(rp, ci, md) as g:
+            assert g.motif(4, formula=True) == KAT[name]["motif4"]
+            assert g.motif(4, formula=True) == KAT[name]["motif4"]
+    for name in ("rmat8", "rmat10", "rmat12", "rmat14", "shaped3000"):
+        rp, ci = _graph(name)
+        want = GOLD[name].get("motif4_formula") or GOLD[name].get("motif4")
+        with capi.DeviceGraph(rp, ci, 0) as g:
+            assert g.motif(4, formula=True) == want, name
+    rp, ci = _graph("rmat12")
+    nv = len(rp) - 1
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        raw = np.zeros(6, np.uint64)
+        for b, e in ((0, 1000), (1000, 1001), (1001, nv)):
+            g.set_source_range(b, e)
+            raw += np.array(g.motif(4, formula=True, raw=True), np.uint64)      # wraps mod 2^64 by design
+        assert capi.motif_formula_finish(4, raw) == GOLD["rmat12"]["motif4_formula"]
+    # complete bipartite K_{a,b}: C(a,2)*C(b,2) chordless 4-cycles, no triangles
+    a, b = 7, 9
+    rp = np.concatenate([[0], np.cumsum([b] * a + [a] * b)]).astype(np.int64)
+    ci = np.concatenate([np.arange(a, a + b)] * a + [np.arange(a)] * b).astype(np.int32)
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        got = g.motif(4, formula=True)
+        assert got[3] == (a * (a - 1) // 2) * (b * (b - 1) // 2) and got[4] == 0 and got[5] == 0
+        assert got == oracle.motif(rp, ci, 4)
+    # K_6: 15 four-cliques, no chordless cycle, no induced diamond
+    n = 6
+    rp = np.arange(0, n * (n - 1) + 1, n - 1, dtype=np.int64)
+    ci = np.concatenate([np.delete(np.arange(n, dtype=np.int32), i) for i in range(n)])
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        assert g.motif(4, formula=True) == [0, 0, 0, 0, 0, 15]
+
+
+@pytest.mark.parametrize("small_max,mid_max", [(0, -1), (0, 0), (16, 300), (512, 2000)])
+def test_motif4_cycle_tiers(small_max, mid_max):
+    """the three 4-cycle tiers (warp table / per-CTA dense array / whole-grid dense array) must agree:
+    thresholds are pushed down so that small graphs reach the mid and heavy code paths"""
+    capi.set_option("motif.algo", "fast")
+    capi.set_option("c4.small_max", small_max)
+    capi.set_option("c4.mid_max", mid_max)
+    for name in ("rmat10", "rmat14", "shaped3000"):
+        rp, ci = _graph(name)
+        with capi.DeviceGraph(rp, ci, 0) as g:
+            assert g.motif(4, formula=True) == GOLD[name]["motif4_formula"], name
