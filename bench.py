@@ -399,7 +399,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         achieved = alg_bytes / (kern_total_ms / args.steps / 1e3) / 1e9 if alg_bytes else None
         kernel = {"tc": "tc_hash_kernel<MODE=2 ranked>", "clique4": "kclique_bitmap_kernel",
-                  "diamond": "sgl_warp_edge<diamond>", "motif4": "motif formula kernels"}[wl.kind]
+                  "diamond": "tc_support_kernel + k_diamond_sum", "motif4": "tc_support_kernel + c4_{small,cta,cluster,heavy}_kernel + kclique_bitmap_kernel"}[wl.kind]
         out = {
             "metric": wl.metric, "value": value, "unit": wl.unit,
             "n_gpus": n, "steps": args.steps, "warmup": args.warmup,

@@ -16,12 +16,18 @@
 // the wedge count is O(m * arboricity).  N(v) ∩ {< u} = N-(v) (all of it) ∪ the prefix of the rank-sorted
 // out-row of v before u, so all that is needed on top of rank.cu are the in-rows with, per in-edge, the
 // position of u in v's out-row.  sum_w C(L[w],2) is accumulated on the fly as the sum of the values the
-// atomic increments return.  Three tiers by wedge count W(u):
-//   small (W <= 512)  warp per root, shared-memory open-addressing table;
-//   mid               CTA per root, a dense u32 array per CTA in global memory, second pass clears it;
-//   heavy (W > 2^21)  one root at a time on the whole grid, one dense array, cudaMemset clears it.
+// atomic increments return.  Four tiers by wedge count W(u):
+//   small (W <= 512)    warp per root, shared-memory open-addressing table;
+//   cta   (W <= 24576)  CTA per root, 192 KB shared-memory table (32 K keys + packed 16-bit counters);
+//   mid   (W <= 2^21)   one thread-block CLUSTER of 16 CTAs per root on a dense u32 array in global memory
+//                       (hardware cluster barrier between the counting and the clearing pass); only as many
+//                       clusters run as dense arrays fit the 126 MB L2 together, so the atomics stay on chip
+//                       (one array per CTA spills to HBM: 1.4 s instead of 0.2 s on the Friendster shape / 16);
+//   heavy               one root at a time on the whole grid, one dense array, cudaMemset clears it.
 #include "gm_internal.cuh"
+#include <cstdlib>
 
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -32,8 +38,14 @@ int prepare_kclique_bitmap(gm_graph *g);
 
 static inline unsigned nblk(int64_t n, int per = 256) { return unsigned((n + per - 1) / per); }
 
+namespace cg = cooperative_groups;
+
 constexpr uint64_t kC4SmallMax = 512;
+constexpr uint64_t kC4CtaMax = 24576;        // <= 0.75 * kC4CtaSlots
+constexpr int kC4CtaSlots = 32768;
+constexpr int kC4CtaSmem = kC4CtaSlots * 4 + kC4CtaSlots * 2;
 constexpr uint64_t kC4MidMaxDefault = uint64_t(1) << 21;
+constexpr int kC4Cluster = 16;
 constexpr int kC4SmallSlots = 1024;          // per warp, >= 2 * kC4SmallMax
 constexpr int kC4MidThreads = 512;
 
@@ -56,7 +68,8 @@ __global__ void k_c4_inrows(vidType nv, const uint2 *__restrict__ vinfo, const v
 // W(u) = sum over in-edges (v, pos) of indeg(v) + pos; class 1 small / 2 mid / 3 heavy / 0 nothing to do
 __global__ void k_c4_classify(vidType nv, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
                               const vidType *__restrict__ orig_of, vidType fb, vidType fe, unsigned long long small_max,
-                              unsigned long long mid_max, unsigned long long *__restrict__ W, unsigned char *__restrict__ cls) {
+                              unsigned long long cta_max, unsigned long long mid_max,
+                              unsigned long long *__restrict__ W, unsigned char *__restrict__ cls) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const vidType u = vidType(t >> 3); const int sub = int(t & 7);
   unsigned long long w = 0;
@@ -71,7 +84,7 @@ __global__ void k_c4_classify(vidType nv, const eidType *__restrict__ inrow, con
     const vidType o = orig_of[u];
     const bool mine = o >= fb && o < fe && (inrow[u + 1] - inrow[u]) >= 2 && w >= 2;
     W[u] = w;
-    cls[u] = !mine ? 0 : w <= small_max ? 1 : w <= mid_max ? 2 : 3;
+    cls[u] = !mine ? 0 : w <= small_max ? 1 : w <= cta_max ? 2 : w <= mid_max ? 3 : 4;
   }
 }
 
@@ -121,6 +134,54 @@ c4_small_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigne
   if (lane == 0 && acc) atomicAdd(total, acc);
 }
 
+// ---- tier 2: CTA per root, shared-memory table (keys u32, counters packed 16-bit) ---------------------------
+__global__ void __launch_bounds__(kC4MidThreads)
+c4_cta_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
+              const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+              const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, int *ticket, AccType *total) {
+  extern __shared__ uint32_t c4_smem[];
+  uint32_t *keys = c4_smem, *cnts = c4_smem + kC4CtaSlots;      // cnts: two 16-bit counters per word
+  __shared__ int64_t s_next;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int NW = kC4MidThreads / 32;
+  AccType acc = 0;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = int64_t(atomicAdd(ticket, 1));
+    __syncthreads();
+    const int64_t idx = s_next;
+    if (idx >= nroots) break;
+    const vidType u = roots[idx];
+    const uint32_t need = uint32_t(W[u]) + (uint32_t(W[u]) >> 1);            // 1.5 W slots at least
+    const int bits = min(15, max(10, 32 - __clz(int(need) - 1)));
+    const uint32_t mask = (1u << bits) - 1u;
+    for (uint32_t i = threadIdx.x; i <= mask; i += kC4MidThreads) keys[i] = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i <= (mask >> 1); i += kC4MidThreads) cnts[i] = 0u;
+    __syncthreads();
+    auto insert = [&](uint32_t x) {
+      uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+      while (true) {
+        const uint32_t old = atomicCAS(&keys[h], 0xffffffffu, x);
+        if (old == 0xffffffffu || old == x) {
+          const uint32_t sh = (h & 1u) << 4;
+          acc += (atomicAdd(&cnts[h >> 1], 1u << sh) >> sh) & 0xffffu;
+          break;
+        }
+        h = (h + 1) & mask;
+      }
+    };
+    for (eidType e = inrow[u] + wid; e < inrow[u + 1]; e += NW) {
+      const uint2 r = incol[e];
+      const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+      for (int i = lane; i < nin; i += 32) insert(incol[vb + i].x);
+      const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
+      for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
+    }
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
 // ---- tiers 2 and 3: dense counting array in global memory -------------------------------------------------
 // PHASE 0: L[w]++ and accumulate the old values; PHASE 1: L[w] = 0.  `nwarps` warps share the in-edges of u.
 template <int PHASE>
@@ -161,6 +222,33 @@ c4_mid_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *
     acc += c4_dense_pass<0>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol);
     __syncthreads();
     c4_dense_pass<1>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol);
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+// tier 3: one cluster per root; cur[cluster] carries the ticket from the cluster's first CTA to the others
+__global__ void __launch_bounds__(kC4MidThreads)
+c4_cluster_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+                  const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *dense, size_t stride,
+                  int *ticket, volatile int64_t *cur, AccType *total) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
+  const int cid = int(blockIdx.x) / csize;
+  const int lane = threadIdx.x & 31;
+  const int wid = crank * (kC4MidThreads / 32) + (threadIdx.x >> 5), nwarps = csize * (kC4MidThreads / 32);
+  uint32_t *L = dense + size_t(cid) * stride;
+  AccType acc = 0;
+  while (true) {
+    cluster.sync();                                                 // previous root cleared by every CTA
+    if (crank == 0 && threadIdx.x == 0) { cur[cid] = int64_t(atomicAdd(ticket, 1)); __threadfence(); }
+    cluster.sync();
+    const int64_t idx = cur[cid];
+    if (idx >= nroots) break;                                       // cluster-uniform
+    const vidType u = roots[idx];
+    acc += c4_dense_pass<0>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol);
+    cluster.sync();
+    c4_dense_pass<1>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol);
   }
   acc = warp_reduce(acc);
   if (lane == 0 && acc) atomicAdd(total, acc);
@@ -216,9 +304,9 @@ __global__ void k_motif4_induced_cycles(AccType *counters) {
 
 // ---- host side ---------------------------------------------------------------------------------------------
 static void free_c4_lists(gm_graph *c) {
-  dfree(c, c->c4_small); dfree(c, c->c4_mid); dfree(c, c->c4_W);
-  c->c4_small = c->c4_mid = nullptr; c->c4_W = nullptr;
-  c->c4_nsmall = c->c4_nmid = 0; c->c4_heavy.clear();
+  dfree(c, c->c4_small); dfree(c, c->c4_cta); dfree(c, c->c4_mid); dfree(c, c->c4_W);
+  c->c4_small = c->c4_cta = c->c4_mid = nullptr; c->c4_W = nullptr;
+  c->c4_nsmall = c->c4_ncta = c->c4_nmid = 0; c->c4_heavy.clear();
   c->c4_lists_ready = false;
 }
 
@@ -237,8 +325,8 @@ void invalidate_range_structures_of_child(gm_graph *c) {
 
 void free_c4(gm_graph *c) {
   free_c4_lists(c);
-  dfree(c, c->c4_inrow); dfree(c, c->c4_incol); dfree(c, c->c4_dense);
-  c->c4_inrow = nullptr; c->c4_incol = nullptr; c->c4_dense = nullptr;
+  dfree(c, c->c4_inrow); dfree(c, c->c4_incol); dfree(c, c->c4_dense); dfree(c, c->c4_cur);
+  c->c4_inrow = nullptr; c->c4_incol = nullptr; c->c4_dense = nullptr; c->c4_cur = nullptr;
 }
 
 // c = the DAG child (ranked, full range); [fb, fe) = the parent's source range (original ids)
@@ -270,15 +358,18 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
   GM_CUDA(dmalloc(c, &cls, size_t(nv)));
   GM_CUDA(dmalloc(c, &d_num, sizeof(int64_t)));
   GM_CUDA(dmalloc(c, &c->c4_small, sizeof(vidType) * size_t(nv)));
+  GM_CUDA(dmalloc(c, &c->c4_cta, sizeof(vidType) * size_t(nv)));
   GM_CUDA(dmalloc(c, &c->c4_mid, sizeof(vidType) * size_t(nv)));
   GM_CUDA(dmalloc(c, &heavy, sizeof(vidType) * size_t(nv)));
-  // tier thresholds ("c4.small_max" <= 512, "c4.mid_max": test hooks that force roots into the larger tiers)
+  // tier thresholds ("c4.small_max" <= 512, "c4.cta_max" <= 24576, "c4.mid_max": test hooks that force
+  // roots into the larger tiers)
   const unsigned long long small_max = std::min<unsigned long long>(kC4SmallMax, options().c4_small_max >= 0 ? options().c4_small_max : kC4SmallMax);
-  const unsigned long long mid_max = options().c4_mid_max >= 0 ? (unsigned long long)options().c4_mid_max : kC4MidMaxDefault;
-  k_c4_classify<<<nblk(int64_t(nv) * 8), 256, 0, c->stream>>>(nv, c->c4_inrow, c->c4_incol, c->rk_orig, fb, fe, small_max, mid_max, c->c4_W, cls);
-  vidType *outs[3] = {c->c4_small, c->c4_mid, heavy};
-  int64_t nums[3] = {0, 0, 0};
-  for (int k = 0; k < 3; k++) {
+  const unsigned long long cta_max = std::max(small_max, std::min<unsigned long long>(kC4CtaMax, options().c4_cta_max >= 0 ? options().c4_cta_max : kC4CtaMax));
+  const unsigned long long mid_max = std::max(cta_max, options().c4_mid_max >= 0 ? (unsigned long long)options().c4_mid_max : kC4MidMaxDefault);
+  k_c4_classify<<<nblk(int64_t(nv) * 8), 256, 0, c->stream>>>(nv, c->c4_inrow, c->c4_incol, c->rk_orig, fb, fe, small_max, cta_max, mid_max, c->c4_W, cls);
+  vidType *outs[4] = {c->c4_small, c->c4_cta, c->c4_mid, heavy};
+  int64_t nums[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; k++) {
     thrust::counting_iterator<vidType> ids(0);
     ClsIs pred{cls, (unsigned char)(k + 1)};
     size_t tmp = 0;
@@ -288,23 +379,57 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
     GM_CUDA(cudaMemcpyAsync(&nums[k], d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     GM_CUDA(cudaStreamSynchronize(c->stream));
   }
-  c->c4_nsmall = nums[0]; c->c4_nmid = nums[1];
-  c->c4_heavy.resize(size_t(nums[2]));
-  if (nums[2] > 0) GM_CUDA(cudaMemcpyAsync(c->c4_heavy.data(), heavy, sizeof(vidType) * size_t(nums[2]), cudaMemcpyDeviceToHost, c->stream));
+  c->c4_nsmall = nums[0]; c->c4_ncta = nums[1]; c->c4_nmid = nums[2];
+  if (const char *tr = getenv("GM_TRACE")) if (*tr && *tr != '0') {       // wedges per tier (diagnostics only)
+    std::vector<unsigned long long> hW(static_cast<size_t>(nv)); std::vector<unsigned char> hc(static_cast<size_t>(nv));
+    cudaMemcpy(hW.data(), c->c4_W, sizeof(unsigned long long) * size_t(nv), cudaMemcpyDeviceToHost);
+    cudaMemcpy(hc.data(), cls, size_t(nv), cudaMemcpyDeviceToHost);
+    unsigned long long sum[5] = {0, 0, 0, 0, 0};
+    for (vidType v = 0; v < nv; v++) sum[hc[size_t(v)]] += hW[size_t(v)];
+    fprintf(stderr, "[gm] 4-cycle tiers: small %lld roots / %llu wedges, cta %lld / %llu, cluster %lld / %llu, heavy %lld / %llu\n",
+            (long long)nums[0], sum[1], (long long)nums[1], sum[2], (long long)nums[2], sum[3], (long long)nums[3], sum[4]);
+  }
+  c->c4_heavy.resize(size_t(nums[3]));
+  if (nums[3] > 0) GM_CUDA(cudaMemcpyAsync(c->c4_heavy.data(), heavy, sizeof(vidType) * size_t(nums[3]), cudaMemcpyDeviceToHost, c->stream));
   GM_CUDA(cudaStreamSynchronize(c->stream));
   GM_CUDA(dfree(c, cls)); GM_CUDA(dfree(c, d_num)); GM_CUDA(dfree(c, heavy));
-  // dense arrays: one per resident CTA of the mid kernel (array 0 also serves the heavy roots)
-  if (!c->c4_dense && (nums[1] > 0 || nums[2] > 0)) {
-    int occ = 0;
-    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c4_mid_kernel, kC4MidThreads, 0));
-    if (occ < 1) occ = 1;
+  // dense arrays of the mid tier: one per resident CLUSTER, as many as fit the L2 together (array 0 also
+  // serves the heavy roots).  Without cluster support: one per resident CTA of the fallback kernel.
+  if (!c->c4_dense && (nums[2] > 0 || nums[3] > 0)) {
     c->c4_dense_stride = (size_t(nv) + 31) & ~size_t(31);
+    const size_t arr_bytes = c->c4_dense_stride * 4;
+    int l2 = 0;
+    GM_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c->device));
+    c->c4_clusters = 0; c->c4_cluster_size = 0;
+    for (int cs = kC4Cluster; cs >= 8 && c->c4_clusters == 0; cs >>= 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(unsigned(cs * 64)); cfg.blockDim = dim3(kC4MidThreads); cfg.dynamicSmemBytes = 0;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(cs); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cs > 8 && cudaFuncSetAttribute(c4_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, c4_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (n > 0) { c->c4_clusters = n; c->c4_cluster_size = cs; }
+    }
+    int64_t arrays;
+    if (c->c4_clusters > 0) {
+      const int64_t fit = std::max<int64_t>(1, int64_t(double(l2) * 0.8) / int64_t(arr_bytes));
+      c->c4_clusters = int(std::min<int64_t>(c->c4_clusters, fit));
+      arrays = c->c4_clusters;
+    } else {
+      int occ = 0;
+      GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c4_mid_kernel, kC4MidThreads, 0));
+      arrays = int64_t(std::max(occ, 1)) * c->num_sms;
+    }
     size_t free_b = 0, total_b = 0;
     GM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    int64_t ctas = std::min<int64_t>(int64_t(occ) * c->num_sms, std::max<int64_t>(1, int64_t(double(free_b) * 0.5) / int64_t(c->c4_dense_stride * 4)));
-    c->c4_dense_ctas = int(ctas);
-    if (dmalloc(c, &c->c4_dense, c->c4_dense_stride * 4 * size_t(ctas)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle counting arrays)"); return GM_ENOMEM; }
-    GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, c->c4_dense_stride * 4 * size_t(ctas), c->stream));
+    arrays = std::min<int64_t>(arrays, std::max<int64_t>(1, int64_t(double(free_b) * 0.5) / int64_t(arr_bytes)));
+    if (c->c4_clusters > 0) c->c4_clusters = int(arrays);
+    c->c4_dense_ctas = int(arrays);
+    if (dmalloc(c, &c->c4_dense, arr_bytes * size_t(arrays)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle counting arrays)"); return GM_ENOMEM; }
+    GM_CUDA(dmalloc(c, &c->c4_cur, sizeof(int64_t) * size_t(arrays)));
+    GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, arr_bytes * size_t(arrays), c->stream));
   }
   c->c4_fb = fb; c->c4_fe = fe; c->c4_lists_ready = true;
   trace_phase(c->stream, "4-cycle: root tiers");
@@ -347,7 +472,27 @@ int run_motif4_fast(gm_graph *g, int *launches) {
                                                  g->d_ticket + 0, g->d_counts + 3);
     (*launches)++;
   }
-  if (c->c4_nmid > 0) {
+  if (c->c4_ncta > 0) {
+    static bool attr_set = false;
+    if (!attr_set) { GM_CUDA(cudaFuncSetAttribute(c4_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem)); attr_set = true; }
+    int grid = int(std::min<int64_t>(c->c4_ncta, int64_t(c->num_sms)));
+    c4_cta_kernel<<<grid, kC4MidThreads, kC4CtaSmem, g->stream>>>(c->c4_cta, c->c4_ncta, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                                  g->d_ticket + 2, g->d_counts + 3);
+    (*launches)++;
+  }
+  if (c->c4_nmid > 0 && c->c4_clusters > 0) {
+    const int nclusters = int(std::min<int64_t>(c->c4_nmid, c->c4_clusters));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(nclusters * c->c4_cluster_size)); cfg.blockDim = dim3(kC4MidThreads);
+    cfg.dynamicSmemBytes = 0; cfg.stream = g->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(c->c4_cluster_size); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol,
+                               (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol, c->c4_dense, c->c4_dense_stride,
+                               g->d_ticket + 1, (volatile int64_t *)c->c4_cur, g->d_counts + 3));
+    (*launches)++;
+  } else if (c->c4_nmid > 0) {
     int grid = int(std::min<int64_t>(c->c4_nmid, int64_t(c->c4_dense_ctas)));
     c4_mid_kernel<<<grid, kC4MidThreads, 0, g->stream>>>(c->c4_mid, c->c4_nmid, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
                                                          c->c4_dense, c->c4_dense_stride, g->d_ticket + 1, g->d_counts + 3);

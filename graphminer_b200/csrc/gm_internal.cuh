@@ -47,7 +47,7 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
-  long long c4_small_max = -1, c4_mid_max = -1;   // 4-cycle tier thresholds (wedges per root); -1 = defaults
+  long long c4_small_max = -1, c4_cta_max = -1, c4_mid_max = -1;   // 4-cycle tier thresholds (wedges per root); -1 = defaults
   std::string motif_algo = "auto";   // 4-motif formula: auto|fast (supports + wedge-pair 4-cycles + bit-matrix 4-cliques) | list
   std::string sgl_algo = "auto";     // diamond: auto|support (DAG triangle supports) | list (operator-API warp-per-edge kernel)
   std::string tc_shard = "source";   // which endpoint of an edge the source range of a shard refers to (ranked TC kernel)
@@ -111,7 +111,8 @@ struct gm_graph {
   // 4-cycle counting on the ranked DAG (cycle4.cu; lives in the child handle)
   gm::eidType *c4_inrow = nullptr; uint2 *c4_incol = nullptr;        // in-rows {v, position of u in v's out-row}
   unsigned long long *c4_W = nullptr;                               // wedges per root
-  gm::vidType *c4_small = nullptr, *c4_mid = nullptr; int64_t c4_nsmall = 0, c4_nmid = 0;
+  gm::vidType *c4_small = nullptr, *c4_cta = nullptr, *c4_mid = nullptr; int64_t c4_nsmall = 0, c4_ncta = 0, c4_nmid = 0;
+  int c4_clusters = 0, c4_cluster_size = 0; int64_t *c4_cur = nullptr;
   std::vector<gm::vidType> c4_heavy;
   uint32_t *c4_dense = nullptr; size_t c4_dense_stride = 0; int c4_dense_ctas = 0;
   bool c4_lists_ready = false; gm::vidType c4_fb = 0, c4_fe = 0;

@@ -445,6 +445,8 @@ int gm_set_option(const char *key, const char *value) {
     options().tc_algo = v;
   } else if (k == "c4.small_max") {
     options().c4_small_max = atoll(value);
+  } else if (k == "c4.cta_max") {
+    options().c4_cta_max = atoll(value);
   } else if (k == "c4.mid_max") {
     options().c4_mid_max = atoll(value);
   } else if (k == "motif.algo") {

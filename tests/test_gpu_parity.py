@@ -30,6 +30,7 @@ def _reset_options():
     capi.set_option("motif.algo", "auto")
     capi.set_option("c4.small_max", -1)
     capi.set_option("c4.mid_max", -1)
+    capi.set_option("c4.cta_max", -1)
 
 
 def _graph(name):
@@ -441,12 +442,13 @@ def test_motif4_formula_both_algorithms(algo, citeseer, mico):
         assert g.motif(4, formula=True) == [0, 0, 0, 0, 0, 15]
 
 
-@pytest.mark.parametrize("small_max,mid_max", [(0, -1), (0, 0), (16, 300), (512, 2000)])
-def test_motif4_cycle_tiers(small_max, mid_max):
-    """the three 4-cycle tiers (warp table / per-CTA dense array / whole-grid dense array) must agree:
-    thresholds are pushed down so that small graphs reach the mid and heavy code paths"""
+@pytest.mark.parametrize("small_max,cta_max,mid_max", [(0, -1, -1), (0, 0, -1), (0, 0, 0), (16, 100, 300), (512, 600, 2000)])
+def test_motif4_cycle_tiers(small_max, cta_max, mid_max):
+    """the four 4-cycle tiers (warp table / CTA table / cluster on a dense array / whole-grid dense array)
+    must agree: thresholds are pushed down so that small graphs reach every code path"""
     capi.set_option("motif.algo", "fast")
     capi.set_option("c4.small_max", small_max)
+    capi.set_option("c4.cta_max", cta_max)
     capi.set_option("c4.mid_max", mid_max)
     for name in ("rmat10", "rmat14", "shaped3000"):
         rp, ci = _graph(name)
