@@ -26,7 +26,7 @@ ALGOS = {"auto": 0, "bsearch": 1, "merge": 2, "hash": 3, "gallop": 4}
 
 # every symbol include/gminer_b200.h declares (tests/test_abi.py checks the library exports them all)
 SYMBOLS = [
-    "gm_last_error", "gm_version", "gm_device_count", "gm_set_option",
+    "gm_last_error", "gm_version", "gm_device_count", "gm_device_init", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
     "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph",
     "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
@@ -62,6 +62,7 @@ def lib():
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.gm_last_error.restype = C.c_char_p
     L.gm_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.gm_device_init.argtypes = [C.c_int]
     L.gm_set_option.argtypes = [C.c_char_p, C.c_char_p]
     L.gm_host_orient.restype = i64
     L.gm_host_orient.argtypes = [i32, _i64p, _i32p, _i64p, _i32p, C.POINTER(i32)]

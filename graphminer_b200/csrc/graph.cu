@@ -428,6 +428,15 @@ extern "C" {
 const char *gm_last_error(void) { return g_err.c_str(); }
 int gm_version(void) { return 100; }
 
+int gm_device_init(int device) {
+  int ndev = 0; gm_device_count(&ndev);
+  if (device < 0 || device >= ndev) { set_error("gm_device_init: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
+  GM_CUDA(cudaSetDevice(device));
+  GM_CUDA(cudaFree(nullptr));
+  (void)device_info(device);
+  return GM_OK;
+}
+
 int gm_device_count(int *count) {
   if (!count) { set_error("count is NULL"); return GM_EINVAL; }
   int n = 0;

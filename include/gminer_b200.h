@@ -43,6 +43,9 @@ typedef struct gm_graph gm_graph_t;   /* opaque device-resident graph (replaces 
 const char *gm_last_error(void);
 int gm_version(void);                       /* 10000*major + 100*minor + patch */
 int gm_device_count(int *count);            /* cudaGetDeviceCount; 0 devices is not an error */
+/* Create the CUDA context of `device` and the library's per-device state ahead of a timed call
+ * (what print_device_info(0) does before the reference starts its timer, triangle/gpu_base.cu:26). */
+int gm_device_init(int device);
 /* Runtime knobs replacing the reference's compile-time macros (src/common.mk:72-114).
  * keys: "tc.algo" = auto|hash|hash_rev|bs|merge, "clique.algo" = auto|bitmap|list,
  *       "motif.algo" = auto|fast|list (4-motif formula: supports + wedge-pair 4-cycles + bit-matrix
