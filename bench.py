@@ -294,25 +294,29 @@ def run_ours(args):
     cnt_dev = torch.zeros(wl.ncounts, dtype=torch.int64, device=dev)
     res_dev = torch.zeros(8, dtype=torch.int64, device=dev)
 
-    def reduce_counts(c):
-        if world > 1:
-            cnt_dev.copy_(torch.tensor(c, dtype=torch.int64))
-            dist.all_reduce(cnt_dev)                   # the only collective: 1 (or 6) 64-bit counts
-            c = [int(x) for x in cnt_dev.tolist()]
-        return wl.finish(c)
-
     if world > 1:
         # device-side results: kernels -> count in res_dev -> NCCL all-reduce on the same stream -> ONE
         # device->host read per step (no host round trip between the pass and its collective)
         g.set_result_buffer(res_dev)
 
-    def step():
-        if world == 1:
-            return wl.finish(wl.solve(g))
-        wl.solve(g)
+    def solve_sharded(gh):
+        """one pass on this rank's shard; the counts end up all-reduced in res_dev"""
+        if wl.kind == "diamond":
+            # the one workload with a data-path exchange: every rank enumerates the triangles of its root
+            # range, the per-edge support arrays are summed over NVLink, every rank sums its own edges
+            gh.sgl_support_begin()
+            dist.all_reduce(gh.support_tensor())
+            gh.sgl_support_finish()
+        else:
+            wl.solve(gh)
         red = res_dev[:wl.ncounts]
         dist.all_reduce(red)
         return wl.finish([int(x) for x in red.tolist()])
+
+    def step():
+        if world == 1:
+            return wl.finish(wl.solve(g))
+        return solve_sharded(g)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -368,9 +372,10 @@ def run_ours(args):
         if world == 1:
             return wl.host_solve(capi, n_rp, n_ci, max_deg)
         with capi.DeviceGraph(n_rp, n_ci, max_deg, device=local) as gg:
+            gg.set_stream(stream.cuda_stream)
             gg.set_source_range(b, e)
-            c = wl.solve(gg)
-        return reduce_counts(c)
+            gg.set_result_buffer(res_dev)
+            return solve_sharded(gg)
 
     e2e_steps = max(1, min(args.steps, 5))
     assert e2e_step() == counts
@@ -408,7 +413,9 @@ def run_ours(args):
             "config": {"workload": wl.name, "nv": nv, "edges": ne, "oriented": wl.oriented, "max_degree": max_deg,
                        "count": counts[0] if len(counts) == 1 else counts, "parity_check_count": check,
                        "l2": "inputs (CSR %.0f MB) larger than the 126 MB L2; no flush" % ((nv * 8 + ne * 4) / 1e6),
-                       "sharding": "contiguous source-vertex ranges, work-balanced; CSR replicated; 1 NCCL all-reduce of %d u64 per step" % wl.ncounts},
+                       "sharding": ("contiguous root ranges, work-balanced; CSR replicated; NCCL all-reduce of the per-edge support array (u32 x DAG edges) + 1 u64 per step"
+                                    if wl.kind == "diamond" and n > 1 else
+                                    "contiguous source-vertex ranges, work-balanced; CSR replicated; 1 NCCL all-reduce of %d u64 per step" % wl.ncounts)},
             "e2e": {"value": e2e_value, "unit": wl.unit,
                     "h2d_bytes_per_step": int((nv + 1) * 8 + ne * 4), "d2h_bytes_per_step": 8 * wl.ncounts,
                     "steps": e2e_steps, "note": "gm_*_host: pinned host CSR -> upload + device-side prepare + kernels + count"},

@@ -29,7 +29,7 @@ SYMBOLS = [
     "gm_last_error", "gm_version", "gm_device_count", "gm_device_init", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
     "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph",
-    "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
+    "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
     "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
     "gm_motif_formula_finish", "gm_last_stats", "gm_last_alg_bytes",
@@ -79,6 +79,9 @@ def lib():
     L.gm_graph_free.argtypes = [vp]
     L.gm_graph_set_stream.argtypes = [vp, vp]
     L.gm_graph_set_result_buffer.argtypes = [vp, vp]
+    L.gm_sgl_support_begin.argtypes = [vp]
+    L.gm_graph_support.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gm_sgl_support_finish.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.gm_graph_set_source_range.argtypes = [vp, i32, i32]
     L.gm_graph_prepare.argtypes = [vp, C.c_char_p]
     L.gm_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_int)]
@@ -264,6 +267,25 @@ class DeviceGraph:
     def sgl(self, pattern: str) -> int:
         t = C.c_uint64(0)
         check(lib().gm_sgl(self._h, pattern.encode(), C.byref(t)))
+        return t.value
+
+    # multi-GPU diamond: partial support pass -> caller all-reduces support_tensor() -> finish
+    def sgl_support_begin(self):
+        check(lib().gm_sgl_support_begin(self._h))
+
+    def support_tensor(self):
+        """the per-edge support array as a torch int32 CUDA tensor sharing the library's memory"""
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib().gm_graph_support(self._h, C.byref(p), C.byref(n)))
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<i4", "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(_Arr(), device=f"cuda:{self.info()['device']}")
+
+    def sgl_support_finish(self) -> int:
+        t = C.c_uint64(0)
+        check(lib().gm_sgl_support_finish(self._h, C.byref(t)))
         return t.value
 
     def motif(self, k: int, formula=False, raw=False):

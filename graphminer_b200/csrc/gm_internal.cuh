@@ -105,6 +105,8 @@ struct gm_graph {
 
   // undirected input: device-side (degree,id) orientation kept in a child handle (support.cu), and the
   // per-edge triangle supports of the diamond solver (indexed like the child's rk_acol)
+  bool force_dest_shard = false;       // ranked partner records filtered by the DESTINATION's original id (child of a partial support pass)
+  int support_launches = 0;
   gm_graph *dag_child = nullptr;
   gm::eidType *dag_rowptr = nullptr; gm::vidType *dag_colidx = nullptr;
   uint32_t *d_support = nullptr; int64_t support_len = 0;
@@ -161,7 +163,7 @@ int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
 int ensure_dag_child(gm_graph *g);
-int prepare_diamond_support(gm_graph *g, bool *ok);
+int prepare_diamond_support(gm_graph *g, bool *ok, bool partial = false);
 int run_diamond_support(gm_graph *g, int *launches);
 int run_support_pass(gm_graph *g, int *launches);
 int prepare_motif4_fast(gm_graph *g, bool *ok);

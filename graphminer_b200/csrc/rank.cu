@@ -168,7 +168,7 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
     k_ranked_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->rk_nrow, units, g->rk_vinfo);
     k_fill_u32<<<nblk(acol_len), 256, 0, g->stream>>>(acol_len, g->rk_acol, kVidMax);
-    const int by_dest = options().tc_shard == "dest";
+    const int by_dest = options().tc_shard == "dest" || g->force_dest_shard;
     k_ranked_edges<0><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end, by_dest,
                                                        g->rk_acol, cnt, nullptr, nullptr, bad);
     GM_CUDA(cudaMemcpyAsync(g->rk_prow, cnt, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, g->stream));

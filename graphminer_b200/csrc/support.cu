@@ -233,15 +233,26 @@ static int launch_support_class(gm_graph *g, gm_graph *c, int cls, cudaStream_t 
 
 // builds everything the support pass needs; *ok = false when the ranked DAG could not be built (then the
 // caller keeps the operator-API kernel)
-int prepare_diamond_support(gm_graph *g, bool *ok) {
+// partial = false: the child enumerates every triangle (single-GPU solvers); partial = true: only the
+// triangles whose middle vertex lies in the parent's source range (multi-GPU: the supports are then
+// summed across the shards by the caller)
+int prepare_diamond_support(gm_graph *g, bool *ok, bool partial) {
   *ok = false;
   if (g->nv == 0 || g->ne == 0) return GM_OK;
   GM_TRY(ensure_dag_child(g));
   gm_graph *c = g->dag_child;
+  const vidType cb = partial ? g->src_begin : 0, ce = partial ? g->src_end : c->nv;
+  c->force_dest_shard = true;
+  if (c->src_begin != cb || c->src_end != ce) {
+    GM_TRY(gm_graph_set_source_range(c, cb, ce));          // drops the child's ranked structures; rebuilt below
+    free_c4(c);                                            // in-rows are rank-order dependent only, but keep it simple
+  }
   GM_TRY(ensure_ranked(c));
   if (!c->rk_valid) return GM_OK;
   GM_TRY(ensure_items(c, 3));
-  if (!g->d_support) {
+  if (!g->d_support || g->support_len != c->rk_acol_len) {
+    if (g->d_support) GM_CUDA(dfree(g, g->d_support));
+    g->d_support = nullptr;
     GM_CUDA(dmalloc(g, &g->d_support, sizeof(uint32_t) * size_t(c->rk_acol_len > 0 ? c->rk_acol_len : 4)));
     g->support_len = c->rk_acol_len;
   }
@@ -274,3 +285,36 @@ int run_diamond_support(gm_graph *g, int *launches) {
 }
 
 }  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_sgl_support_begin(gm_graph_t *g) {
+  if (!g) { set_error("gm_sgl_support_begin: null graph"); return GM_EINVAL; }
+  bool ok = false;
+  GM_TRY(prepare_diamond_support(g, &ok, /*partial=*/true));
+  if (!ok) { set_error("gm_sgl_support_begin: the graph has no edges or its DAG could not be ranked"); return GM_EUNSUPPORTED; }
+  g->last_alg_bytes = 0; g->last_alg_kind = 3;
+  GM_TRY(begin_timed(g));
+  g->support_launches = 0;
+  return run_support_pass(g, &g->support_launches);
+}
+
+extern "C" int gm_graph_support(gm_graph_t *g, uint32_t **d_support, int64_t *n) {
+  if (!g || !d_support || !n) { set_error("gm_graph_support: null argument"); return GM_EINVAL; }
+  if (!g->d_support) { set_error("gm_graph_support: call gm_sgl_support_begin first"); return GM_EINVAL; }
+  *d_support = g->d_support; *n = g->support_len;
+  return GM_OK;
+}
+
+extern "C" int gm_sgl_support_finish(gm_graph_t *g, uint64_t *total) {
+  if (!g || !total) { set_error("gm_sgl_support_finish: null argument"); return GM_EINVAL; }
+  gm_graph *c = g->dag_child;
+  if (!c || !g->d_support || !c->rk_valid) { set_error("gm_sgl_support_finish: call gm_sgl_support_begin first"); return GM_EINVAL; }
+  int launches = g->support_launches;
+  if (c->nv > 0) {
+    k_diamond_sum<<<nblk(int64_t(c->nv) * 8), 256, 0, g->stream>>>(c->nv, c->rk_vinfo, c->rk_acol, c->rk_orig, g->d_support,
+                                                                   g->src_begin, g->src_end, g->d_counts);
+    launches++;
+  }
+  return end_timed(g, launches, 1, total);
+}

@@ -121,6 +121,18 @@ int gm_kclique(gm_graph_t *g, int k, uint64_t *total);
 /* SglSolver, src/sgl/gpu_base.cu:21-103.  Undirected input; pattern in
  * {"diamond","rectangle","house","pentagon"} (edge-induced counts). */
 int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total);
+/* Multi-GPU diamond with a real exchange step (sgl.algo=support; the reference's sgl_multigpu has the
+ * diamond launch commented out, src/sgl/multigpu.cu:111).  Every shard enumerates only the triangles whose
+ * middle vertex (in (degree,id) order) lies in its source range and adds them to its copy of the per-edge
+ * support array; the copies are summed over NVLink (ncclAllReduce, ncclUint32, ncclSum -- or
+ * torch.distributed) and every shard then sums C(t,2) over the edges it owns:
+ *   gm_sgl_support_begin(g)            zero + enumerate, asynchronous on the handle's stream
+ *   gm_graph_support(g, &d_sup, &n)    the device array uint32[n] to all-reduce in place
+ *   gm_sgl_support_finish(g, &total)   the shard's diamond count (honours gm_graph_set_result_buffer)
+ * gm_last_stats covers begin..finish including the caller's collective. */
+int gm_sgl_support_begin(gm_graph_t *g);
+int gm_graph_support(gm_graph_t *g, uint32_t **d_support, int64_t *n);
+int gm_sgl_support_finish(gm_graph_t *g, uint64_t *total);
 /* MotifSolver, src/motif/gpu_base.cu:21-111.  Undirected input; k=3 -> counts[2] = {wedge, triangle}
  * (OMP order, motif/cpu_kernels/automine_base.h:13,18), k=4 -> counts[6] = {3-star, 4-path,
  * tailed-triangle, 4-cycle, diamond, 4-clique} (vertex-induced). */

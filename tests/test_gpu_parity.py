@@ -454,3 +454,33 @@ def test_motif4_cycle_tiers(small_max, cta_max, mid_max):
         rp, ci = _graph(name)
         with capi.DeviceGraph(rp, ci, 0) as g:
             assert g.motif(4, formula=True) == GOLD[name]["motif4_formula"], name
+
+
+def test_diamond_partitioned_support_exchange():
+    """the multi-GPU diamond path on one device: N logical shards each enumerate the triangles of their root
+    range (gm_sgl_support_begin), the support arrays are summed (what the NCCL all-reduce does), every shard
+    sums C(t,2) over its own edges (gm_sgl_support_finish) -- per-shard oracle equality and the total."""
+    import torch
+    rp, ci = _graph("rmat12")
+    nv = len(rp) - 1
+    cuts = [0, nv // 3, nv // 3 + 1, nv - 100, nv]
+    shards = []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        g = capi.DeviceGraph(rp, ci, 0)
+        g.set_source_range(b, e)
+        g.sgl_support_begin()
+        shards.append((g, b, e))
+    torch.cuda.synchronize()
+    sups = [g.support_tensor() for g, _, _ in shards]
+    total_sup = torch.stack(sups).sum(0).to(torch.int32)
+    assert int(total_sup.sum()) == 3 * oracle.tc(*capi.host_orient(rp, ci)[:2])      # every triangle marks 3 edges
+    got = 0
+    for (g, b, e), sup in zip(shards, sups):
+        sup.copy_(total_sup)
+        c = g.sgl_support_finish()
+        assert c == oracle.sgl(rp, ci, "diamond", (b, e)), (b, e)
+        got += c
+        # the handle still serves the single-GPU solvers afterwards (child switches back to the full pass)
+        assert g.sgl("diamond") == oracle.sgl(rp, ci, "diamond", (b, e))
+        g.close()
+    assert got == GOLD["rmat12"]["diamond"]
