@@ -456,14 +456,19 @@ batch_pipe_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ 
 // fit the ring are appended to two overflow lists (<= 4608 staged elements: the two-warp stage pipeline
 // above; longer: operator API from global memory).
 constexpr int kRingSlots = 8;
+constexpr int kRingBlk = 16;                 // pair descriptors per ticket
 
 template <int RWORDS, int NW>
 struct RingCfg {
-  static constexpr int kWarpBytes = RWORDS * 4 + kRingSlots * 16 + kRingSlots * 8;
+  // ring | slot descriptors (int4) | mbarriers | current descriptor block (kRingBlk entries of 32 bytes)
+  static constexpr int kWarpBytes = RWORDS * 4 + kRingSlots * 16 + kRingSlots * 8 + kRingBlk * 32;
   static constexpr int kSmemBytes = NW * kWarpBytes;
   static_assert(kWarpBytes % 16 == 0, "rings must stay 16-byte aligned");
 };
 
+// A block entry holds everything the issue of one pair needs, precomputed lane-parallel when the block is
+// stored: {src a (u64), src b (u64), units_a | units_b << 16, na | nb << 16,
+//          head_a | head_b << 2 | merge << 4 | need << 8, pair index}
 template <int RWORDS, int NW, int CORE, bool PRED>
 __global__ void __launch_bounds__(NW * 32)
 batch_ring_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
@@ -475,87 +480,107 @@ batch_ring_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + size_t(w) * Cfg::kWarpBytes;
   const uint32_t sring = smem_u32(wbase);
-  const uint32_t sdesc = sring + RWORDS * 4;               // int4 per slot: {pair, na | nb << 16, head_a | head_b << 2 | units_a << 4, ring word offset}
+  const uint32_t sdesc = sring + RWORDS * 4;               // int4 per slot: {pair, na | nb << 16, units_a | units_b << 16, flags | ring word offset << 8}
   uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + RWORDS * 4 + kRingSlots * 16);
+  const uint32_t sblk = sdesc + kRingSlots * 16 + kRingSlots * 8;
   if (lane == 0) { for (int i = 0; i < kRingSlots; i++) mbar_init(&bars[i], 1); fence_barrier_init(); }
   __syncwarp();
 
-  const int64_t nblocks = (npairs + 31) >> 5;
-  // descriptors of one block, lane-parallel; `need` = ring words of the lane's pair
-  struct Block { int64_t ao, bo; int32_t al, bl, need; int64_t first; int cnt; };
-  auto load_block = [&](Block &r) {
+  const int64_t nblocks = (npairs + kRingBlk - 1) / kRingBlk;
+  // the NEXT block: raw descriptors in registers (lane l < ncnt), loaded one block ahead
+  int64_t nao = 0, nbo = 0, nfirst = 0; int32_t nal = 0, nbl = 0; int ncnt = 0;
+  auto load_next = [&]() {
     unsigned t = 0;
     if (lane == 0) t = atomicAdd(ticket, 1u);
     t = __shfl_sync(kFullMask, t, 0);
-    r.first = int64_t(t) << 5; r.cnt = 0; r.al = r.bl = 0; r.ao = r.bo = 0; r.need = 0;
+    nfirst = int64_t(t) * kRingBlk; ncnt = 0;
     if (int64_t(t) >= nblocks) return;
-    r.cnt = int(min(int64_t(32), npairs - r.first));
-    if (lane < r.cnt) {
-      const int64_t p = r.first + lane;
-      r.ao = a_off[p]; r.al = a_len[p]; r.bo = b_off[p]; r.bl = b_len[p];
-      const PairDesc d = describe_pair(r.ao, r.al, r.bo, r.bl);
-      const int L = ((r.al + r.bl + 63) >> 6) | 1;
-      r.need = 4 + (d.units_a + 1 + d.units_b) * 4 + ((L + 1 + 3) & ~3);
-      if (int64_t(d.units_a) + d.units_b + 2 > (int64_t(1) << 20)) r.need = 0x7fffffff;
+    ncnt = int(min(int64_t(kRingBlk), npairs - nfirst));
+    if (lane < ncnt) {
+      const int64_t p = nfirst + lane;
+      nao = a_off[p]; nal = a_len[p]; nbo = b_off[p]; nbl = b_len[p];
     }
   };
-  Block cur, nxt;
-  load_block(cur);
-  load_block(nxt);
-  int ci = 0;
-  int wr = 0, rd = 0, inflight = 0, head = 0, tail = 0;   // ring state, warp-uniform
-  int slot_start = 0;                                       // lane s: ring offset of slot s
-  uint32_t phases = 0;
-
-  int need = -1;                                             // ring words of pair (cur, ci); -1: not fetched yet
-  auto try_issue = [&]() -> bool {
-    if (need < 0) {
-      if (ci >= cur.cnt) {
-        if (cur.cnt == 0) return false;                     // tickets exhausted
-        cur = nxt; ci = 0;
-        load_block(nxt);
-        if (cur.cnt == 0) return false;
+  // turn the prefetched block into the current one: entries to shared memory, then prefetch the following block
+  auto store_block = [&]() {
+    if (lane < ncnt) {
+      const PairDesc d = describe_pair(nao, nal, nbo, nbl);
+      const int L = ((nal + nbl + 63) >> 6) | 1;
+      int64_t need = 4 + (int64_t(d.units_a) + 1 + d.units_b) * 4 + ((L + 1 + 3) & ~3);
+      if (need > RWORDS) need = 0xffffff;                    // overflow marker (RWORDS < 2^24)
+      bool merge = CORE == 0;
+      if (CORE == 2) {                                       // per-pair choice by instruction-count model
+        const int nk = min(nal, nbl), ns = max(nal, nbl);
+        const int search_cost = ((nk + 63) >> 6) * (9 * (32 - __clz(ns)) + 15);
+        const int merge_cost = 170 + 15 * ((nal + nbl + 63) >> 6);
+        merge = merge_cost < search_cost;
       }
-      need = __shfl_sync(kFullMask, cur.need, ci);
+      const unsigned long long sa = reinterpret_cast<unsigned long long>(pool + (nao - d.head_a));
+      const unsigned long long sb = reinterpret_cast<unsigned long long>(pool + (nbo - d.head_b));
+      const uint32_t e = sblk + 32u * lane;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e), "r"(uint32_t(sa)), "r"(uint32_t(sa >> 32)), "r"(uint32_t(sb)), "r"(uint32_t(sb >> 32)) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e + 16u), "r"(uint32_t(d.units_a) | (uint32_t(d.units_b) << 16)),
+                   "r"(uint32_t(nal) | (uint32_t(nbl) << 16)),
+                   "r"(uint32_t(d.head_a) | (uint32_t(d.head_b) << 2) | (uint32_t(merge) << 4) | (uint32_t(need) << 8)),
+                   "r"(uint32_t(nfirst + lane)) : "memory");
     }
-    if (need > RWORDS) {                                    // does not fit: hand over to the overflow kernels
-      if (lane == ci) {
-        const PairDesc d = describe_pair(cur.ao, cur.al, cur.bo, cur.bl);
-        const int which = (int64_t(d.units_a) + d.units_b + 2) * 4 <= pipe_stage_elems(kPipeClasses - 1) ? 0 : 1;
+    __syncwarp();
+  };
+
+  int cnt = 0, ci = 0;                                       // current block (in shared memory)
+  int wr = 0, rd = 0, inflight = 0, head = 0, tail = 0;      // ring state, warp-uniform
+  int slot_start = 0;                                        // lane s: ring offset of slot s
+  uint32_t phases = 0;
+  load_next();
+
+  auto try_issue = [&]() -> bool {
+    if (ci >= cnt) {
+      if (ncnt == 0) return false;                           // tickets exhausted
+      store_block();
+      cnt = ncnt; ci = 0;
+      load_next();                                           // consumed one block from now
+    }
+    uint32_t e0, e1, e2, e3, e4, e5, e6, e7;                 // broadcast read of entry ci
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"(sblk + 32u * ci) : "memory");
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e4), "=r"(e5), "=r"(e6), "=r"(e7) : "r"(sblk + 32u * ci + 16u) : "memory");
+    const int need = int(e6 >> 8);
+    const int units_a = int(e4 & 0xffffu), units_b = int(e4 >> 16);
+    if (need > RWORDS) {                                     // does not fit: hand over to the overflow kernels
+      if (lane == 0) {
+        const int which = (int64_t(units_a) + units_b + 2) * 4 <= pipe_stage_elems(kPipeClasses - 1) ? 0 : 1;
         const unsigned at = atomicAdd(&big_counts[which], 1u);
-        big_lists[int64_t(which) * npairs + at] = int32_t(cur.first + ci);
+        big_lists[int64_t(which) * npairs + at] = int32_t(e7);
       }
-      ci++; need = -1;
+      ci++;
       return true;
     }
     if (inflight == kRingSlots) return false;
     if (inflight == 0) { wr = 0; rd = 0; }
     int off;
     if (wr >= rd) {
-      if (inflight > 0 && wr == rd) return false;          // full
+      if (inflight > 0 && wr == rd) return false;           // full
       if (wr + need <= RWORDS) off = wr;
-      else if (need <= rd) off = 0;                         // wrap; [wr, RWORDS) idles until rd passes it
+      else if (need <= rd) off = 0;                          // wrap; [wr, RWORDS) idles until rd passes it
       else return false;
     } else {
       if (wr + need <= rd) off = wr; else return false;
     }
     wr = off + need;
     if (lane == tail) slot_start = off;
-    if (lane == ci) {
-      const PairDesc d = describe_pair(cur.ao, cur.al, cur.bo, cur.bl);
-      asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(sdesc + 16u * tail), "r"(int32_t(cur.first + ci)),
-                   "r"(d.na | (d.nb << 16)), "r"(d.head_a | (d.head_b << 2) | (d.units_a << 4)), "r"(off) : "memory");
-      const int units = d.units_a + d.units_b;
+    if (lane == 0) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdesc + 16u * tail), "r"(e7), "r"(e5), "r"(e4),
+                   "r"((e6 & 0xffu) | (uint32_t(off) << 8)) : "memory");
+      const int units = units_a + units_b;
       if (units > 0) {
         const uint32_t dst = sring + 4u * uint32_t(off) + 16u;                  // behind the pad unit
         mbar_expect_tx(&bars[tail], uint32_t(units) * 16u);
-        if (d.units_a) tma_bulk_g2s_addr(dst, pool + (cur.ao - d.head_a), uint32_t(d.units_a) * 16u, &bars[tail]);
-        if (d.units_b) tma_bulk_g2s_addr(dst + uint32_t(d.units_a + 1) * 16u, pool + (cur.bo - d.head_b), uint32_t(d.units_b) * 16u, &bars[tail]);
+        if (units_a) tma_bulk_g2s_addr(dst, reinterpret_cast<const void *>((unsigned long long)e0 | ((unsigned long long)e1 << 32)), uint32_t(units_a) * 16u, &bars[tail]);
+        if (units_b) tma_bulk_g2s_addr(dst + uint32_t(units_a + 1) * 16u, reinterpret_cast<const void *>((unsigned long long)e2 | ((unsigned long long)e3 << 32)), uint32_t(units_b) * 16u, &bars[tail]);
       } else {
         mbar_arrive(&bars[tail]);
       }
     }
-    ci++; need = -1; inflight++; tail = (tail + 1) & (kRingSlots - 1);
+    ci++; inflight++; tail = (tail + 1) & (kRingSlots - 1);
     return true;
   };
 
@@ -563,20 +588,15 @@ batch_ring_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ 
     while (try_issue()) {}
     if (inflight == 0) break;                               // nothing in flight and nothing left to issue
     mbar_wait(&bars[head], (phases >> head) & 1u); phases ^= 1u << head;
-    int dp, dn, dh, doff;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(dp), "=r"(dn), "=r"(dh), "=r"(doff) : "r"(sdesc + 16u * head) : "memory");
-    const int na = dn & 0xffff, nb = dn >> 16, head_a = dh & 3, head_b = (dh >> 2) & 3, units_a = dh >> 4;
+    int dp, dn, du, dh;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(dp), "=r"(dn), "=r"(du), "=r"(dh) : "r"(sdesc + 16u * head) : "memory");
+    const int na = dn & 0xffff, nb = int(uint32_t(dn) >> 16), units_a = du & 0xffff;
+    const int head_a = dh & 3, head_b = (dh >> 2) & 3, doff = int(uint32_t(dh) >> 8);
+    const bool merge = (dh >> 4) & 1;
     const uint32_t sA = sring + 4u * uint32_t(doff + 4 + head_a);
     const uint32_t sB = sring + 4u * uint32_t(doff + 4 + (units_a + 1) * 4 + head_b);
     uint32_t c = 0;
     if (na > 0 && nb > 0) {
-      bool merge = CORE == 0;
-      if (CORE == 2) {                                       // per-pair choice by instruction-count model
-        const int nk = min(na, nb), ns = max(na, nb);
-        const int search_cost = ((nk + 63) >> 6) * (9 * (32 - __clz(ns)) + 15);
-        const int merge_cost = 170 + 15 * ((na + nb + 63) >> 6);
-        merge = merge_cost < search_cost;
-      }
       if (merge) {
         c = merge_path_count<1, PRED>(sA, na, sB, nb, lane);
         fence_proxy_async();                                 // sentinel stores before the ring's next bulk copy here
@@ -644,7 +664,7 @@ static int launch_ring(const vidType *pool, const int64_t *a_off, const int32_t 
     GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NW * 32, Cfg::kSmemBytes));
     if (occ < 1) occ = 1;
   }
-  int grid = int(std::min<int64_t>((npairs + 32 * NW - 1) / (32 * NW), int64_t(occ) * sms));
+  int grid = int(std::min<int64_t>((npairs + kRingBlk * NW - 1) / (kRingBlk * NW), int64_t(occ) * sms));
   k<<<grid, NW * 32, Cfg::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, npairs, ticket, big_lists, big_counts, out);
   return GM_OK;
 }
