@@ -307,11 +307,13 @@ template <bool TRI>
 static int run_bitmap_classes(gm_graph *g, int k, int *launches) {
   GM_TRY(fork_streams(g));
   if (k == 4) {           // no per-warp mask levels needed: the big class affords 1024 threads
-    GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));
+    if (options().clique_gt1 == 512) GM_TRY((launch_clique_class<512, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));
+    else GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));
     GM_TRY((launch_clique_class<1024, 13, 64, 2048, 1024, 0, TRI>(g, k, 2, g->side[0], launches)));
     GM_TRY((launch_clique_class<32, 7, 16, 32, 32, 0, TRI>(g, k, 0, g->side[1], launches)));
   } else {
-    GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 4, TRI>(g, k, 1, g->stream, launches)));
+    if (options().clique_gt1 == 512) GM_TRY((launch_clique_class<512, 11, 64, 512, 512, 4, TRI>(g, k, 1, g->stream, launches)));
+    else GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 4, TRI>(g, k, 1, g->stream, launches)));
     GM_TRY((launch_clique_class<512, 13, 64, 2048, 1024, 4, TRI>(g, k, 2, g->side[0], launches)));
     GM_TRY((launch_clique_class<32, 7, 16, 32, 32, 4, TRI>(g, k, 0, g->side[1], launches)));
   }

@@ -47,6 +47,9 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
+  int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
+  int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)
+  int clique_gt1 = 256;              // threads per group of the d <= 512 class of the k-clique bit-matrix kernel (256 | 512)
   long long c4_small_max = -1, c4_cta_max = -1, c4_mid_max = -1;   // 4-cycle tier thresholds (wedges per root); -1 = defaults
   std::string motif_algo = "auto";   // 4-motif formula: auto|fast (supports + wedge-pair 4-cycles + bit-matrix 4-cliques) | list
   std::string sgl_algo = "auto";     // diamond: auto|support (DAG triangle supports) | list (operator-API warp-per-edge kernel)

@@ -467,6 +467,18 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "tc.shard") {
     if (v != "source" && v != "dest") { set_error("tc.shard: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_shard = v;
+  } else if (k == "tc.gt2") {
+    int t = atoi(value);
+    if (t != 256 && t != 512) { set_error("tc.gt2: 256 or 512"); return GM_EINVAL; }
+    options().tc_gt2 = t;
+  } else if (k == "sup.gt2") {
+    int t = atoi(value);
+    if (t != 256 && t != 512 && t != 1024) { set_error("sup.gt2: 256, 512 or 1024"); return GM_EINVAL; }
+    options().sup_gt2 = t;
+  } else if (k == "clique.gt1") {
+    int t = atoi(value);
+    if (t != 256 && t != 512) { set_error("clique.gt1: 256 or 512"); return GM_EINVAL; }
+    options().clique_gt1 = t;
   } else if (k == "clique.algo") {
     if (v != "auto" && v != "bitmap" && v != "list") { set_error("clique.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().clique_algo = v;

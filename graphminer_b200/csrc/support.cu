@@ -266,7 +266,10 @@ int run_support_pass(gm_graph *g, int *launches) {
   GM_CUDA(cudaMemsetAsync(g->d_support, 0, sizeof(uint32_t) * size_t(g->support_len), g->stream));
   GM_TRY(fork_streams(g));
   GM_TRY((launch_support_class<256, 11, 64>(g, c, 1, g->stream, launches)));
-  GM_TRY((launch_support_class<256, 13, 64>(g, c, 2, g->side[0], launches)));
+  // class 2 (70 KB per group): wider groups raise the occupancy of the three resident CTAs
+  if (options().sup_gt2 == 1024) GM_TRY((launch_support_class<1024, 13, 64>(g, c, 2, g->side[0], launches)));
+  else if (options().sup_gt2 == 512) GM_TRY((launch_support_class<512, 13, 64>(g, c, 2, g->side[0], launches)));
+  else GM_TRY((launch_support_class<256, 13, 64>(g, c, 2, g->side[0], launches)));
   GM_TRY((launch_support_class<1024, 14, 64>(g, c, 3, g->side[1], launches)));
   GM_TRY((launch_support_class<32, 7, 16>(g, c, 0, g->side[2], launches)));
   GM_TRY(join_streams(g));

@@ -202,7 +202,9 @@ static int run_tc_hash(gm_graph *g, int *launches) {
   // the four size classes are independent: run them concurrently so their tails overlap
   GM_TRY(fork_streams(g));
   GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 1, g->stream, launches)));
-  GM_TRY((launch_hash_class<256, 13, 64, MODE>(g, 2, g->side[0], launches)));
+  // class 2 (41 KB tables): 512-thread groups keep the SM at full occupancy (5 x 256 threads otherwise)
+  if (options().tc_gt2 == 512) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[0], launches)));
+  else GM_TRY((launch_hash_class<256, 13, 64, MODE>(g, 2, g->side[0], launches)));
   GM_TRY((launch_hash_class<1024, 15, 64, MODE>(g, 3, g->side[1], launches)));
   GM_TRY((launch_hash_class<32, 7, 16, MODE>(g, 0, g->side[2], launches)));
   GM_TRY(join_streams(g));
