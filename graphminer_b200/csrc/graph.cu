@@ -545,6 +545,9 @@ int gm_graph_free(gm_graph_t *g) {
   dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support);
   if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
   dfree(g, g->d_counts); dfree(g, g->d_ticket); dfree(g, g->d_scratch); dfree(g, g->d_gmat);
+  // complete the stream-ordered frees now: the blocks return to the pool free of stream dependencies, so
+  // the next handle (usually on another stream) reuses them instead of growing the pool
+  if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->h_counts) cudaFreeHost(g->h_counts);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
