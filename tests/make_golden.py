@@ -3,7 +3,7 @@
 (oracle/_ref, built from /root/reference by oracle/Makefile) on this repo's deterministic R-MAT
 graphs (graphminer_b200/rmat.py).  These are the golden vectors beyond citeseer/mico.
 
-Run in the build container:  python tools/make_golden.py
+Run in the build container:  python tests/make_golden.py
 """
 import json, os, sys
 import numpy as np
@@ -34,7 +34,7 @@ def ref_counts(rp, ci, heavy):
 
 
 def main():
-    res = {"_how": "tools/make_golden.py: oracle/_ref/*_omp_base (unmodified reference) on graphminer_b200.rmat graphs"}
+    res = {"_how": "tests/make_golden.py: oracle/_ref/*_omp_base (unmodified reference) on graphminer_b200.rmat graphs"}
     for scale, heavy in ((8, True), (10, True), (12, True), (14, False), (16, False)):
         rp, ci = rmat_graph(scale)
         res[f"rmat{scale}"] = ref_counts(rp.numpy(), ci.numpy(), heavy)

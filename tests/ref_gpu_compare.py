@@ -8,7 +8,7 @@ sm_100 by oracle/Makefile) against this engine on the SAME B200 and the SAME gra
     ours_cli_s     the `runtime [...]` line of this repo's drop-in binary (upload + device-side preparation +
                    kernels, i.e. MORE than the reference's line covers)
 
-    python tools/ref_gpu_compare.py [--json out.json] [--only tc,clique4,diamond,motif4] [--timeout 600]
+    python tests/ref_gpu_compare.py [--json out.json] [--only tc,clique4,diamond,motif4] [--timeout 600]
 """
 import argparse, json, os, re, subprocess, sys, tempfile, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")

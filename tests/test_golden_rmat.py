@@ -1,6 +1,6 @@
 """The oracle (C restatement) against golden vectors produced by the UNMODIFIED reference OpenMP
 binaries on this repo's deterministic R-MAT graphs (tests/golden/rmat_counts.json, made by
-tools/make_golden.py in the build container).  Also guards the generator against drift."""
+tests/make_golden.py in the build container).  Also guards the generator against drift."""
 import json
 import os
 
