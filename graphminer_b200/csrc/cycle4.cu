@@ -19,7 +19,7 @@
 // atomic increments return.  Four tiers by wedge count W(u):
 //   small (W <= 512)    warp per root, shared-memory open-addressing table;
 //   cta   (W <= 24576)  CTA per root, 192 KB shared-memory table (32 K keys + packed 16-bit counters);
-//   mid   (W <= 2^21)   one thread-block CLUSTER of 16 CTAs per root on a dense u32 array in global memory
+//   mid   (W <= 2^20)   one thread-block CLUSTER of 16 CTAs per root on a dense u32 array in global memory
 //                       (hardware cluster barrier between the counting and the clearing pass); only as many
 //                       clusters run as dense arrays fit the 126 MB L2 together, so the atomics stay on chip
 //                       (one array per CTA spills to HBM: 1.4 s instead of 0.2 s on the Friendster shape / 16);
@@ -44,7 +44,7 @@ constexpr uint64_t kC4SmallMax = 512;
 constexpr uint64_t kC4CtaMax = 24576;        // <= 0.75 * kC4CtaSlots
 constexpr int kC4CtaSlots = 32768;
 constexpr int kC4CtaSmem = kC4CtaSlots * 4 + kC4CtaSlots * 2;
-constexpr uint64_t kC4MidMaxDefault = uint64_t(1) << 21;
+constexpr uint64_t kC4MidMaxDefault = uint64_t(1) << 20;
 constexpr int kC4Cluster = 16;
 constexpr int kC4SmallSlots = 1024;          // per warp, >= 2 * kC4SmallMax
 constexpr int kC4MidThreads = 512;
