@@ -392,14 +392,20 @@ def run_ours(args):
     # ---- CPU baseline: the reference's own OpenMP code on a bounded sample (rank 0, N=1) ---------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(n_rp, n_ci, max_deg, wl.kind, budget_s=args.cpu_seconds)
+        try:
+            cpu = cpu_baseline(n_rp, n_ci, max_deg, wl.kind, budget_s=args.cpu_seconds)
+        except Exception as ex:                        # an auxiliary leg must not cost the bench line
+            cpu = {"error": repr(ex)}
 
     g.close()
     del g, rp, ci
     torch.cuda.empty_cache()
     stream_rf = None
     if rank == 0 and world == 1 and not args.no_stream:
-        stream_rf = stream_microbench(torch, capi, dev)
+        try:
+            stream_rf = stream_microbench(torch, capi, dev)
+        except Exception as ex:
+            stream_rf = {"error": repr(ex)}
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = alg_bytes / (kern_total_ms / args.steps / 1e3) / 1e9 if alg_bytes else None
