@@ -436,6 +436,48 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
   return GM_OK;
 }
 
+// all tiers of the wedge-pair 4-cycle count for the roots selected by ensure_c4; tickets g->d_ticket[0..2]
+static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launches) {
+  if (c->c4_nsmall > 0) {
+    int grid = int(std::min<int64_t>((c->c4_nsmall + 15) / 16, int64_t(c->num_sms) * 6));
+    c4_small_kernel<<<grid, 128, 0, g->stream>>>(c->c4_small, c->c4_nsmall, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                 g->d_ticket + 0, total);
+    (*launches)++;
+  }
+  if (c->c4_ncta > 0) {
+    static bool attr_set = false;
+    if (!attr_set) { GM_CUDA(cudaFuncSetAttribute(c4_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem)); attr_set = true; }
+    int grid = int(std::min<int64_t>(c->c4_ncta, int64_t(c->num_sms)));
+    c4_cta_kernel<<<grid, kC4MidThreads, kC4CtaSmem, g->stream>>>(c->c4_cta, c->c4_ncta, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                                  g->d_ticket + 2, total);
+    (*launches)++;
+  }
+  if (c->c4_nmid > 0 && c->c4_clusters > 0) {
+    const int nclusters = int(std::min<int64_t>(c->c4_nmid, c->c4_clusters));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(nclusters * c->c4_cluster_size)); cfg.blockDim = dim3(kC4MidThreads);
+    cfg.dynamicSmemBytes = 0; cfg.stream = g->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(c->c4_cluster_size); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol,
+                               (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol, c->c4_dense, c->c4_dense_stride,
+                               g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total));
+    (*launches)++;
+  } else if (c->c4_nmid > 0) {
+    int grid = int(std::min<int64_t>(c->c4_nmid, int64_t(c->c4_dense_ctas)));
+    c4_mid_kernel<<<grid, kC4MidThreads, 0, g->stream>>>(c->c4_mid, c->c4_nmid, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                         c->c4_dense, c->c4_dense_stride, g->d_ticket + 1, total);
+    (*launches)++;
+  }
+  for (vidType u : c->c4_heavy) {
+    c4_heavy_kernel<<<c->num_sms * 8, 256, 0, g->stream>>>(u, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol, c->c4_dense, total);
+    GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, c->c4_dense_stride * 4, g->stream));
+    (*launches)++;
+  }
+  return GM_OK;
+}
+
 // everything the fast formula pass needs; *ok = false -> the caller keeps the operator-API kernel
 int prepare_motif4_fast(gm_graph *g, bool *ok) {
   *ok = false;
@@ -455,6 +497,29 @@ int prepare_motif4_fast(gm_graph *g, bool *ok) {
   return GM_OK;
 }
 
+// sgl rectangle = every 4-cycle once (edge-induced, src/sgl/cpu_kernels/rectangle.h:1-11) = the wedge-pair
+// count without the chord correction.  The reference partitions the cycles by their largest vertex ID, this
+// count by their highest-RANKED vertex, so the fast path serves the full source range only.
+int prepare_rectangle_fast(gm_graph *g, bool *ok) {
+  *ok = false;
+  if (g->nv == 0 || g->ne == 0 || g->src_begin != 0 || g->src_end != g->nv) return GM_OK;
+  GM_TRY(ensure_dag_child(g));
+  gm_graph *c = g->dag_child;
+  c->force_dest_shard = true;
+  if (c->src_begin != 0 || c->src_end != c->nv) { GM_TRY(gm_graph_set_source_range(c, 0, c->nv)); free_c4(c); }
+  GM_TRY(ensure_ranked(c));
+  if (!c->rk_valid) return GM_OK;
+  GM_TRY(ensure_c4(c, 0, g->nv));
+  *ok = true;
+  return GM_OK;
+}
+
+int run_rectangle_fast(gm_graph *g, int *launches) {
+  GM_TRY(launch_c4_tiers(g, g->dag_child, g->d_counts, launches));
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
 int run_motif4_fast(gm_graph *g, int *launches) {
   gm_graph *c = g->dag_child;
   // 1. supports (full graph) -> closed forms over the owned edges
@@ -466,43 +531,7 @@ int run_motif4_fast(gm_graph *g, int *launches) {
     (*launches)++;
   }
   // 2. 4-cycles
-  if (c->c4_nsmall > 0) {
-    int grid = int(std::min<int64_t>((c->c4_nsmall + 15) / 16, int64_t(c->num_sms) * 6));
-    c4_small_kernel<<<grid, 128, 0, g->stream>>>(c->c4_small, c->c4_nsmall, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
-                                                 g->d_ticket + 0, g->d_counts + 3);
-    (*launches)++;
-  }
-  if (c->c4_ncta > 0) {
-    static bool attr_set = false;
-    if (!attr_set) { GM_CUDA(cudaFuncSetAttribute(c4_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem)); attr_set = true; }
-    int grid = int(std::min<int64_t>(c->c4_ncta, int64_t(c->num_sms)));
-    c4_cta_kernel<<<grid, kC4MidThreads, kC4CtaSmem, g->stream>>>(c->c4_cta, c->c4_ncta, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
-                                                                  g->d_ticket + 2, g->d_counts + 3);
-    (*launches)++;
-  }
-  if (c->c4_nmid > 0 && c->c4_clusters > 0) {
-    const int nclusters = int(std::min<int64_t>(c->c4_nmid, c->c4_clusters));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(nclusters * c->c4_cluster_size)); cfg.blockDim = dim3(kC4MidThreads);
-    cfg.dynamicSmemBytes = 0; cfg.stream = g->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(c->c4_cluster_size); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol,
-                               (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol, c->c4_dense, c->c4_dense_stride,
-                               g->d_ticket + 1, (volatile int64_t *)c->c4_cur, g->d_counts + 3));
-    (*launches)++;
-  } else if (c->c4_nmid > 0) {
-    int grid = int(std::min<int64_t>(c->c4_nmid, int64_t(c->c4_dense_ctas)));
-    c4_mid_kernel<<<grid, kC4MidThreads, 0, g->stream>>>(c->c4_mid, c->c4_nmid, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
-                                                         c->c4_dense, c->c4_dense_stride, g->d_ticket + 1, g->d_counts + 3);
-    (*launches)++;
-  }
-  for (vidType u : c->c4_heavy) {
-    c4_heavy_kernel<<<c->num_sms * 8, 256, 0, g->stream>>>(u, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol, c->c4_dense, g->d_counts + 3);
-    GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, c->c4_dense_stride * 4, g->stream));
-    (*launches)++;
-  }
+  GM_TRY(launch_c4_tiers(g, c, g->d_counts + 3, launches));
   // 3. 4-cliques: the bit-matrix kernel on the child, accumulating straight into counters[5]
   {
     unsigned long long *save = c->d_counts;

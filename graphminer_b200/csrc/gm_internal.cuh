@@ -171,6 +171,8 @@ int run_diamond_support(gm_graph *g, int *launches);
 int run_support_pass(gm_graph *g, int *launches);
 int prepare_motif4_fast(gm_graph *g, bool *ok);
 int run_motif4_fast(gm_graph *g, int *launches);
+int prepare_rectangle_fast(gm_graph *g, bool *ok);
+int run_rectangle_fast(gm_graph *g, int *launches);
 void invalidate_range_structures_of_child(gm_graph *c);
 void free_c4(gm_graph *c);
 int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break = 0);

@@ -484,3 +484,34 @@ def test_diamond_partitioned_support_exchange():
         assert g.sgl("diamond") == oracle.sgl(rp, ci, "diamond", (b, e))
         g.close()
     assert got == GOLD["rmat12"]["diamond"]
+
+
+@pytest.mark.parametrize("algo", ["auto", "list"])
+def test_rectangle_both_algorithms(algo, citeseer, mico):
+    """sgl rectangle (every 4-cycle once): wedge-pair counting on the DAG (full source range) and the
+    warp-per-edge operator-API kernel; with a partial range both settings take the operator-API kernel."""
+    capi.set_option("sgl.algo", algo)
+    for (rp, ci, md), name in ((citeseer, "citeseer"), (mico, "mico")):
+        with capi.DeviceGraph(rp, ci, md) as g:
+            assert g.sgl("rectangle") == KAT[name]["rectangle"]
+            assert g.sgl("diamond") == KAT[name]["diamond"]          # the two fast paths share the child handle
+            assert g.sgl("rectangle") == KAT[name]["rectangle"]
+    for name in ("rmat8", "rmat10", "rmat12", "shaped3000"):
+        rp, ci = _graph(name)
+        with capi.DeviceGraph(rp, ci, 0) as g:
+            assert g.sgl("rectangle") == GOLD[name]["rectangle"], name
+            nv = len(rp) - 1
+            g.set_source_range(nv // 2, nv)
+            assert g.sgl("rectangle") == oracle.sgl(rp, ci, "rectangle", (nv // 2, nv))
+            g.set_source_range(0, nv)
+            assert g.sgl("rectangle") == GOLD[name]["rectangle"]
+    a, b = 6, 11                                                     # K_{a,b}: C(a,2) * C(b,2) four-cycles
+    rp = np.concatenate([[0], np.cumsum([b] * a + [a] * b)]).astype(np.int64)
+    ci = np.concatenate([np.arange(a, a + b)] * a + [np.arange(a)] * b).astype(np.int32)
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        assert g.sgl("rectangle") == (a * (a - 1) // 2) * (b * (b - 1) // 2)
+    n = 9                                                            # K_n: 3 * C(n,4) four-cycles
+    rp = np.arange(0, n * (n - 1) + 1, n - 1, dtype=np.int64)
+    ci = np.concatenate([np.delete(np.arange(n, dtype=np.int32), i) for i in range(n)])
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        assert g.sgl("rectangle") == 3 * (n * (n - 1) * (n - 2) * (n - 3) // 24)
