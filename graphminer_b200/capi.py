@@ -28,7 +28,7 @@ ALGOS = {"auto": 0, "bsearch": 1, "merge": 2, "hash": 3, "gallop": 4}
 SYMBOLS = [
     "gm_last_error", "gm_version", "gm_device_count", "gm_device_init", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
-    "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph",
+    "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
     "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
     "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
@@ -74,6 +74,8 @@ def lib():
     L.gm_host_read_meta.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]
     L.gm_host_read_graph.argtypes = [C.c_char_p, i32, i64, _i64p, _i32p]
     L.gm_host_write_graph.argtypes = [C.c_char_p, i32, i64, i32, _i64p, _i32p]
+    L.gm_host_sort_neighbors.argtypes = [i32, _i64p, _i32p]
+    L.gm_host_check_sorted.argtypes = [i32, _i64p, _i32p]
     L.gm_graph_upload.argtypes = [vp, vp, i32, i64, i32, C.c_int, C.POINTER(vp)]
     L.gm_graph_adopt.argtypes = [vp, vp, i32, i64, i32, C.c_int, C.POINTER(vp)]
     L.gm_graph_free.argtypes = [vp]
@@ -182,6 +184,22 @@ def read_graph(prefix: str):
     ci = np.empty(max(1, ne.value), dtype=np.int32)
     check(lib().gm_host_read_graph(prefix.encode(), nv.value, ne.value, rp, ci))
     return rp, ci[:ne.value], md.value
+
+
+def sort_neighbors(rowptr, colidx):
+    """Graph::sort_neighbors: returns a copy of colidx with every row sorted."""
+    rp, ci, nv = _csr(rowptr, colidx)
+    out = _pad(ci).copy()
+    check(lib().gm_host_sort_neighbors(nv, rp, out))
+    return out[: len(ci)]
+
+
+def check_sorted(rowptr, colidx) -> bool:
+    rp, ci, nv = _csr(rowptr, colidx)
+    r = lib().gm_host_check_sorted(nv, rp, _pad(ci))
+    if r < 0:
+        check(int(r))
+    return bool(r)
 
 
 def write_graph(prefix: str, rowptr, colidx, max_degree=None):

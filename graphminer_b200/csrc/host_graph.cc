@@ -3,7 +3,9 @@
 // immediately before the hot path: the binary loader (src/common/graph.cc:19-41), the DAG
 // orientation (graph.cc:233-279), the COO builder (graph.cc:297-326) and the 1-D vertex-range
 // partitioner with 1-hop induced subgraphs (src/common/graph_partition.cc:24-132).
+#include <fcntl.h>
 #include <omp.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -157,12 +159,26 @@ int gm_host_read_meta(const char *prefix, int32_t *nv, int64_t *ne, int32_t *max
   return GM_OK;
 }
 
+// Parallel positional read: the file is cut into 64 MiB pieces read with pread() by the OpenMP team (the
+// reference reads each file with one ifstream::read, include/custom_alloc.h:33-44).
 static int read_all(const std::string &path, void *dst, size_t bytes) {
-  FILE *fp = std::fopen(path.c_str(), "rb");
-  if (!fp) { set_error("cannot open %s", path.c_str()); return GM_EIO; }
-  size_t got = bytes ? std::fread(dst, 1, bytes, fp) : 0;
-  std::fclose(fp);
-  if (got != bytes) { set_error("%s: short read (%zu of %zu bytes)", path.c_str(), got, bytes); return GM_EIO; }
+  int fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) { set_error("cannot open %s", path.c_str()); return GM_EIO; }
+  const size_t piece = size_t(64) << 20;
+  const int64_t npieces = int64_t((bytes + piece - 1) / piece);
+  int bad = 0;
+  #pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
+  for (int64_t i = 0; i < npieces; i++) {
+    size_t off = size_t(i) * piece, left = std::min(piece, bytes - off);
+    char *out = static_cast<char *>(dst) + off;
+    while (left > 0) {
+      ssize_t got = ::pread(fd, out, left, off_t(off));
+      if (got <= 0) { bad |= 1; break; }
+      out += got; off += size_t(got); left -= size_t(got);
+    }
+  }
+  ::close(fd);
+  if (bad) { set_error("%s: short read (file smaller than %zu bytes)", path.c_str(), bytes); return GM_EIO; }
   return GM_OK;
 }
 
@@ -174,6 +190,30 @@ int gm_host_read_graph(const char *prefix, int32_t nv, int64_t ne, int64_t *rowp
   if (r != GM_OK) return r;
   if (rowptr[0] != 0 || rowptr[nv] != ne) { set_error("%s: rowptr does not match meta (rowptr[nv]=%lld, ne=%lld)", prefix, (long long)rowptr[nv], (long long)ne); return GM_EIO; }
   return GM_OK;
+}
+
+// Graph::sort_neighbors, src/common/graph.cc:138-146 (the `adj_sorted = 0` path of triangle/main.cc:21-22)
+int gm_host_sort_neighbors(int32_t nv, const int64_t *rowptr, int32_t *colidx) {
+  if (nv < 0 || !rowptr || (rowptr[nv] > 0 && !colidx)) { set_error("gm_host_sort_neighbors: bad arguments"); return GM_EINVAL; }
+  #pragma omp parallel for schedule(dynamic, 1024)
+  for (int32_t v = 0; v < nv; v++) std::sort(colidx + rowptr[v], colidx + rowptr[v + 1]);
+  return GM_OK;
+}
+
+// The standing assumption of every solver ("we assume the neighbor lists are sorted", triangle/main.cc:13):
+// returns 1 when every row is strictly increasing, has no self loop and only ids in [0, nv); 0 otherwise.
+int gm_host_check_sorted(int32_t nv, const int64_t *rowptr, const int32_t *colidx) {
+  if (nv < 0 || !rowptr || (rowptr[nv] > 0 && !colidx)) { set_error("gm_host_check_sorted: bad arguments"); return GM_EINVAL; }
+  int bad = 0;
+  #pragma omp parallel for schedule(dynamic, 4096) reduction(| : bad)
+  for (int32_t v = 0; v < nv; v++) {
+    if (rowptr[v + 1] < rowptr[v]) { bad |= 1; continue; }
+    for (int64_t i = rowptr[v]; i < rowptr[v + 1]; i++) {
+      const int32_t u = colidx[i];
+      if (u < 0 || u >= nv || u == v || (i > rowptr[v] && colidx[i - 1] >= u)) { bad |= 1; break; }
+    }
+  }
+  return bad ? 0 : 1;
 }
 
 int gm_host_write_graph(const char *prefix, int32_t nv, int64_t ne, int32_t max_degree,

@@ -68,6 +68,11 @@ class Graph {
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "Time on generating the DAG: " << s << " sec\n";
   }
+  // Graph::sort_neighbors (graph.cc:138-146)
+  void sort_neighbors() {
+    std::cout << "Sorting the neighbor lists (used for pattern mining)\n";
+    die_on(gm_host_sort_neighbors(nv_, rowptr_.data(), colidx_.data()), "sort_neighbors");
+  }
   vidType V() const { return nv_; }
   eidType E() const { return ne_; }
   vidType num_vertices() const { return nv_; }

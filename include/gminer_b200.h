@@ -85,6 +85,12 @@ int gm_host_read_meta(const char *prefix, int32_t *nv, int64_t *ne, int32_t *max
 int gm_host_read_graph(const char *prefix, int32_t nv, int64_t ne, int64_t *rowptr, int32_t *colidx);
 int gm_host_write_graph(const char *prefix, int32_t nv, int64_t ne, int32_t max_degree,
                         const int64_t *rowptr, const int32_t *colidx);
+/* Graph::sort_neighbors, src/common/graph.cc:138-146: sort every adjacency row in place (the
+ * `adj_sorted = 0` path of triangle/main.cc:21-22). */
+int gm_host_sort_neighbors(int32_t nv, const int64_t *rowptr, int32_t *colidx);
+/* 1 when every row is strictly increasing, loop-free and within [0, nv) -- the solvers' standing
+ * assumption (triangle/main.cc:13) --, 0 otherwise, negative on bad arguments. */
+int gm_host_check_sorted(int32_t nv, const int64_t *rowptr, const int32_t *colidx);
 
 /* ---- device graph ------------------------------------------------------------------------- */
 /* GraphGPU::init, include/graph_gpu.h:69-122: copy a host CSR to `device`.  Host arrays are

@@ -85,3 +85,30 @@ def test_bad_arguments_are_errors_not_exits():
         capi.kclique_host(np.zeros(2, np.int64), np.zeros(0, np.int32), 9)
     with pytest.raises(capi.GMError):
         capi.sgl_host(np.zeros(2, np.int64), np.zeros(0, np.int32), "no-such-pattern")
+
+
+def test_loader_sort_and_check(tmp_path):
+    """Loader-side pieces (SURVEY §8f N3): parallel positional read round-trips the reference format;
+    gm_host_sort_neighbors = Graph::sort_neighbors; gm_host_check_sorted states the solvers' assumption."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    nv = 5000
+    deg = rng.integers(0, 40, nv)
+    rp = np.zeros(nv + 1, np.int64); rp[1:] = np.cumsum(deg)
+    rows = [np.sort(rng.choice(np.delete(np.arange(nv), v), d, replace=False)).astype(np.int32) for v, d in enumerate(deg)]
+    ci = np.concatenate(rows) if len(rows) else np.zeros(0, np.int32)
+    assert capi.check_sorted(rp, ci)
+    shuffled = np.concatenate([rng.permutation(r) for r in rows])
+    assert not capi.check_sorted(rp, shuffled)
+    assert np.array_equal(capi.sort_neighbors(rp, shuffled), ci)
+    loop = ci.copy(); loop[rp[7]] = 7 if deg[7] else loop[rp[7]]
+    if deg[7]:
+        assert not capi.check_sorted(rp, loop)
+    prefix = str(tmp_path / "graph")
+    capi.write_graph(prefix, rp, ci)
+    rp2, ci2, md = capi.read_graph(prefix)
+    assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and md == int(deg.max())
+    with open(prefix + ".edge.bin", "r+b") as f:            # truncated file: loud failure, not a short read
+        f.truncate(max(0, ci.nbytes - 4))
+    with pytest.raises(capi.GMError):
+        capi.read_graph(prefix)

@@ -68,3 +68,18 @@ def test_usage_exit_code():
         pytest.skip("not built")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 1 and "Usage:" in r.stdout
+
+
+def test_tc_unsorted_input(tmp_path_factory, citeseer):
+    """`tc <graph> 1 1024 0`: adj_sorted = 0 sorts the neighbour lists after loading (triangle/main.cc:21-22)."""
+    import numpy as np
+    rp, ci, md = citeseer
+    rng = np.random.default_rng(1)
+    shuffled = ci.copy()
+    for v in range(len(rp) - 1):
+        shuffled[rp[v]:rp[v + 1]] = rng.permutation(ci[rp[v]:rp[v + 1]])
+    assert not capi.check_sorted(rp, shuffled)
+    prefix = str(tmp_path_factory.mktemp("citeseer_unsorted") / "graph")
+    capi.write_graph(prefix, rp, shuffled, md)
+    out = run("tc_gpu_base", prefix, 1, 1024, 0)
+    assert "Sorting the neighbor lists" in out and f"total_num_triangles = {KAT['tc']}\n" in out
