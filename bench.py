@@ -445,17 +445,25 @@ def run_ours(args):
 
 def cpu_baseline(rp, ci, max_deg, kind, budget_s=12.0):
     """oracle/_ref/libgm_ref.so = the reference's VertexSet code + its loop nest over a source range
-    (tc / 4-clique / diamond); 4-motif: the oracle port of automine_4motif (kind "port")."""
+    (tc / 4-clique / diamond / formula 4-motif); without it the oracle port (kind "port")."""
     import oracle
     nv = len(rp) - 1
-    use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so")) and kind != "motif4"
+    use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so"))
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if use_ref:
         L = oracle.ref_lib()
         L.gmr_set_num_threads(ncpu)            # torchrun sets OMP_NUM_THREADS=1; use every host core
         h = L.gmr_graph_create(nv, rp, ci, max_deg)
+        def motif4_formula(a, b):
+            # the reference's formula loop nest (automine_formula.h:21-56) on the range, then its fix-up
+            # (omp_formula.cc:39-46; linear up to integer rounding, so a range's share is well defined)
+            t = np.zeros(6, np.uint64)
+            L.gmr_motif4_formula_raw_range(h, a, b, t)
+            t = [int(x) for x in t]
+            t[4] = t[4] // 2 - t[5] * 6; t[2] = t[2] // 2 - t[4] * 2; t[1] = t[1] - t[3] * 4; t[0] = t[0] // 6 - t[2] // 3
+            return max(0, sum(t))
         run = {"tc": lambda a, b: L.gmr_tc_range(h, a, b), "clique4": lambda a, b: L.gmr_kclique_range(h, 4, a, b),
-               "diamond": lambda a, b: L.gmr_diamond_range(h, a, b)}[kind]
+               "diamond": lambda a, b: L.gmr_diamond_range(h, a, b), "motif4": motif4_formula}[kind]
         cores = L.gmr_num_threads()
     else:
         oracle.set_num_threads(ncpu)

@@ -253,6 +253,8 @@ def ref_lib():
         L.gmr_kclique_range.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int32]
         L.gmr_diamond_range.restype = C.c_uint64
         L.gmr_diamond_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.gmr_motif4_formula_raw_range.restype = None
+        L.gmr_motif4_formula_raw_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]
         L.gmr_num_threads.restype = C.c_int
         L.gmr_set_num_threads.argtypes = [C.c_int]
         _ref = L

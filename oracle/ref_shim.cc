@@ -4,7 +4,7 @@
 // into oracle/_ref/libgm_ref.so.  It lets bench.py time the reference's own set operators
 // (VertexSet::get_intersect_num / operator& -- include/VertexSet.h:53-76) driven by the
 // reference's loop nests (src/triangle/omp_base.cc:15-21, src/clique/cpu_kernels/automine_omp.h:67-83,
-// src/sgl/cpu_kernels/diamond.h:1-14) on an in-memory CSR, over a bounded source-vertex range
+// src/sgl/cpu_kernels/diamond.h:1-14, src/motif/cpu_kernels/automine_formula.h:21-56) on an in-memory CSR, over a bounded source-vertex range
 // [v_begin, v_end) -- the stock binaries can only run whole files.  Nothing of the product links this.
 #include "graph.h"
 
@@ -88,6 +88,40 @@ uint64_t gmr_diamond_range(void *h, int32_t v_begin, int32_t v_end) {
     }
   }
   return counter;
+}
+
+// loop nest of the formula 4-motif solver, src/motif/cpu_kernels/automine_formula.h:21-56, over a source range;
+// out[0..5] = RAW sums (the closed-form fix-up of omp_formula.cc:39-46 is applied by the caller)
+void gmr_motif4_formula_raw_range(void *h, int32_t v_begin, int32_t v_end, uint64_t *out) {
+  Graph &g = *static_cast<ViewGraph *>(h);
+  uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+  #pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2, c3, c4, c5)
+  for (vidType v0 = v_begin; v0 < v_end; v0++) {
+    VertexSet y0 = g.N(v0);
+    VertexSet y0f0 = bounded(y0, v0);
+    for (vidType idx1 = 0; idx1 < y0f0.size(); idx1++) {
+      vidType v1 = y0f0.begin()[idx1];
+      VertexSet y1 = g.N(v1);
+      uint64_t tri = intersection_num(y0, y1);
+      uint64_t staru = y0.size() - tri - 1, starv = y1.size() - tri - 1;
+      c4 += tri * (tri - 1);
+      c2 += tri * (staru + starv);
+      c1 += staru * starv;
+      c0 += staru * (staru - 1) + starv * (starv - 1);
+      VertexSet y0f0y1f1 = intersection_set(y0f0, y1, v1);
+      VertexSet n0f0y1; difference_set(n0f0y1, y1, y0);
+      VertexSet y0f0n1f1 = difference_set(y0f0, y1, v1);
+      for (vidType idx2 = 0; idx2 < y0f0y1f1.size(); idx2++) {
+        vidType v2 = y0f0y1f1.begin()[idx2];
+        c5 += intersection_num(y0f0y1f1, g.N(v2), v2);
+      }
+      for (vidType idx2 = 0; idx2 < y0f0n1f1.size(); idx2++) {
+        vidType v2 = y0f0n1f1.begin()[idx2];
+        c3 += intersection_num(n0f0y1, g.N(v2), v0);
+      }
+    }
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3; out[4] = c4; out[5] = c5;
 }
 
 void gmr_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }   // torchrun exports OMP_NUM_THREADS=1

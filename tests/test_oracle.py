@@ -68,3 +68,29 @@ def test_edgelist_semantics(citeseer):
     assert len(src) == len(ci) // 2 and np.all(src > dst)
     src, dst = oracle.edgelist(rp, ci, sym_break=False)
     assert len(src) == len(ci) and np.array_equal(dst, ci)
+
+
+def test_reference_formula_shim_shards_add_up():
+    """oracle/_ref/libgm_ref.so runs the reference's own formula 4-motif loop nest over a source range
+    (bench.py's CPU baseline for the motif workload): raw sums of the shards + fix-up = the golden counts."""
+    import json
+    import os
+    import numpy as np
+    import oracle
+    from graphminer_b200.rmat import rmat_graph
+    if not oracle.have_ref() or not os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so")):
+        import pytest
+        pytest.skip("reference objects not built")
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rmat_counts.json")))["rmat12"]["motif4_formula"]
+    rp, ci = (t.numpy() for t in rmat_graph(12))
+    L = oracle.ref_lib()
+    nv = len(rp) - 1
+    h = L.gmr_graph_create(nv, rp, ci, int(np.diff(rp).max()))
+    tot, raw = np.zeros(6, np.uint64), np.zeros(6, np.uint64)
+    for b, e in ((0, 777), (777, 778), (778, nv)):
+        L.gmr_motif4_formula_raw_range(h, b, e, raw)
+        tot += raw
+    L.gmr_graph_free(h)
+    t = [int(x) for x in tot]
+    t[4] = t[4] // 2 - t[5] * 6; t[2] = t[2] // 2 - t[4] * 2; t[1] = t[1] - t[3] * 4; t[0] = t[0] // 6 - t[2] // 3
+    assert t == gold
