@@ -140,7 +140,8 @@ class Workload:
         self.oriented = k in ("tc", "clique4")
         self.scaling = "strong"                    # the same graph at every N, sharded by source-vertex range
         if self.oriented:
-            self.scale = args.scale or (23 if k == "clique4" else 22)
+            # north_star target: TC and 4-clique on R-MAT scale 24 at 1/2/4/8 GPUs; configs[2] names scale 23 for 4-clique
+            self.scale = args.scale or (23 if k == "clique4" else 24)
             self.name = f"{'kclique4' if k == 'clique4' else 'tc'}_rmat_scale{self.scale}"
         elif k == "diamond":
             self.div = max(1, args.shape_div or 1)
@@ -179,6 +180,18 @@ class Workload:
             return [g.sgl("diamond")]
         return g.motif(4, formula=True, raw=True)
 
+    # the second implementation of the same count: the warp-per-edge kernels over the operator API
+    # (include/gm/set_ops.cuh), which follow the reference's own schedule
+    SECOND = {"tc": ("tc.algo", "bs"), "clique4": ("clique.algo", "list"), "diamond": ("sgl.algo", "list"), "motif4": ("motif.algo", "list")}
+
+    def solve_second(self, capi, g):
+        key, val = self.SECOND[self.kind]
+        capi.set_option(key, val)
+        try:
+            return self.solve(g)
+        finally:
+            capi.set_option(key, "auto")
+
     def finish(self, counts):
         if self.kind == "motif4":
             from graphminer_b200 import capi
@@ -187,6 +200,10 @@ class Workload:
 
     def units(self, counts, ne):
         return ne if self.kind == "tc" else int(sum(counts))
+
+    def tasks(self, ne):
+        """DFS roots of the reference's schedule: one warp task per (oriented / symmetry-broken) edge"""
+        return ne if self.oriented else ne // 2
 
     def host_solve(self, capi, rp, ci, max_deg):
         k = self.kind
@@ -221,10 +238,10 @@ def shard_bounds(torch, rp, ci, n, kind="tc"):
     return [0] + [int(c) for c in cuts] + [nv]
 
 
-def stream_microbench(torch, capi, dev, gb=4.0, reps=7):
+def stream_microbench(torch, capi, dev, gb=8.0, reps=7):
     """The north-star's HBM-roofline claim: every streaming variant of gm_intersect_batch on independent
-    pairs drawn from the scale-24 out-degree pairs, each list read once, pool (4 GB) far beyond L2.
-    Algorithmic bytes = 4*(|a|+|b|) per pair = the DRAM traffic of a single pass."""
+    pairs drawn from the scale-24 out-degree pairs, each list read once, pool (8 GB) far
+    beyond L2.  Algorithmic bytes = 4*(|a|+|b|) per pair = the DRAM traffic of a single pass."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from batch_bench import make_batch
     pool, ao, al, bo, bl = make_batch(24, gb, dev)
@@ -249,12 +266,88 @@ def stream_microbench(torch, capi, dev, gb=4.0, reps=7):
             "variants": out}
 
 
-def ncu_traffic(name):
-    """DRAM bytes per step of the pass's kernels from the committed ncu --set full capture, or None."""
+def ncu_profile(name):
+    """Per-step DRAM bytes, warp instructions and IPC of the pass's kernels, from profiles/traffic.json --
+    written by tools/ncu_traffic.py from the ncu capture of this same bench command (never measured under the
+    profiler here).  None when the workload has no committed capture."""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
     except Exception:
         return None
+
+
+def cpu_reference(rp, ci, max_deg, kind, budget_s=12.0, full_cap_s=0.0):
+    """oracle/_ref/libgm_ref.so = the reference's VertexSet code + its loop nest over a source range
+    (tc / 4-clique / diamond / formula 4-motif); without it the oracle port (kind "port").
+    Consecutive source ranges [0,n1) of growing size until ~budget_s of CPU time is spent (vertex ids are
+    randomly permuted, so a prefix of the id range is an unbiased sample); the pass continues to the WHOLE
+    graph when its projected total stays below full_cap_s.  Returns the raw counts of the range as well: the
+    GPU must reproduce them on the same range (parity pin on the driver's box)."""
+    import oracle
+    nv = len(rp) - 1
+    use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so"))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nc = 6 if kind == "motif4" else 1
+    if use_ref:
+        L = oracle.ref_lib()
+        L.gmr_set_num_threads(ncpu)            # torchrun sets OMP_NUM_THREADS=1; use every host core
+        h = L.gmr_graph_create(nv, rp, ci, max_deg)
+
+        def motif4_raw(a, b):
+            # the reference's formula loop nest (automine_formula.h:21-56) on the range: RAW sums
+            t = np.zeros(6, np.uint64)
+            L.gmr_motif4_formula_raw_range(h, a, b, t)
+            return [int(x) for x in t]
+        run = {"tc": lambda a, b: [L.gmr_tc_range(h, a, b)], "clique4": lambda a, b: [L.gmr_kclique_range(h, 4, a, b)],
+               "diamond": lambda a, b: [L.gmr_diamond_range(h, a, b)], "motif4": motif4_raw}[kind]
+        cores = L.gmr_num_threads()
+    else:
+        oracle.set_num_threads(ncpu)
+        run = {"tc": lambda a, b: [oracle.tc(rp, ci, (a, b))], "clique4": lambda a, b: [oracle.kclique(rp, ci, 4, (a, b))],
+               "diamond": lambda a, b: [oracle.sgl(rp, ci, "diamond", (a, b))],
+               "motif4": lambda a, b: None}[kind]
+        cores = oracle.num_threads()
+    done, raw, dt = 0, [0] * nc, 0.0
+    step = max(1, nv // (200 if kind in ("tc", "clique4") else 50000))
+    while done < nv:
+        projected = dt * nv / done if done else float("inf")
+        if dt >= 0.8 * budget_s and projected > full_cap_s:
+            break
+        hi = min(nv, done + step)
+        t0 = time.perf_counter(); r = run(done, hi); dt += time.perf_counter() - t0
+        if r is None:
+            raise RuntimeError("no CPU formula-motif range kernel without oracle/_ref")
+        raw = [(x + y) & ((1 << 64) - 1) for x, y in zip(raw, r)]
+        done = hi
+        rate = done / max(dt, 1e-6)                                   # sources per second so far
+        left = (full_cap_s if dt * nv / done <= full_cap_s else budget_s) - dt
+        step = int(max(1, min(2 * done, rate * max(left, 0.0))))
+    n1 = done
+    edges = int(rp[n1] - rp[0])
+    if kind == "motif4":
+        t = list(raw)                                                 # fix-up of omp_formula.cc:39-46 (integer, exact on the whole graph)
+        t[4] = t[4] // 2 - t[5] * 6; t[2] = t[2] // 2 - t[4] * 2; t[1] = t[1] - t[3] * 4; t[0] = t[0] // 6 - t[2] // 3
+        units = max(0, sum(t))
+    else:
+        units = edges if kind == "tc" else raw[0]
+    if use_ref:
+        L.gmr_graph_free(h)
+    return {"value": units / dt, "unit": "edges/s" if kind == "tc" else "matches/s", "cores": cores,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"source vertices [0,{n1}) of {nv} ({edges} CSR entries), {dt:.2f} s",
+            "n1": n1, "raw": raw, "full": n1 == nv}
+
+
+def gpu_range_counts(capi, g, wl, n1, nv):
+    """the timed solver and the operator-API solver restricted to DFS roots [0,n1) (reference shard semantics)"""
+    g.set_result_buffer(None)
+    g.set_source_range(0, n1)
+    try:
+        fast = wl.solve(g)
+        second = wl.solve_second(capi, g)
+    finally:
+        g.set_source_range(0, nv)
+    return fast, second
 
 
 def run_ours(args):
@@ -291,7 +384,6 @@ def run_ours(args):
     g.set_stream(stream.cuda_stream)
     g.set_source_range(b, e)
     g.prepare(wl.prepare)
-    cnt_dev = torch.zeros(wl.ncounts, dtype=torch.int64, device=dev)
     res_dev = torch.zeros(8, dtype=torch.int64, device=dev)
 
     if world > 1:
@@ -348,54 +440,95 @@ def run_ours(args):
     alg_bytes = int(alg_bytes.item())
 
     units = wl.units(counts, ne)                       # matches/s for k-CL / SgL / k-MC, edges/s for TC
-    value = units / (elapsed_ms / args.steps / 1e3)
+    step_s = elapsed_ms / args.steps / 1e3
+    value = units / step_s
 
-    # ---- parity guard (outside the timed region): a second implementation must agree -------------
-    check = None
-    if wl.kind == "tc":
-        g.set_result_buffer(None)
-        capi.set_option("tc.algo", "bs")
-        c2 = torch.tensor([g.tc()], dtype=torch.int64, device=dev)
-        capi.set_option("tc.algo", "auto")
-        if world > 1:
-            dist.all_reduce(c2)
-        check = int(c2.item())
-        assert check == counts[0], f"parity failure: hash path {counts[0]} != operator path {check}"
-
-    # ---- end to end through the host entry point (pinned host CSR in, count out) ----------------
+    # ---- end to end: HOST CSR in (pinned), count out; every copy inside the timed region ------------
     h_rp = torch.empty(rp.shape, dtype=rp.dtype, pin_memory=True); h_rp.copy_(rp)
     h_ci = torch.empty(ci.shape, dtype=ci.dtype, pin_memory=True); h_ci.copy_(ci)
     torch.cuda.synchronize()
     n_rp, n_ci = h_rp.numpy(), h_ci.numpy()
+    if world > 1:
+        # every rank copies 1/N of the host CSR over its own PCIe link; the slices are exchanged over NVLink
+        # (one all-gather each for rowptr and colidx) -- the H2D volume of the whole job is the CSR, once
+        crp, cci = -(-(nv + 1) // world), -(-max(ne, 1) // world)
+        d_rp_all = torch.empty(crp * world, dtype=rp.dtype, device=dev)
+        d_ci_all = torch.empty(cci * world, dtype=ci.dtype, device=dev)
+        rp_lo, rp_hi = min(rank * crp, nv + 1), min((rank + 1) * crp, nv + 1)
+        ci_lo, ci_hi = min(rank * cci, ne), min((rank + 1) * cci, ne)
 
     def e2e_step():
         if world == 1:
-            return wl.host_solve(capi, n_rp, n_ci, max_deg)
-        with capi.DeviceGraph(n_rp, n_ci, max_deg, device=local) as gg:
+            return wl.finish(wl.host_solve(capi, n_rp, n_ci, max_deg))   # gm_*_host: upload + prepare + kernels + D2H
+        d_rp_all[rp_lo:rp_hi].copy_(h_rp[rp_lo:rp_hi], non_blocking=True)
+        d_ci_all[ci_lo:ci_hi].copy_(h_ci[ci_lo:ci_hi], non_blocking=True)
+        dist.all_gather_into_tensor(d_rp_all, d_rp_all[rank * crp:(rank + 1) * crp])
+        dist.all_gather_into_tensor(d_ci_all, d_ci_all[rank * cci:(rank + 1) * cci])
+        gg = capi.DeviceGraph.adopt(d_rp_all[:nv + 1], d_ci_all[:ne], max_deg)
+        try:
             gg.set_stream(stream.cuda_stream)
             gg.set_source_range(b, e)
             gg.set_result_buffer(res_dev)
             return solve_sharded(gg)
+        finally:
+            gg.close()
 
     e2e_steps = max(1, min(args.steps, 5))
-    assert e2e_step() == counts
+    for _ in range(2):
+        got = e2e_step()
+        assert got == counts, f"end-to-end path disagrees: {got} != {counts}"
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        assert e2e_step() == counts
+        got = e2e_step()
     sync_all()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    assert got == counts
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        del d_rp_all, d_ci_all
     e2e_value = units / float(e2e_s)
 
-    # ---- CPU baseline: the reference's own OpenMP code on a bounded sample (rank 0, N=1) ---------
+    # ---- parity (outside the timed regions) -------------------------------------------------------
+    # (1) the operator-API solver (the reference's warp-per-edge schedule) on the whole graph for TC;
+    # (2) the reference's own CPU code on a source range [0,n1) -- the whole graph when it is fast enough --
+    #     against BOTH device solvers restricted to the same range (N=1, rank 0: the spec's CPU leg)
+    parity = {"second_algorithm": None, "reference_cpu": None}
+    if wl.kind == "tc":
+        g.set_result_buffer(None)
+        c2 = torch.tensor(wl.solve_second(capi, g), dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(c2)
+            g.set_result_buffer(res_dev)
+        c2 = [int(x) for x in c2.tolist()]
+        assert c2 == counts, f"parity failure: timed solver {counts} != operator-API solver {c2}"
+        parity["second_algorithm"] = {"algo": "tc.algo=bs (warp per edge, gm::intersect_num)", "range": [0, nv], "count": c2[0], "match": True}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_baseline(n_rp, n_ci, max_deg, wl.kind, budget_s=args.cpu_seconds)
+            cpu = cpu_reference(n_rp, n_ci, max_deg, wl.kind, budget_s=args.cpu_seconds, full_cap_s=args.cpu_full_cap)
         except Exception as ex:                        # an auxiliary leg must not cost the bench line
             cpu = {"error": repr(ex)}
+        if "raw" in cpu:
+            n1, want = cpu.pop("n1"), cpu.pop("raw")
+            fast, second = gpu_range_counts(capi, g, wl, n1, nv)
+            # formula 4-motif: the fast path counts 4-cycles / 4-cliques at their highest-RANKED vertex, the
+            # reference at their largest id -- equal over the whole graph, not per range; the four closed
+            # forms and the operator-API kernel partition exactly like the reference
+            idx = range(wl.ncounts) if (wl.kind != "motif4" or n1 == nv) else (0, 1, 2, 4)
+            ok_fast = all(fast[i] == want[i] for i in idx)
+            ok_second = second == want
+            assert ok_fast and ok_second, f"parity failure on sources [0,{n1}): reference CPU {want}, timed solver {fast}, operator-API solver {second}"
+            if n1 == nv:
+                assert wl.finish(list(want)) == counts, f"parity failure: reference CPU {want} vs timed {counts}"
+            parity["reference_cpu"] = {"range": [0, n1], "full": n1 == nv, "reference_count": want if wl.ncounts > 1 else want[0],
+                                       "timed_solver_match": True, "operator_api_solver_match": True,
+                                       "compared_indices": list(idx)}
+            if parity["second_algorithm"] is None:
+                parity["second_algorithm"] = {"algo": "%s=%s" % wl.SECOND[wl.kind], "range": [0, n1], "match": True}
+    parity_tag = ("reference_cpu_full" if parity["reference_cpu"] and parity["reference_cpu"]["full"] else
+                  "reference_cpu_range" if parity["reference_cpu"] else
+                  "second_algorithm" if parity["second_algorithm"] else "none")
 
     g.close()
     del g, rp, ci
@@ -408,31 +541,53 @@ def run_ours(args):
             stream_rf = {"error": repr(ex)}
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = alg_bytes / (kern_total_ms / args.steps / 1e3) / 1e9 if alg_bytes else None
+        kms = kern_total_ms / args.steps
+        prof = ncu_profile(wl.name) if n == 1 else None
+        traffic = prof.get("dram_bytes_per_step") if prof else None
+        dram_gbs = traffic / (kms / 1e3) / 1e9 if traffic else None
         kernel = {"tc": "tc_hash_kernel<MODE=2 ranked>", "clique4": "kclique_bitmap_kernel",
                   "diamond": "tc_support_kernel + k_diamond_sum", "motif4": "tc_support_kernel + c4_{small,cta,cluster,heavy}_kernel + kclique_bitmap_kernel"}[wl.kind]
+        roofline = {
+            # PHYSICAL HBM fraction: DRAM bytes the pass moves (ncu, per step) / device time / measured copy peak.
+            # The solvers keep their working set in shared memory and the 126 MB L2, so this is far below 1 by
+            # design; what limits them is instruction issue (`issue`), and the single-pass HBM roofline of the
+            # intersection kernels themselves is `stream_roofline`.
+            "bound": "hbm", "achieved": dram_gbs, "peak": peak, "unit": "GB/s",
+            "frac": (dram_gbs / peak) if dram_gbs else None, "traffic": traffic,
+            "peak_source": peak_src, "kernel": kernel + " (all size classes of one pass, run concurrently)",
+            "kernel_ms_per_step": kms,
+            "limiter": "issue" if prof and prof.get("ipc") else None,
+            "issue": ({"warp_insts_per_step": prof.get("warp_insts_per_step"), "ipc": prof.get("ipc"), "ipc_peak": 4.0,
+                       "frac": prof.get("ipc") / 4.0} if prof and prof.get("ipc") else None),
+            "alg_bytes_per_step": alg_bytes,
+            "alg_gbs": (alg_bytes / (kms / 1e3) / 1e9) if alg_bytes else None,
+            "source": (prof.get("source") if prof else None),
+            "note": "frac = ncu DRAM bytes per step / CUDA-event kernel time / peak (profiles/traffic.json, written by tools/ncu_traffic.py "
+                    "from the launch list of this command); alg_gbs = SURVEY 8(d) algorithmic bytes / time is reported for reference only: "
+                    "rows are re-read out of L2 and the ranked kernel streams row suffixes, so it is not a physical rate",
+        }
         out = {
             "metric": wl.metric, "value": value, "unit": wl.unit,
             "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": wl.scaling,
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": wl.name, "nv": nv, "edges": ne, "oriented": wl.oriented, "max_degree": max_deg,
-                       "count": counts[0] if len(counts) == 1 else counts, "parity_check_count": check,
+            "config": {"workload": wl.name, "nv": nv, "edges": ne, "oriented": wl.oriented},
+            "detail": {"max_degree": max_deg, "count": counts[0] if len(counts) == 1 else counts,
+                       "parity": parity_tag, "parity_checks": parity,
+                       "tasks_per_sec": wl.tasks(ne) / step_s,
+                       "tasks_note": "DFS root tasks (edges) per second: the work rate; matches/s of the count-form solvers divides a closed-form count by time",
                        "l2": "inputs (CSR %.0f MB) larger than the 126 MB L2; no flush" % ((nv * 8 + ne * 4) / 1e6),
                        "sharding": ("contiguous root ranges, work-balanced; CSR replicated; NCCL all-reduce of the per-edge support array (u32 x DAG edges) + 1 u64 per step"
                                     if wl.kind == "diamond" and n > 1 else
                                     "contiguous source-vertex ranges, work-balanced; CSR replicated; 1 NCCL all-reduce of %d u64 per step" % wl.ncounts)},
             "e2e": {"value": e2e_value, "unit": wl.unit,
-                    "h2d_bytes_per_step": int((nv + 1) * 8 + ne * 4), "d2h_bytes_per_step": 8 * wl.ncounts,
-                    "steps": e2e_steps, "note": "gm_*_host: pinned host CSR -> upload + device-side prepare + kernels + count"},
+                    "h2d_bytes_per_step": int((nv + 1) * 8 + ne * 4), "d2h_bytes_per_step": 8 * wl.ncounts * n,
+                    "steps": e2e_steps, "ms_per_step": float(e2e_s) * 1e3,
+                    "note": ("gm_*_host: pinned host CSR -> upload + device-side prepare + kernels + count" if n == 1 else
+                             "pinned host CSR -> each rank uploads 1/N (its PCIe link), NCCL all-gather over NVLink, gm_graph_adopt + device-side prepare "
+                             "+ kernels + all-reduce + count")},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(wl.name) if n == 1 else None,
-                         "peak_source": peak_src, "kernel": kernel + " (all size classes of one pass, run concurrently)",
-                         "alg_bytes_per_step": alg_bytes, "kernel_ms_per_step": kern_total_ms / args.steps,
-                         "note": "achieved = SURVEY 8(d) algorithmic bytes / device time; rows are re-read out of the 126 MB L2 and the "
-                                 "ranked kernel streams row suffixes only, so it may exceed the DRAM peak; traffic = ncu dram bytes per step; "
-                                 "the single-pass HBM roofline of the intersection kernels is in stream_roofline"},
+            "roofline": roofline,
             "stream_roofline": stream_rf,
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
@@ -441,55 +596,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(rp, ci, max_deg, kind, budget_s=12.0):
-    """oracle/_ref/libgm_ref.so = the reference's VertexSet code + its loop nest over a source range
-    (tc / 4-clique / diamond / formula 4-motif); without it the oracle port (kind "port")."""
-    import oracle
-    nv = len(rp) - 1
-    use_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libgm_ref.so"))
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    if use_ref:
-        L = oracle.ref_lib()
-        L.gmr_set_num_threads(ncpu)            # torchrun sets OMP_NUM_THREADS=1; use every host core
-        h = L.gmr_graph_create(nv, rp, ci, max_deg)
-        def motif4_formula(a, b):
-            # the reference's formula loop nest (automine_formula.h:21-56) on the range, then its fix-up
-            # (omp_formula.cc:39-46; linear up to integer rounding, so a range's share is well defined)
-            t = np.zeros(6, np.uint64)
-            L.gmr_motif4_formula_raw_range(h, a, b, t)
-            t = [int(x) for x in t]
-            t[4] = t[4] // 2 - t[5] * 6; t[2] = t[2] // 2 - t[4] * 2; t[1] = t[1] - t[3] * 4; t[0] = t[0] // 6 - t[2] // 3
-            return max(0, sum(t))
-        run = {"tc": lambda a, b: L.gmr_tc_range(h, a, b), "clique4": lambda a, b: L.gmr_kclique_range(h, 4, a, b),
-               "diamond": lambda a, b: L.gmr_diamond_range(h, a, b), "motif4": motif4_formula}[kind]
-        cores = L.gmr_num_threads()
-    else:
-        oracle.set_num_threads(ncpu)
-        run = {"tc": lambda a, b: oracle.tc(rp, ci, (a, b)), "clique4": lambda a, b: oracle.kclique(rp, ci, 4, (a, b)),
-               "diamond": lambda a, b: oracle.sgl(rp, ci, "diamond", (a, b)),
-               "motif4": lambda a, b: sum(oracle.motif(rp, ci, 4, (a, b)))}[kind]
-        cores = oracle.num_threads()
-    # consecutive source ranges of growing size until ~budget_s of CPU time is spent (vertex ids are
-    # randomly permuted, so a prefix of the id range is an unbiased sample of the workload); each next
-    # range is sized from the rate seen so far so that the total stays bounded
-    done, cnt, dt = 0, 0, 0.0
-    step = max(1, nv // (200 if kind in ("tc", "clique4") else 50000))
-    while done < nv and dt < 0.8 * budget_s:
-        hi = min(nv, done + step)
-        t0 = time.perf_counter(); cnt += run(done, hi); dt += time.perf_counter() - t0
-        done = hi
-        rate = done / max(dt, 1e-6)                                   # sources per second so far
-        step = int(max(1, min(2 * done, rate * max(budget_s - dt, 0.0))))
-    n1 = done
-    edges = int(rp[n1] - rp[0])
-    units = edges if kind == "tc" else cnt
-    if use_ref:
-        L.gmr_graph_free(h)
-    return {"value": units / dt, "unit": "edges/s" if kind == "tc" else "matches/s", "cores": cores,
-            "kind": "reference" if use_ref else "port",
-            "sample": f"source vertices [0,{n1}) of {nv} ({edges} CSR entries), {dt:.2f} s"}
 
 
 def run_reference(args):
@@ -508,11 +614,12 @@ def run_reference(args):
     vals, last = [], None
     per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(rp, ci, max_deg, wl.kind, budget_s=per_step)
+        last = cpu_reference(rp, ci, max_deg, wl.kind, budget_s=per_step)
         if i >= args.warmup:
             vals.append(last["value"])
     v = statistics.mean(vals)
     last["value"] = v
+    last.pop("raw", None); last.pop("n1", None)
     print(json.dumps({
         "impl": "reference", "metric": wl.metric,
         "value": v, "unit": wl.unit, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
@@ -533,9 +640,11 @@ def main():
     ap.add_argument("--workload", default="tc", choices=["tc", "clique4", "diamond", "motif4"])
     ap.add_argument("--shape-div", type=int, default=0, help="divide the shaped graphs (|V|, samples) by this (default: diamond 1, motif4 16)")
     ap.add_argument("--no-stream", action="store_true", help="skip the streaming-intersection roofline leg")
-    ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale at N=1 (default 22 / 23)")
+    ap.add_argument("--scale", type=int, default=0, help="R-MAT scale (default: tc 24, clique4 23)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the reference sample (the cpu_baseline leg)")
+    ap.add_argument("--cpu-full-cap", type=float, default=75.0,
+                    help="let the CPU reference finish the WHOLE graph when that is projected to take at most this long (full parity pin)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -15,6 +15,8 @@
 #include "gm_internal.cuh"
 #include "hash_table.cuh"
 
+#include <atomic>
+
 namespace gm {
 
 // ---- mbarrier / TMA bulk copy PTX wrappers (sm_90+; SASS: SYNCS.* / UBLKCP) -------------------
@@ -637,11 +639,15 @@ static int launch_pipe(const vidType *pool, const int64_t *a_off, const int32_t 
   using Cfg = PipeCfg<STAGE, NSTAGE, G, NG>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "pipeline class does not fit shared memory");
   auto k = batch_pipe_kernel<STAGE, NSTAGE, G, NG, CORE, PRED>;
-  static int occ = -1;                                       // per instantiation
+  // the shared-memory opt-in is a PER-DEVICE function attribute: set it on every launch (a process-wide
+  // "done" flag would leave every device but the first without it); only the occupancy is cached
+  GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  static std::atomic<int> occ_cache{-1};                     // per instantiation
+  int occ = occ_cache.load(std::memory_order_relaxed);
   if (occ < 0) {
-    GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, Cfg::kThreads, Cfg::kSmemBytes));
     if (occ < 1) occ = 1;
+    occ_cache.store(occ, std::memory_order_relaxed);
   }
   // the list length lives on the device; size the persistent grid by the upper bound npairs
   int grid = int(std::min<int64_t>((npairs + NG - 1) / NG, int64_t(occ) * sms));
@@ -658,11 +664,13 @@ static int launch_ring(const vidType *pool, const int64_t *a_off, const int32_t 
   using Cfg = RingCfg<RWORDS, NW>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "ring does not fit shared memory");
   auto k = batch_ring_kernel<RWORDS, NW, CORE, PRED>;
-  static int occ = -1;                                       // per instantiation
+  GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));   // per device, see launch_pipe
+  static std::atomic<int> occ_cache{-1};                     // per instantiation
+  int occ = occ_cache.load(std::memory_order_relaxed);
   if (occ < 0) {
-    GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NW * 32, Cfg::kSmemBytes));
     if (occ < 1) occ = 1;
+    occ_cache.store(occ, std::memory_order_relaxed);
   }
   int grid = int(std::min<int64_t>((npairs + kRingBlk * NW - 1) / (kRingBlk * NW), int64_t(occ) * sms));
   k<<<grid, NW * 32, Cfg::kSmemBytes, s>>>(pool, a_off, a_len, b_off, b_len, npairs, ticket, big_lists, big_counts, out);
@@ -796,11 +804,13 @@ static int launch_batch_variant(int algo, const vidType *pool, const int64_t *a_
     }
   } else {
     size_t smem = sizeof(uint32_t) * size_t(kBatchHashWords) * kBatchHashWarps;
-    static int occ = -1;
+    GM_CUDA(cudaFuncSetAttribute(batch_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));   // per device
+    static std::atomic<int> occ_cache{-1};
+    int occ = occ_cache.load(std::memory_order_relaxed);
     if (occ < 0) {
-      GM_CUDA(cudaFuncSetAttribute(batch_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, batch_hash_kernel, kBatchHashWarps * 32, smem));
       if (occ < 1) occ = 1;
+      occ_cache.store(occ, std::memory_order_relaxed);
     }
     int grid = int(std::min<int64_t>((npairs + kBatchHashWarps - 1) / kBatchHashWarps, int64_t(occ) * sms));
     batch_hash_kernel<<<grid, kBatchHashWarps * 32, smem, s>>>(pool, a_off, a_len, b_off, b_len, npairs, out);

@@ -24,6 +24,7 @@
 namespace gm {
 
 int run_kclique_list_filtered(gm_graph *g, int k, vidType min_src_degree, int *launches, cudaStream_t stream);
+int reserve_kclique_list_scratch(gm_graph *g, int k);
 
 template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS>
 struct CliqueCfg {
@@ -94,14 +95,14 @@ __device__ __forceinline__ uint32_t count_level(Words<SMP> Mp, int W, Words<SMM>
 
 // cliques whose second vertex is local row i (warp-collective; masks = this warp's level buffers)
 template <bool SMM, bool TRI>
-__device__ __forceinline__ uint32_t count_row(int k, int i, int W, Words<SMM> M, int stride,
-                                              uint32_t *masks, int wmax, int lane) {
+__device__ __forceinline__ AccType count_row(int k, int i, int W, Words<SMM> M, int stride,
+                                             uint32_t *masks, int wmax, int lane) {
   const Words<SMM> Ai = M.row(size_t(i) * stride);
   if (k == 4) return count_level<SMM, SMM, TRI>(Ai, W, M, stride, lane);
   const int depth = k - 4;                 // serially chosen vertices below row i
   // level 0 reads the matrix row, deeper levels read this warp's masks (always shared memory)
   int wi[6]; uint32_t word[6];
-  uint32_t c = 0;
+  AccType c = 0;                           // a whole sub-tree per lane: exceeds 2^32 for k >= 6 on dense neighbourhoods
   int t = 0;
   wi[0] = 0; word[0] = Ai[0];
   auto cur_word = [&](int lvl, int w) -> uint32_t { return lvl == 0 ? Ai[w] : masks[(lvl - 1) * wmax + w]; };
@@ -229,8 +230,8 @@ kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int
     }
     cl_sync<GT>();
 
-    // 3. count with AND + POPC
-    uint32_t c = 0;
+    // 3. count with AND + POPC (64-bit per lane: one root of degree ~2048 can hold > 2^32 cliques per lane)
+    AccType c = 0;
     const bool in_smem = d <= SMEM_MAXD;                     // group-uniform
     auto rows = [&](auto Mw) {
       if (GT == 32) {
@@ -255,7 +256,7 @@ kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int
 }
 
 template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS, bool TRI>
-static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream, int *launches) {
+static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream, int *launches, bool reserve_only = false) {
   const ItemList &il = g->items[TRI ? 4 : 2][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>;
@@ -279,6 +280,7 @@ static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream,
     }
     gmat = g->d_gmat;
   }
+  if (reserve_only) return GM_OK;          // slabs sized on the main stream ahead of fork_streams()
   GraphGPU view = g->view(0);
   if (TRI) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; }     // rank-relabelled rows
   kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, k, il.d_items, il.n, g->d_ticket + 4 + cls, gmat, g->d_counts);
@@ -305,6 +307,9 @@ int prepare_kclique_bitmap(gm_graph *g) {
 
 template <bool TRI>
 static int run_bitmap_classes(gm_graph *g, int k, int *launches) {
+  if (g->items[TRI ? 4 : 2][3].n > 0) GM_TRY(reserve_kclique_list_scratch(g, k));   // before the fork: the side stream must see it
+  if (k == 4) GM_TRY((launch_clique_class<1024, 13, 64, 2048, 1024, 0, TRI>(g, k, 2, g->stream, launches, true)));
+  else GM_TRY((launch_clique_class<512, 13, 64, 2048, 1024, 4, TRI>(g, k, 2, g->stream, launches, true)));
   GM_TRY(fork_streams(g));
   if (k == 4) {           // no per-warp mask levels needed: the big class affords 1024 threads
     if (options().clique_gt1 == 512) GM_TRY((launch_clique_class<512, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));

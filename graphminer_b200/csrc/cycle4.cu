@@ -445,8 +445,8 @@ static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launch
     (*launches)++;
   }
   if (c->c4_ncta > 0) {
-    static bool attr_set = false;
-    if (!attr_set) { GM_CUDA(cudaFuncSetAttribute(c4_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem)); attr_set = true; }
+    // per-device function attribute: set on every launch (one host thread per device in gm_motif_host)
+    GM_CUDA(cudaFuncSetAttribute(c4_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem));
     int grid = int(std::min<int64_t>(c->c4_ncta, int64_t(c->num_sms)));
     c4_cta_kernel<<<grid, kC4MidThreads, kC4CtaSmem, g->stream>>>(c->c4_cta, c->c4_ncta, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
                                                                   g->d_ticket + 2, total);

@@ -66,7 +66,8 @@ void trace_phase(cudaStream_t s, const char *name);   // batch.cu: "batch.g2048"
 // The opaque handle of the C ABI.
 struct gm_graph {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;         // where the solvers launch: res_stream, or the caller's (gm_graph_set_stream)
+  cudaStream_t res_stream = nullptr;     // the handle's own stream (recycled per device, graph.cu)
   bool own_stream = false;
   bool own_csr = false;
   gm::vidType nv = 0;

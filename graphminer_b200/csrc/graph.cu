@@ -48,6 +48,14 @@ __global__ void k_degree(vidType nv, const eidType *rowptr, uint32_t *units, vid
   }
 }
 
+__global__ void k_max_degree(vidType nv, const eidType *rowptr, vidType *maxdeg) {
+  vidType v = blockIdx.x * blockDim.x + threadIdx.x;
+  vidType d = v < nv ? vidType(rowptr[v + 1] - rowptr[v]) : 0;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(kFullMask, d, o));
+  if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(maxdeg, d);
+}
+
 __global__ void k_make_vinfo(vidType nv, const eidType *rowptr, const uint32_t *off_units, uint2 *vinfo) {
   vidType v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < nv) vinfo[v] = make_uint2(off_units[v], uint32_t(rowptr[v + 1] - rowptr[v]));
@@ -382,41 +390,101 @@ static DeviceInfo &device_info(int dev) {
   return d;
 }
 
-static int init_stream(gm_graph *g) {
-  GM_CUDA(cudaSetDevice(g->device));
-  device_info(g->device);
-  GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-  g->own_stream = true;
-  return GM_OK;
+// Streams, events and the pinned result words of a handle are recycled per device: creating them costs
+// several driver calls and cudaMallocHost / cudaFreeHost synchronise the whole device, which showed up in
+// every end-to-end gm_*_host call (one handle per call).
+struct HandleRes {
+  cudaStream_t stream = nullptr, side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  unsigned long long *h_counts = nullptr;
+};
+static std::mutex g_res_mu;
+static std::vector<HandleRes> g_res_cache[64];
+constexpr size_t kResCacheMax = 4;
+
+static void destroy_res(HandleRes &r) {
+  if (r.h_counts) cudaFreeHost(r.h_counts);
+  if (r.ev0) cudaEventDestroy(r.ev0);
+  if (r.ev1) cudaEventDestroy(r.ev1);
+  if (r.fork_ev) cudaEventDestroy(r.fork_ev);
+  for (int i = 0; i < 3; i++) { if (r.side[i]) cudaStreamDestroy(r.side[i]); if (r.join_ev[i]) cudaEventDestroy(r.join_ev[i]); }
+  if (r.stream) cudaStreamDestroy(r.stream);
+  r = HandleRes();
 }
 
-static int init_common(gm_graph *g) {
+static int acquire_res(gm_graph *g) {
   GM_CUDA(cudaSetDevice(g->device));
-  GM_CUDA(dmalloc(g, &g->d_counts, 8 * sizeof(unsigned long long)));
-  GM_CUDA(dmalloc(g, &g->d_ticket, 8 * sizeof(int)));
-  GM_CUDA(cudaMallocHost(&g->h_counts, 8 * sizeof(unsigned long long)));
-  GM_CUDA(cudaEventCreate(&g->ev0));
-  GM_CUDA(cudaEventCreate(&g->ev1));
-  GM_CUDA(cudaEventCreateWithFlags(&g->fork_ev, cudaEventDisableTiming));
-  for (int i = 0; i < 3; i++) {
-    GM_CUDA(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
-    GM_CUDA(cudaEventCreateWithFlags(&g->join_ev[i], cudaEventDisableTiming));
-  }
   const DeviceInfo &di = device_info(g->device);
   g->num_sms = di.sms;
   g->smem_optin = di.smem_optin;
+  HandleRes r;
+  bool cached = false;
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    auto &c = g_res_cache[g->device & 63];
+    if (!c.empty()) { r = c.back(); c.pop_back(); cached = true; }
+  }
+  if (!cached) {
+    int rc = [&]() -> int {
+      GM_CUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+      GM_CUDA(cudaMallocHost(&r.h_counts, 8 * sizeof(unsigned long long)));
+      GM_CUDA(cudaEventCreate(&r.ev0));
+      GM_CUDA(cudaEventCreate(&r.ev1));
+      GM_CUDA(cudaEventCreateWithFlags(&r.fork_ev, cudaEventDisableTiming));
+      for (int i = 0; i < 3; i++) {
+        GM_CUDA(cudaStreamCreateWithFlags(&r.side[i], cudaStreamNonBlocking));
+        GM_CUDA(cudaEventCreateWithFlags(&r.join_ev[i], cudaEventDisableTiming));
+      }
+      return GM_OK;
+    }();
+    if (rc != GM_OK) { destroy_res(r); return rc; }
+  }
+  g->res_stream = r.stream; g->stream = r.stream; g->own_stream = true;
+  g->h_counts = r.h_counts; g->ev0 = r.ev0; g->ev1 = r.ev1; g->fork_ev = r.fork_ev;
+  for (int i = 0; i < 3; i++) { g->side[i] = r.side[i]; g->join_ev[i] = r.join_ev[i]; }
+  return GM_OK;
+}
+
+static void release_res(gm_graph *g) {
+  HandleRes r;
+  r.stream = g->res_stream; r.h_counts = g->h_counts; r.ev0 = g->ev0; r.ev1 = g->ev1; r.fork_ev = g->fork_ev;
+  for (int i = 0; i < 3; i++) { r.side[i] = g->side[i]; r.join_ev[i] = g->join_ev[i]; }
+  g->res_stream = g->stream = nullptr; g->h_counts = nullptr; g->ev0 = g->ev1 = g->fork_ev = nullptr;
+  for (int i = 0; i < 3; i++) { g->side[i] = nullptr; g->join_ev[i] = nullptr; }
+  if (!r.stream) { destroy_res(r); return; }
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    auto &c = g_res_cache[g->device & 63];
+    if (c.size() < kResCacheMax) { c.push_back(r); return; }
+  }
+  destroy_res(r);
+}
+
+// device-side part of the handle set-up; queues the max-degree reduction WITHOUT synchronising
+static int init_common(gm_graph *g, vidType **d_md_out) {
+  GM_CUDA(cudaSetDevice(g->device));
+  GM_CUDA(dmalloc(g, &g->d_counts, 8 * sizeof(unsigned long long)));
+  GM_CUDA(dmalloc(g, &g->d_ticket, 8 * sizeof(int)));
   g->src_begin = 0; g->src_end = g->nv;
-  if (g->max_degree <= 0 && g->nv > 0) {
-    vidType *d_md = nullptr; uint32_t *units = nullptr;
+  // the true maximum degree is always computed (one cheap launch): a caller value that is too small (a stale
+  // meta.txt) would under-size the per-warp frontiers of the list kernels (patterns.cu)
+  *d_md_out = nullptr;
+  if (g->nv > 0) {
+    vidType *d_md = nullptr;
     GM_CUDA(dmalloc(g, &d_md, sizeof(vidType)));
-    GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * size_t(g->nv)));
     GM_CUDA(cudaMemsetAsync(d_md, 0, sizeof(vidType), g->stream));
-    k_degree<<<nblk(g->nv), 256, 0, g->stream>>>(g->nv, g->d_rowptr, units, d_md);
-    GM_CUDA(cudaMemcpyAsync(&g->max_degree, d_md, sizeof(vidType), cudaMemcpyDeviceToHost, g->stream));
-    GM_CUDA(cudaStreamSynchronize(g->stream));
-    dfree(g, d_md); dfree(g, units);
+    k_max_degree<<<nblk(g->nv), 256, 0, g->stream>>>(g->nv, g->d_rowptr, d_md);
+    GM_CUDA(cudaMemcpyAsync(reinterpret_cast<vidType *>(g->h_counts), d_md, sizeof(vidType), cudaMemcpyDeviceToHost, g->stream));
+    *d_md_out = d_md;
   }
   return GM_OK;
+}
+// after the stream has been synchronised
+static void finish_common(gm_graph *g, vidType *d_md) {
+  if (!d_md) return;
+  const vidType computed = *reinterpret_cast<vidType *>(g->h_counts);
+  if (computed > g->max_degree) g->max_degree = computed;
+  dfree(g, d_md);
 }
 
 }  // namespace gm
@@ -500,7 +568,7 @@ int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, in
   gm_graph *g = new gm_graph();
   g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
   int r = [&]() -> int {
-    GM_TRY(init_stream(g));
+    GM_TRY(acquire_res(g));
     GM_CUDA(dmalloc(g, &g->d_rowptr, sizeof(eidType) * (size_t(nv) + 1)));
     GM_CUDA(dmalloc(g, &g->d_colidx, sizeof(vidType) * size_t(ne > 0 ? ne : 1)));
     // stream-ordered copies: with pinned host arrays the call returns while the DMA runs and the
@@ -508,8 +576,10 @@ int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, in
     // synchronisation at the end of this function
     GM_CUDA(cudaMemcpyAsync(g->d_rowptr, rowptr, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyHostToDevice, g->stream));
     if (ne > 0) GM_CUDA(cudaMemcpyAsync(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice, g->stream));
-    GM_TRY(init_common(g));
+    vidType *d_md = nullptr;
+    GM_TRY(init_common(g, &d_md));
     GM_CUDA(cudaStreamSynchronize(g->stream));
+    finish_common(g, d_md);
     trace_phase(g->stream, "upload (H2D CSR)");
     return GM_OK;
   }();
@@ -527,8 +597,14 @@ int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv,
   g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = false;
   g->d_rowptr = const_cast<eidType *>(d_rowptr);
   g->d_colidx = const_cast<vidType *>(d_colidx);
-  int r = init_stream(g);
-  if (r == GM_OK) r = init_common(g);
+  int r = [&]() -> int {
+    GM_TRY(acquire_res(g));
+    vidType *d_md = nullptr;
+    GM_TRY(init_common(g, &d_md));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    finish_common(g, d_md);
+    return GM_OK;
+  }();
   if (r != GM_OK) { gm_graph_free(g); return r; }
   *out = g;
   return GM_OK;
@@ -548,12 +624,9 @@ int gm_graph_free(gm_graph_t *g) {
   // complete the stream-ordered frees now: the blocks return to the pool free of stream dependencies, so
   // the next handle (usually on another stream) reuses them instead of growing the pool
   if (g->stream) cudaStreamSynchronize(g->stream);
-  if (g->h_counts) cudaFreeHost(g->h_counts);
-  if (g->ev0) cudaEventDestroy(g->ev0);
-  if (g->ev1) cudaEventDestroy(g->ev1);
-  if (g->fork_ev) cudaEventDestroy(g->fork_ev);
-  for (int i = 0; i < 3; i++) { if (g->side[i]) cudaStreamDestroy(g->side[i]); if (g->join_ev[i]) cudaEventDestroy(g->join_ev[i]); }
-  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  if (g->res_stream && g->res_stream != g->stream) cudaStreamSynchronize(g->res_stream);
+  for (int i = 0; i < 3; i++) if (g->side[i]) cudaStreamSynchronize(g->side[i]);
+  release_res(g);
   cudaGetLastError();
   delete g;
   return GM_OK;
@@ -563,9 +636,9 @@ int gm_graph_set_stream(gm_graph_t *g, void *cuda_stream) {
   if (!g) { set_error("null graph"); return GM_EINVAL; }
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  // the handle's own stream (res_stream) stays with the handle and goes back to the per-device cache on free
   if (cuda_stream) { g->stream = static_cast<cudaStream_t>(cuda_stream); g->own_stream = false; }
-  else { GM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)); g->own_stream = true; }
+  else { g->stream = g->res_stream; g->own_stream = true; }
   if (g->dag_child) GM_TRY(gm_graph_set_stream(g->dag_child, g->stream));
   return GM_OK;
 }

@@ -320,6 +320,16 @@ int run_kclique_list_filtered(gm_graph *g, int k, vidType min_src_degree, int *l
   return GM_OK;
 }
 
+// sizes the per-warp frontier on the graph's main stream, so that a launch from a forked side stream finds
+// the allocation already stream-ordered before the fork event
+int reserve_kclique_list_scratch(gm_graph *g, int k) {
+  GM_TRY(ensure_coo(g, 0));
+  if (g->nnz[0] == 0) return GM_OK;
+  int grid; vidType *scratch;
+  int64_t md = std::max<int64_t>(g->max_degree, 1);
+  return pattern_grid(g, (const void *)kclique_warp_edge, g->nnz[0], k > 3 ? md * (k - 3) : 0, &grid, &scratch);
+}
+
 int run_kclique_list(gm_graph *g, int k, int *launches) {
   return run_kclique_list_filtered(g, k, -1, launches, g->stream);
 }

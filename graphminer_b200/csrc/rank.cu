@@ -9,16 +9,22 @@
 //      sum_a C(d+(a), 2)
 // elements instead of sum_a d+(a)^2 -- half the probes, same exact count (triangle counts are
 // invariant under renaming).  Built entirely on the device:
-//   1. key(v) = (in+out degree, v)  -> radix sort -> rank[v]
-//   2. edge keys (rank[u] << 32 | rank[v]) -> radix sort  (rows by new id, each row ascending)
-//   3. aligned rows (16-byte aligned, padded with kVidMax) + per new root b the partner records
-//      {element offset of the suffix of row a after b, its length} for every edge a -> b whose source
-//      lies in the handle's source range and whose suffix is non-empty.
+//   1. in-degrees (atomics), key(v) = in+out degree -> stable 32-bit radix sort of (key, v) -> rank[v]
+//      (ties keep the id order, i.e. the (degree, id) order);
+//   2. every row is gathered through rank[], SORTED IN PLACE BY ITS OWN THREAD GROUP (bitonic network:
+//      in registers for d <= 32, in shared memory per warp up to 256 and per CTA up to 4096; the few longer
+//      rows go through one segmented radix sort) and written to its 16-byte aligned slot, padded with
+//      kVidMax.  Round 1 sorted all |E| 64-bit (source, destination) keys globally instead: 5.8 of the
+//      10.4 ms of preparation on R-MAT scale 22, and two 8|E|-byte temporaries;
+//   3. per new root b the partner records {element offset of the suffix of row a after b, its length}
+//      for every edge a -> b whose source (or, with tc.shard=dest, destination) lies in the handle's source
+//      range and whose suffix is non-empty.
 // If some edge does not go upwards in the recovered order (the input was not produced by the
 // reference's orientation) rk_valid stays false and gm_tc falls back to the unranked kernel.
 #include "gm_internal.cuh"
 
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace gm {
 
@@ -30,65 +36,190 @@ __global__ void k_indeg_all(vidType nv, const eidType *rowptr, const vidType *co
   if (v >= nv) return;
   for (eidType i = rowptr[v] + sub; i < rowptr[v + 1]; i += 8) atomicAdd(&indeg[colidx[i]], 1u);
 }
-__global__ void k_vertex_keys(vidType nv, const eidType *rowptr, const unsigned *indeg, unsigned long long *keys) {
+__global__ void k_vertex_keys(vidType nv, const eidType *rowptr, const unsigned *indeg, unsigned *keys, vidType *ids) {
   vidType v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  unsigned long long d = (unsigned long long)(rowptr[v + 1] - rowptr[v]) + indeg[v];
-  keys[v] = (d << 32) | (unsigned)v;
+  keys[v] = unsigned(rowptr[v + 1] - rowptr[v]) + indeg[v];
+  ids[v] = v;
 }
-// sorted vertex keys -> rank[orig] = position, orig_of[position] = orig, new degree / aligned units
-__global__ void k_assign_rank(vidType nv, const unsigned long long *sorted, const eidType *rowptr,
-                              vidType *rank, vidType *orig_of, eidType *ndeg, uint32_t *units) {
+// sorted vertex ids -> rank[orig] = position, new degree / aligned units
+__global__ void k_assign_rank(vidType nv, const vidType *orig_of, const eidType *rowptr,
+                              vidType *rank, eidType *ndeg, uint32_t *units) {
   vidType i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nv) return;
-  vidType v = vidType(sorted[i] & 0xffffffffull);
-  rank[v] = i; orig_of[i] = v;
+  vidType v = orig_of[i];
+  rank[v] = i;
   eidType d = rowptr[v + 1] - rowptr[v];
   ndeg[i] = d; units[i] = (uint32_t(d) + 3u) >> 2;
-}
-__global__ void k_edge_keys(vidType nv, const eidType *rowptr, const vidType *colidx, const vidType *rank,
-                            unsigned long long *keys) {
-  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  vidType v = vidType(t >> 3); int sub = int(t & 7);
-  if (v >= nv) return;
-  unsigned long long hi = (unsigned long long)(unsigned)rank[v] << 32;
-  for (eidType i = rowptr[v] + sub; i < rowptr[v + 1]; i += 8) keys[i] = hi | (unsigned)rank[colidx[i]];
-}
-__global__ void k_fill_u32(int64_t n, vidType *p, vidType val) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = val;
 }
 __global__ void k_ranked_vinfo(vidType nv, const eidType *nrow, const uint32_t *off_units, uint2 *vinfo) {
   vidType v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < nv) vinfo[v] = make_uint2(off_units[v], uint32_t(nrow[v + 1] - nrow[v]));
 }
-// PASS 0: write the aligned rows, check upward orientation, count partner records per new root.
-// PASS 1: write the partner records.
-template <int PASS>
-__global__ void k_ranked_edges(eidType ne, const unsigned long long *ekeys, const eidType *nrow, const uint2 *vinfo,
-                               const vidType *orig_of, vidType src_begin, vidType src_end, int by_dest,
-                               vidType *acol, unsigned long long *cnt, const eidType *prow, uint2 *prec, int *bad) {
-  eidType e = eidType(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  unsigned long long k = ekeys[e];
-  vidType a = vidType(k >> 32), b = vidType(k & 0xffffffffull);
-  uint2 va = vinfo[a];
-  uint32_t i = uint32_t(e - nrow[a]);
-  uint32_t rem = va.y - i - 1;
-  if (PASS == 0) {
-    acol[(size_t(va.x) << 2) + i] = b;
-    if (b <= a) atomicOr(bad, 1);
+
+// ---- per-row sorting ----------------------------------------------------------------------------------
+constexpr int kMidMax = 256;      // warp per row, bitonic network in shared memory
+constexpr int kBigMax = 4096;     // CTA per row
+struct RowCtx {
+  vidType nv;
+  const eidType *rowptr; const vidType *colidx;      // input DAG (original ids)
+  const vidType *rank, *orig_of;
+  const uint2 *vinfo;                                // aligned slots of the relabelled rows
+  vidType *acol;
+  unsigned *cnt;                                     // partner records per new root
+  vidType src_begin, src_end; int by_dest, full_range;
+  int *bad;
+  vidType *lists;                                    // [0, cap): mid rows, [cap, 2cap): big rows, [2cap, 3cap): huge rows
+  unsigned *nlist;                                   // their lengths
+  int64_t cap;
+};
+
+// lanes of one row agree on `keep_src`; a record is owned by the shard of its source or destination
+__device__ __forceinline__ bool rec_kept(const RowCtx &c, bool keep_src, vidType b) {
+  if (c.full_range) return true;
+  if (!c.by_dest) return keep_src;
+  const vidType ob = c.orig_of[b];
+  return ob >= c.src_begin && ob < c.src_end;
+}
+
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ uint32_t warp_sort32(uint32_t x, int lane) {
+  #pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+    #pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint32_t y = __shfl_xor_sync(kFullMask, x, j);
+      const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+      x = take_min ? min(x, y) : max(x, y);
+    }
   }
-  // the shard owns the edges whose source (reference semantics, triangle/multigpu.cu:73-75) or -- with
-  // tc.shard=dest -- whose destination lies in the range; the latter keeps every root (= destination)
-  // and its shared-memory table on exactly one shard
-  vidType oa = orig_of[by_dest ? b : a];
-  if (rem == 0 || oa < src_begin || oa >= src_end) return;
-  if (PASS == 0) {
-    atomicAdd(&cnt[b], 1ull);
-  } else {
-    unsigned long long p = atomicAdd(&cnt[b], 1ull);
-    prec[prow[b] + eidType(p)] = make_uint2((va.x << 2) + i + 1, rem);
+  return x;
+}
+
+// bitonic sort of s[0..P) (P a power of two) by a group of GT threads
+template <int GT>
+__device__ __forceinline__ void group_sort(uint32_t *s, int P, int tid) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += GT) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+        const uint32_t a = s[i], b = s[p];
+        if ((a > b) == ((i & k) == 0)) { s[i] = b; s[p] = a; }
+      }
+      if (GT == 32) __syncwarp(); else __syncthreads();
+    }
+  }
+}
+
+// warp per new vertex: rows of up to 32 entries are finished here, longer ones queued by size class
+__global__ void __launch_bounds__(256)
+k_rows_small(RowCtx c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i < c.nv; i += nw) {
+    const uint2 vi = c.vinfo[i];
+    const int d = int(vi.y);
+    if (d == 0) continue;
+    if (d > 32) {
+      if (lane == 0) {
+        const int cls = d <= kMidMax ? 0 : d <= kBigMax ? 1 : 2;
+        c.lists[cls * c.cap + atomicAdd(&c.nlist[cls], 1u)] = vidType(i);
+      }
+      continue;
+    }
+    const vidType v = c.orig_of[i];
+    const vidType *row = c.colidx + c.rowptr[v];
+    uint32_t x = lane < d ? uint32_t(c.rank[__ldg(row + lane)]) : uint32_t(kVidMax);
+    x = warp_sort32(x, lane);
+    const int padded = (d + 3) & ~3;
+    if (lane < padded) c.acol[(size_t(vi.x) << 2) + lane] = vidType(x);
+    if (lane < d && vidType(x) <= vidType(i)) atomicOr(c.bad, 1);
+    const bool keep_src = v >= c.src_begin && v < c.src_end;
+    if (lane < d - 1 && rec_kept(c, keep_src, vidType(x))) atomicAdd(&c.cnt[x], 1u);
+  }
+}
+
+// GT threads per row, the row in shared memory (P = next power of two of d, padded with kVidMax)
+template <int GT, int MAXD, int CLS>
+__global__ void __launch_bounds__(256)
+k_rows_group(RowCtx c) {
+  constexpr int kGroups = 256 / GT;
+  __shared__ uint32_t smem[kGroups * MAXD];
+  const int tid = threadIdx.x % GT, grp = threadIdx.x / GT;
+  uint32_t *s = smem + grp * MAXD;
+  const int64_t n = int64_t(c.nlist[CLS]);
+  for (int64_t q = int64_t(blockIdx.x) * kGroups + grp; q < n; q += int64_t(gridDim.x) * kGroups) {
+    const vidType i = c.lists[CLS * c.cap + q];
+    const uint2 vi = c.vinfo[i];
+    const int d = int(vi.y);
+    int P = 64; while (P < d) P <<= 1;
+    const vidType v = c.orig_of[i];
+    const vidType *row = c.colidx + c.rowptr[v];
+    for (int t = tid; t < P; t += GT) s[t] = t < d ? uint32_t(c.rank[__ldg(row + t)]) : uint32_t(kVidMax);
+    if (GT == 32) __syncwarp(); else __syncthreads();
+    group_sort<GT>(s, P, tid);
+    const int padded = (d + 3) & ~3;
+    vidType *dst = c.acol + (size_t(vi.x) << 2);
+    const bool keep_src = v >= c.src_begin && v < c.src_end;
+    for (int t = tid; t < padded; t += GT) {
+      const uint32_t x = s[t];                        // s[d..P) holds kVidMax: exactly the padding value
+      dst[t] = vidType(x);
+      if (t < d && vidType(x) <= i) atomicOr(c.bad, 1);
+      if (t < d - 1 && rec_kept(c, keep_src, vidType(x))) atomicAdd(&c.cnt[x], 1u);
+    }
+    if (GT == 32) __syncwarp(); else __syncthreads();
+  }
+}
+
+// rows beyond kBigMax: gather + pad now, sort with one segmented radix sort, count afterwards
+__global__ void __launch_bounds__(256)
+k_rows_huge_gather(RowCtx c, eidType *seg_begin, eidType *seg_end) {
+  const int64_t n = int64_t(c.nlist[2]);
+  for (int64_t q = blockIdx.x; q < n; q += gridDim.x) {
+    const vidType i = c.lists[2 * c.cap + q];
+    const uint2 vi = c.vinfo[i];
+    const int d = int(vi.y), padded = (d + 3) & ~3;
+    const vidType *row = c.colidx + c.rowptr[c.orig_of[i]];
+    vidType *dst = c.acol + (size_t(vi.x) << 2);
+    for (int t = threadIdx.x; t < padded; t += blockDim.x) dst[t] = t < d ? c.rank[__ldg(row + t)] : kVidMax;
+    if (threadIdx.x == 0) { seg_begin[q] = eidType(size_t(vi.x) << 2); seg_end[q] = eidType(size_t(vi.x) << 2) + d; }
+  }
+}
+__global__ void __launch_bounds__(256)
+k_rows_huge_finish(RowCtx c, const vidType *sorted) {
+  const int64_t n = int64_t(c.nlist[2]);
+  for (int64_t q = blockIdx.x; q < n; q += gridDim.x) {
+    const vidType i = c.lists[2 * c.cap + q];
+    const uint2 vi = c.vinfo[i];
+    const int d = int(vi.y);
+    const vidType v = c.orig_of[i];
+    const size_t base = size_t(vi.x) << 2;
+    const bool keep_src = v >= c.src_begin && v < c.src_end;
+    for (int t = threadIdx.x; t < d; t += blockDim.x) {
+      const vidType x = sorted[base + t];
+      c.acol[base + t] = x;
+      if (x <= i) atomicOr(c.bad, 1);
+      if (t < d - 1 && rec_kept(c, keep_src, x)) atomicAdd(&c.cnt[x], 1u);
+    }
+  }
+}
+
+// partner records: 8 lanes per sorted row
+__global__ void __launch_bounds__(256)
+k_partner_fill(RowCtx c, const eidType *prow, unsigned *cursor, uint2 *prec) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType a = vidType(t >> 3); const int sub = int(t & 7);
+  if (a >= c.nv) return;
+  const uint2 vi = c.vinfo[a];
+  const uint32_t d = vi.y, base = vi.x << 2;
+  if (d < 2) return;
+  const vidType v = c.orig_of[a];
+  const bool keep_src = v >= c.src_begin && v < c.src_end;
+  for (uint32_t i = sub; i + 1 < d; i += 8) {
+    const vidType b = c.acol[size_t(base) + i];
+    if (!rec_kept(c, keep_src, b)) continue;
+    const unsigned p = atomicAdd(&cursor[b], 1u);
+    prec[prow[b] + eidType(p)] = make_uint2(base + i + 1, d - i - 1);
   }
 }
 
@@ -101,12 +232,9 @@ static int scan_inplace(gm_graph *g, T *d, int64_t n) {   // n+1 slots
   return GM_OK;
 }
 
-static int sort_keys(gm_graph *g, unsigned long long *in, unsigned long long *out, int64_t n, int end_bit) {
-  size_t tmp = 0;
-  GM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, in, out, n, 0, end_bit, g->stream));
-  GM_TRY(ensure_scratch(g, tmp));
-  GM_CUDA(cub::DeviceRadixSort::SortKeys(g->d_scratch, tmp, in, out, n, 0, end_bit, g->stream));
-  return GM_OK;
+__global__ void k_widen(int64_t n, const unsigned *in, eidType *out) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = eidType(in[i]);
 }
 
 static int bits_of(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b < 1 ? 1 : b; }
@@ -117,75 +245,98 @@ int ensure_ranked(gm_graph *g) {
   const vidType nv = g->nv; const eidType ne = g->ne;
   g->rk_valid = false;
   if (nv == 0 || ne == 0 || ne >= (eidType(1) << 31) * 2) { g->rk_ready = true; return GM_OK; }
+  if ((uint64_t(ne) + 3ull * uint64_t(nv)) >= (1ull << 32)) { g->rk_ready = true; return GM_OK; }   // element offsets must fit 32 bits
 
-  unsigned *indeg = nullptr; unsigned long long *vk0 = nullptr, *vk1 = nullptr, *ek0 = nullptr, *ek1 = nullptr, *cnt = nullptr;
-  vidType *rank = nullptr, *orig_of = nullptr; uint32_t *units = nullptr; int *bad = nullptr;
+  unsigned *indeg = nullptr, *k0 = nullptr, *k1 = nullptr, *cnt = nullptr, *nlist = nullptr;
+  vidType *id0 = nullptr, *rank = nullptr, *orig_of = nullptr, *lists = nullptr, *huge_tmp = nullptr;
+  uint32_t *units = nullptr; int *bad = nullptr; eidType *seg = nullptr;
   auto cleanup = [&]() {
-    dfree(g, indeg); dfree(g, vk0); dfree(g, vk1); dfree(g, ek0); dfree(g, ek1); dfree(g, cnt);
-    dfree(g, rank); dfree(g, units); dfree(g, bad);
+    dfree(g, indeg); dfree(g, k0); dfree(g, k1); dfree(g, cnt); dfree(g, nlist); dfree(g, id0);
+    dfree(g, rank); dfree(g, lists); dfree(g, huge_tmp); dfree(g, units); dfree(g, bad); dfree(g, seg);
   };
   int rc = [&]() -> int {
-    GM_CUDA(dmalloc(g, &indeg, sizeof(unsigned) * size_t(nv)));
-    GM_CUDA(dmalloc(g, &vk0, sizeof(unsigned long long) * size_t(nv)));
-    GM_CUDA(dmalloc(g, &vk1, sizeof(unsigned long long) * size_t(nv)));
-    GM_CUDA(dmalloc(g, &rank, sizeof(vidType) * size_t(nv)));
-    GM_CUDA(dmalloc(g, &orig_of, sizeof(vidType) * size_t(nv)));
-    GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * (size_t(nv) + 1)));
-    GM_CUDA(dmalloc(g, &g->rk_nrow, sizeof(eidType) * (size_t(nv) + 1)));
+    const size_t nv1 = size_t(nv) + 1;
+    GM_CUDA(dmalloc(g, &indeg, sizeof(unsigned) * nv1));
+    GM_CUDA(dmalloc(g, &k0, sizeof(unsigned) * nv1));
+    GM_CUDA(dmalloc(g, &k1, sizeof(unsigned) * nv1));
+    GM_CUDA(dmalloc(g, &id0, sizeof(vidType) * nv1));
+    GM_CUDA(dmalloc(g, &rank, sizeof(vidType) * nv1));
+    GM_CUDA(dmalloc(g, &orig_of, sizeof(vidType) * nv1));
+    GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * nv1));
+    GM_CUDA(dmalloc(g, &g->rk_nrow, sizeof(eidType) * nv1));
     GM_CUDA(dmalloc(g, &bad, sizeof(int)));
-    GM_CUDA(cudaMemsetAsync(indeg, 0, sizeof(unsigned) * size_t(nv), g->stream));
+    GM_CUDA(dmalloc(g, &nlist, sizeof(unsigned) * 4));
+    GM_CUDA(cudaMemsetAsync(indeg, 0, sizeof(unsigned) * nv1, g->stream));
     GM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), g->stream));
-    GM_CUDA(cudaMemsetAsync(units, 0, sizeof(uint32_t) * (size_t(nv) + 1), g->stream));
-    GM_CUDA(cudaMemsetAsync(g->rk_nrow, 0, sizeof(eidType) * (size_t(nv) + 1), g->stream));
-    // 1. rank
+    GM_CUDA(cudaMemsetAsync(nlist, 0, sizeof(unsigned) * 4, g->stream));
+    GM_CUDA(cudaMemsetAsync(units + nv, 0, sizeof(uint32_t), g->stream));
+    GM_CUDA(cudaMemsetAsync(g->rk_nrow + nv, 0, sizeof(eidType), g->stream));
+    // 1. rank = position in the stable sort by total degree
     k_indeg_all<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, indeg);
-    k_vertex_keys<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, indeg, vk0);
-    GM_TRY(sort_keys(g, vk0, vk1, nv, 64));
-    k_assign_rank<<<nblk(nv), 256, 0, g->stream>>>(nv, vk1, g->d_rowptr, rank, orig_of, g->rk_nrow, units);
+    k_vertex_keys<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, indeg, k0, id0);
+    {
+      size_t tmp = 0;
+      const int end_bit = bits_of(uint64_t(nv));              // a degree is below nv
+      GM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, id0, orig_of, int64_t(nv), 0, end_bit, g->stream));
+      GM_TRY(ensure_scratch(g, tmp));
+      GM_CUDA(cub::DeviceRadixSort::SortPairs(g->d_scratch, tmp, k0, k1, id0, orig_of, int64_t(nv), 0, end_bit, g->stream));
+    }
+    k_assign_rank<<<nblk(nv), 256, 0, g->stream>>>(nv, orig_of, g->d_rowptr, rank, g->rk_nrow, units);
     GM_TRY(scan_inplace(g, g->rk_nrow, nv));
     GM_TRY(scan_inplace(g, units, nv));
     uint32_t total_units = 0;
     GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
     trace_phase(g->stream, "rank: vertex order");
-    GM_CUDA(dfree(g, vk0)); vk0 = nullptr; GM_CUDA(dfree(g, vk1)); vk1 = nullptr; GM_CUDA(dfree(g, indeg)); indeg = nullptr;
-    if ((uint64_t(ne) + 3ull * uint64_t(nv)) >= (1ull << 32)) return GM_OK;      // element offsets must fit 32 bits
-    // 2. edges by (new source, new destination)
-    GM_CUDA(dmalloc(g, &ek0, sizeof(unsigned long long) * size_t(ne)));
-    GM_CUDA(dmalloc(g, &ek1, sizeof(unsigned long long) * size_t(ne)));
-    k_edge_keys<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, rank, ek0);
-    GM_TRY(sort_keys(g, ek0, ek1, ne, 32 + bits_of(uint64_t(nv))));
-    GM_CUDA(cudaStreamSynchronize(g->stream));
-    trace_phase(g->stream, "rank: edge sort");
-    GM_CUDA(dfree(g, ek0)); ek0 = nullptr;
-    // 3. aligned rows + partner records
+    // 2. relabelled, sorted, aligned rows + partner counts
     const int64_t acol_len = int64_t(total_units) * 4;
     g->rk_acol_len = acol_len;
+    const int64_t cap = std::min<int64_t>(int64_t(nv), ne / 33 + 1);      // rows with more than 32 entries
     GM_CUDA(dmalloc(g, &g->rk_vinfo, sizeof(uint2) * size_t(nv)));
     GM_CUDA(dmalloc(g, &g->rk_acol, sizeof(vidType) * size_t(acol_len > 0 ? acol_len : 4)));
-    GM_CUDA(dmalloc(g, &cnt, sizeof(unsigned long long) * (size_t(nv) + 1)));
-    GM_CUDA(dmalloc(g, &g->rk_prow, sizeof(eidType) * (size_t(nv) + 1)));
-    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
+    GM_CUDA(dmalloc(g, &cnt, sizeof(unsigned) * nv1));
+    GM_CUDA(dmalloc(g, &lists, sizeof(vidType) * size_t(cap) * 3));
+    GM_CUDA(dmalloc(g, &g->rk_prow, sizeof(eidType) * nv1));
+    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * nv1, g->stream));
     k_ranked_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->rk_nrow, units, g->rk_vinfo);
-    k_fill_u32<<<nblk(acol_len), 256, 0, g->stream>>>(acol_len, g->rk_acol, kVidMax);
-    const int by_dest = options().tc_shard == "dest" || g->force_dest_shard;
-    k_ranked_edges<0><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end, by_dest,
-                                                       g->rk_acol, cnt, nullptr, nullptr, bad);
-    GM_CUDA(cudaMemcpyAsync(g->rk_prow, cnt, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, g->stream));
-    GM_TRY(scan_inplace(g, g->rk_prow, nv));
-    eidType nrec = 0; int h_bad = 0;
-    GM_CUDA(cudaMemcpyAsync(&nrec, g->rk_prow + nv, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
-    GM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    RowCtx c;
+    c.nv = nv; c.rowptr = g->d_rowptr; c.colidx = g->d_colidx; c.rank = rank; c.orig_of = orig_of;
+    c.vinfo = g->rk_vinfo; c.acol = g->rk_acol; c.cnt = cnt;
+    c.src_begin = g->src_begin; c.src_end = g->src_end;
+    c.by_dest = options().tc_shard == "dest" || g->force_dest_shard;
+    c.full_range = g->src_begin == 0 && g->src_end == nv;
+    c.bad = bad; c.lists = lists; c.nlist = nlist; c.cap = cap;
+    const int wide = g->num_sms * 8;
+    k_rows_small<<<unsigned(std::min<int64_t>(nblk(int64_t(nv) * 32), int64_t(wide) * 4)), 256, 0, g->stream>>>(c);
+    k_rows_group<32, kMidMax, 0><<<wide, 256, 0, g->stream>>>(c);
+    k_rows_group<256, kBigMax, 1><<<wide, 256, 0, g->stream>>>(c);
+    unsigned h_nlist[4] = {0, 0, 0, 0};
+    GM_CUDA(cudaMemcpyAsync(h_nlist, nlist, sizeof h_nlist, cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    trace_phase(g->stream, "rank: rows + count");
-    if (h_bad) return GM_OK;                                                     // not the (degree,id) orientation
-    GM_CUDA(dmalloc(g, &g->rk_prec, sizeof(uint2) * size_t(nrec > 0 ? nrec : 1)));
-    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t(nv) + 1), g->stream));
-    k_ranked_edges<1><<<nblk(ne), 256, 0, g->stream>>>(ne, ek1, g->rk_nrow, g->rk_vinfo, orig_of, g->src_begin, g->src_end, by_dest,
-                                                       g->rk_acol, cnt, g->rk_prow, g->rk_prec, bad);
+    if (h_nlist[2] > 0) {
+      const int nh = int(h_nlist[2]);
+      GM_CUDA(dmalloc(g, &seg, sizeof(eidType) * size_t(nh) * 2));
+      GM_CUDA(dmalloc(g, &huge_tmp, sizeof(vidType) * size_t(acol_len)));
+      k_rows_huge_gather<<<std::min(nh, wide), 256, 0, g->stream>>>(c, seg, seg + nh);
+      size_t tmp = 0;
+      GM_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp, g->rk_acol, huge_tmp, acol_len, nh, seg, seg + nh, 0, bits_of(uint64_t(nv)), g->stream));
+      GM_TRY(ensure_scratch(g, tmp));
+      GM_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(g->d_scratch, tmp, g->rk_acol, huge_tmp, acol_len, nh, seg, seg + nh, 0, bits_of(uint64_t(nv)), g->stream));
+      k_rows_huge_finish<<<std::min(nh, wide), 256, 0, g->stream>>>(c, huge_tmp);
+    }
+    trace_phase(g->stream, "rank: rows (gather + sort)");
+    // 3. partner records (their number is at most ne: no read-back needed to size the array)
+    k_widen<<<nblk(int64_t(nv) + 1), 256, 0, g->stream>>>(int64_t(nv) + 1, cnt, g->rk_prow);
+    GM_TRY(scan_inplace(g, g->rk_prow, nv));
+    GM_CUDA(dmalloc(g, &g->rk_prec, sizeof(uint2) * size_t(ne)));
+    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * nv1, g->stream));
+    k_partner_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, g->rk_prow, cnt, g->rk_prec);
+    int h_bad = 0;
+    GM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
     GM_CUDA(cudaGetLastError());
     trace_phase(g->stream, "rank: partner records");
+    if (h_bad) return GM_OK;                                                     // not the (degree,id) orientation
     g->rk_valid = true;
     g->rk_orig = orig_of; orig_of = nullptr;
     return GM_OK;
