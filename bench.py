@@ -4,22 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload tc|clique4|diamond|motif4] [--scale S] [--shape-div D]
 
-A "step" is one full pass of the solver over the synthetic graph.  Workload (BASELINE.json configs[1]):
-triangle counting on Graph500 R-MAT scale 22 (16*2^22 sampled edges, seed 0x5EED0016, SURVEY.md §8d);
-`--workload clique4` runs configs[2] (4-clique, R-MAT scale 23); `--scale 24` gives the north-star size.
-For N>1 the SAME graph is sharded by contiguous source-vertex range (work-balanced) over the N ranks --
-one process per GPU, every rank holds the CSR, no data-path collective, one NCCL all-reduce of the
-64-bit count per step ("strong" scaling: total work fixed).
-`--workload diamond` = configs[3] (sgl diamond on the LiveJournal-shaped synthetic, |V|=4,847,571, 68,993,773
-samples; strong scaling: the same graph at every N); `--workload motif4` = configs[4]'s shape (Friendster-
-shaped, flatter R-MAT) divided by --shape-div (default 16; the full 1.8 B-edge graph is an 8-GPU run),
-counted with the formula solver (motif_gpu_formula semantics).
+A "step" is one full pass of the solver over the synthetic graph.  Default workload: triangle counting on
+Graph500 R-MAT scale 24 (16*2^24 sampled edges, seed 0x5EED0018) -- the size BASELINE.json's
+north_star quotes its target on -- at every N; `--scale 22` is configs[1], `--workload clique4` configs[2]
+(4-clique, R-MAT scale 23; `--scale 24` the north-star size), `--workload diamond` configs[3] (sgl diamond on
+the LiveJournal-shaped synthetic, |V|=4,847,571, 68,993,773 samples), `--workload motif4` configs[4]'s shape
+(Friendster-shaped, flatter R-MAT) divided by --shape-div (default 16; `--shape-div 1` is the full 1.8 B-edge
+graph, an 8-GPU run), counted with the formula solver (motif_gpu_formula semantics).
+For N>1 the SAME graph is sharded by contiguous source-vertex range (work-balanced) over the N ranks -- one
+process per GPU, no data-path collective except for diamond (per-edge supports), one NCCL all-reduce of the
+64-bit count(s) per step ("strong" scaling: total work fixed).
 
-Prints ONE JSON line (see the driver contract): `value` = |E+| / device-timed step (inputs resident in
-HBM), `e2e` = the same metric through gm_tc_host with pinned HOST CSR buffers (H2D + device-side
-preparation + kernels + D2H inside the timed region), `roofline` for the pass's kernels from CUDA
-events on the launch stream, `cpu_baseline` = the reference's own OpenMP code (oracle/_ref/libgm_ref.so)
-on a bounded sample of source vertices of the same graph.
+Prints ONE JSON line (see the driver contract):
+  value     |E+| (TC) or matches / device-timed step, inputs resident in HBM;
+  e2e       the same metric from pinned HOST CSR buffers: gm_*_host at N=1 (H2D + device-side preparation +
+            kernels + D2H inside the timed region); at N>1 every rank uploads 1/N of the CSR, NCCL all-gathers
+            it, prepares and solves its shard;
+  roofline  PHYSICAL: ncu DRAM bytes per step (profiles/traffic.json, tools/ncu_traffic.py) / CUDA-event kernel
+            time / measured copy peak, plus the issue-slot utilisation that actually limits the solvers;
+            stream_roofline = the single-pass HBM roofline of every gm_intersect_batch variant (8 GB stream);
+  detail.parity  the reference's own CPU code (oracle/_ref/libgm_ref.so) on a source range -- the whole graph
+            when that takes about a minute -- must equal both device solvers on the same range;
+  cpu_baseline   that CPU run's throughput (a reported baseline, not the target).
 """
 from __future__ import annotations
 
@@ -310,7 +316,7 @@ def cpu_reference(rp, ci, max_deg, kind, budget_s=12.0, full_cap_s=0.0):
     done, raw, dt = 0, [0] * nc, 0.0
     step = max(1, nv // (200 if kind in ("tc", "clique4") else 50000))
     while done < nv:
-        projected = dt * nv / done if done else float("inf")
+        projected = 1.3 * dt * nv / done if done else float("inf")      # margin: hub sources make the tail slower than the prefix
         if dt >= 0.8 * budget_s and projected > full_cap_s:
             break
         hi = min(nv, done + step)
@@ -320,7 +326,7 @@ def cpu_reference(rp, ci, max_deg, kind, budget_s=12.0, full_cap_s=0.0):
         raw = [(x + y) & ((1 << 64) - 1) for x, y in zip(raw, r)]
         done = hi
         rate = done / max(dt, 1e-6)                                   # sources per second so far
-        left = (full_cap_s if dt * nv / done <= full_cap_s else budget_s) - dt
+        left = (full_cap_s if 1.3 * dt * nv / done <= full_cap_s else budget_s) - dt
         step = int(max(1, min(2 * done, rate * max(left, 0.0))))
     n1 = done
     edges = int(rp[n1] - rp[0])
@@ -399,6 +405,11 @@ def run_ours(args):
             gh.sgl_support_begin()
             dist.all_reduce(gh.support_tensor())
             gh.sgl_support_finish()
+        elif wl.kind == "motif4":
+            # same exchange: only the support pass is shared; closed forms, 4-cycles, 4-cliques partition by range
+            gh.motif_support_begin()
+            dist.all_reduce(gh.support_tensor())
+            gh.motif_support_finish()
         else:
             wl.solve(gh)
         red = res_dev[:wl.ncounts]
@@ -459,7 +470,7 @@ def run_ours(args):
 
     def e2e_step():
         if world == 1:
-            return wl.finish(wl.host_solve(capi, n_rp, n_ci, max_deg))   # gm_*_host: upload + prepare + kernels + D2H
+            return wl.host_solve(capi, n_rp, n_ci, max_deg)   # gm_*_host: upload + prepare + kernels + D2H (+ the formula fix-up)
         d_rp_all[rp_lo:rp_hi].copy_(h_rp[rp_lo:rp_hi], non_blocking=True)
         d_ci_all[ci_lo:ci_hi].copy_(h_ci[ci_lo:ci_hi], non_blocking=True)
         dist.all_gather_into_tensor(d_rp_all, d_rp_all[rank * crp:(rank + 1) * crp])
@@ -577,8 +588,8 @@ def run_ours(args):
                        "tasks_per_sec": wl.tasks(ne) / step_s,
                        "tasks_note": "DFS root tasks (edges) per second: the work rate; matches/s of the count-form solvers divides a closed-form count by time",
                        "l2": "inputs (CSR %.0f MB) larger than the 126 MB L2; no flush" % ((nv * 8 + ne * 4) / 1e6),
-                       "sharding": ("contiguous root ranges, work-balanced; CSR replicated; NCCL all-reduce of the per-edge support array (u32 x DAG edges) + 1 u64 per step"
-                                    if wl.kind == "diamond" and n > 1 else
+                       "sharding": ("contiguous root ranges, work-balanced; CSR replicated; NCCL all-reduce of the per-edge support array (u32 x DAG edges) + %d u64 per step" % wl.ncounts
+                                    if wl.kind in ("diamond", "motif4") and n > 1 else
                                     "contiguous source-vertex ranges, work-balanced; CSR replicated; 1 NCCL all-reduce of %d u64 per step" % wl.ncounts)},
             "e2e": {"value": e2e_value, "unit": wl.unit,
                     "h2d_bytes_per_step": int((nv + 1) * 8 + ne * 4), "d2h_bytes_per_step": 8 * wl.ncounts * n,

@@ -29,7 +29,7 @@ SYMBOLS = [
     "gm_last_error", "gm_version", "gm_device_count", "gm_device_init", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
     "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
-    "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
+    "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_motif_support_begin", "gm_motif_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
     "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
     "gm_motif_formula_finish", "gm_last_stats", "gm_last_alg_bytes",
@@ -84,6 +84,8 @@ def lib():
     L.gm_sgl_support_begin.argtypes = [vp]
     L.gm_graph_support.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.gm_sgl_support_finish.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.gm_motif_support_begin.argtypes = [vp]
+    L.gm_motif_support_finish.argtypes = [vp, _u64p]
     L.gm_graph_set_source_range.argtypes = [vp, i32, i32]
     L.gm_graph_prepare.argtypes = [vp, C.c_char_p]
     L.gm_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_int)]
@@ -305,6 +307,15 @@ class DeviceGraph:
         t = C.c_uint64(0)
         check(lib().gm_sgl_support_finish(self._h, C.byref(t)))
         return t.value
+
+    # multi-GPU formula 4-motif: partial support pass -> all-reduce support_tensor() -> raw sums of the shard
+    def motif_support_begin(self):
+        check(lib().gm_motif_support_begin(self._h))
+
+    def motif_support_finish(self):
+        out = np.zeros(8, dtype=np.uint64)
+        check(lib().gm_motif_support_finish(self._h, out))
+        return [int(x) for x in out[:6]]
 
     def motif(self, k: int, formula=False, raw=False):
         out = np.zeros(8, dtype=np.uint64)

@@ -479,18 +479,21 @@ static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launch
 }
 
 // everything the fast formula pass needs; *ok = false -> the caller keeps the operator-API kernel
-int prepare_motif4_fast(gm_graph *g, bool *ok) {
+// partial: the support pass enumerates only the triangles whose middle vertex lies in the parent's source
+// range (multi-GPU: the caller sums the support arrays of the shards before run_motif4_rest)
+int prepare_motif4_fast(gm_graph *g, bool *ok, bool partial) {
   *ok = false;
   bool sup = false;
-  GM_TRY(prepare_diamond_support(g, &sup));
+  GM_TRY(prepare_diamond_support(g, &sup, partial));
   if (!sup) return GM_OK;
   gm_graph *c = g->dag_child;
   GM_TRY(ensure_c4(c, g->src_begin, g->src_end));
   // 4-clique work items of the child for the parent's source range (roots by original id)
   if (!c->items_ready[4]) {
+    const vidType sb = c->src_begin, se = c->src_end;
     c->src_begin = g->src_begin; c->src_end = g->src_end;
     int r = prepare_kclique_bitmap(c);
-    c->src_begin = 0; c->src_end = c->nv;
+    c->src_begin = sb; c->src_end = se;
     GM_TRY(r);
   }
   *ok = true;
@@ -521,9 +524,14 @@ int run_rectangle_fast(gm_graph *g, int *launches) {
 }
 
 int run_motif4_fast(gm_graph *g, int *launches) {
-  gm_graph *c = g->dag_child;
-  // 1. supports (full graph) -> closed forms over the owned edges
+  // 1. supports (full graph)
   GM_TRY(run_support_pass(g, launches));
+  return run_motif4_rest(g, launches);
+}
+
+// everything after the support pass: closed forms over the owned edges, 4-cycles, 4-cliques
+int run_motif4_rest(gm_graph *g, int *launches) {
+  gm_graph *c = g->dag_child;
   GM_CUDA(cudaMemsetAsync(g->d_ticket, 0, 8 * sizeof(int), g->stream));        // tickets are reused below
   if (c->nv > 0) {
     k_motif4_closed<<<nblk(int64_t(c->nv) * 8), 256, 0, g->stream>>>(c->nv, c->rk_vinfo, c->rk_acol, c->rk_orig, g->d_support,
@@ -537,10 +545,11 @@ int run_motif4_fast(gm_graph *g, int *launches) {
     unsigned long long *save = c->d_counts;
     c->d_counts = g->d_counts + 5;
     GM_CUDA(cudaMemsetAsync(c->d_ticket, 0, 8 * sizeof(int), g->stream));
+    const vidType sb = c->src_begin, se = c->src_end;
     c->src_begin = g->src_begin; c->src_end = g->src_end;
     bool handled = false;
     int r = run_kclique_bitmap(c, 4, launches, &handled);
-    c->src_begin = 0; c->src_end = c->nv;
+    c->src_begin = sb; c->src_end = se;
     c->d_counts = save;
     GM_TRY(r);
   }

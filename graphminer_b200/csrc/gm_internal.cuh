@@ -106,6 +106,9 @@ struct gm_graph {
   uint2 *rk_prec = nullptr;            // partner records {element offset of the suffix, length}
   gm::vidType *rk_orig = nullptr;      // new id -> original id
   int64_t rk_acol_len = 0;             // elements of rk_acol (aligned, padded)
+  // tc.algo=merge: every kept partner record as one (row suffix, root row) pair of gm_intersect_batch
+  int64_t *mg_aoff = nullptr, *mg_boff = nullptr; int32_t *mg_alen = nullptr, *mg_blen = nullptr;
+  unsigned long long *mg_out = nullptr; int64_t mg_npairs = -1;
 
   // undirected input: device-side (degree,id) orientation kept in a child handle (support.cu), and the
   // per-edge triangle supports of the diamond solver (indexed like the child's rk_acol)
@@ -161,6 +164,10 @@ inline cudaError_t dmalloc(gm_graph *g, T **p, size_t bytes) {
   return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 4, g->stream);
 }
 inline cudaError_t dfree(gm_graph *g, void *p) { return p ? cudaFreeAsync(p, g->stream) : cudaSuccess; }
+// a handle that OWNS uninitialised CSR arrays of the given byte sizes (>= the CSR itself); the caller fills them
+// on g->stream and then calls graph_finish_owned (solvers.cu: sharded upload + all-gather)
+int graph_alloc_owned(int32_t nv, int64_t ne, int32_t max_degree, int device, size_t rowptr_bytes, size_t colidx_bytes, gm_graph **out);
+int graph_finish_owned(gm_graph *g);
 int ensure_aligned(gm_graph *g);
 int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
@@ -170,8 +177,9 @@ int ensure_dag_child(gm_graph *g);
 int prepare_diamond_support(gm_graph *g, bool *ok, bool partial = false);
 int run_diamond_support(gm_graph *g, int *launches);
 int run_support_pass(gm_graph *g, int *launches);
-int prepare_motif4_fast(gm_graph *g, bool *ok);
+int prepare_motif4_fast(gm_graph *g, bool *ok, bool partial = false);
 int run_motif4_fast(gm_graph *g, int *launches);
+int run_motif4_rest(gm_graph *g, int *launches);
 int prepare_rectangle_fast(gm_graph *g, bool *ok);
 int run_rectangle_fast(gm_graph *g, int *launches);
 void invalidate_range_structures_of_child(gm_graph *c);

@@ -365,6 +365,8 @@ static void free_aux(gm_graph *g) {
   dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec); dfree(g, g->rk_orig);
   g->rk_orig = nullptr; g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   g->rk_ready = g->rk_valid = false;
+  dfree(g, g->mg_aoff); dfree(g, g->mg_boff); dfree(g, g->mg_alen); dfree(g, g->mg_blen); dfree(g, g->mg_out);
+  g->mg_aoff = g->mg_boff = nullptr; g->mg_alen = g->mg_blen = nullptr; g->mg_out = nullptr; g->mg_npairs = -1;
   dfree(g, g->d_rrowptr); dfree(g, g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
 }
 
@@ -487,6 +489,28 @@ static void finish_common(gm_graph *g, vidType *d_md) {
   dfree(g, d_md);
 }
 
+int graph_alloc_owned(int32_t nv, int64_t ne, int32_t max_degree, int device, size_t rowptr_bytes, size_t colidx_bytes, gm_graph **out) {
+  gm_graph *g = new gm_graph();
+  g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
+  int r = [&]() -> int {
+    GM_TRY(acquire_res(g));
+    GM_CUDA(dmalloc(g, &g->d_rowptr, std::max(rowptr_bytes, sizeof(eidType) * (size_t(nv) + 1))));
+    GM_CUDA(dmalloc(g, &g->d_colidx, std::max(colidx_bytes, sizeof(vidType) * size_t(ne > 0 ? ne : 1))));
+    return GM_OK;
+  }();
+  if (r != GM_OK) { gm_graph_free(g); return r; }
+  *out = g;
+  return GM_OK;
+}
+
+int graph_finish_owned(gm_graph *g) {
+  vidType *d_md = nullptr;
+  GM_TRY(init_common(g, &d_md));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  finish_common(g, d_md);
+  return GM_OK;
+}
+
 }  // namespace gm
 
 using namespace gm;
@@ -518,14 +542,13 @@ int gm_set_option(const char *key, const char *value) {
   if (!key || !value) { set_error("null option"); return GM_EINVAL; }
   std::string k(key), v(value);
   if (k == "tc.algo") {
-    if (v != "auto" && v != "rank" && v != "hash" && v != "hash_rev" && v != "bs") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
+    if (v != "auto" && v != "rank" && v != "hash" && v != "hash_rev" && v != "bs" && v != "merge") { set_error("tc.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_algo = v;
-  } else if (k == "c4.small_max") {
-    options().c4_small_max = atoll(value);
-  } else if (k == "c4.cta_max") {
-    options().c4_cta_max = atoll(value);
-  } else if (k == "c4.mid_max") {
-    options().c4_mid_max = atoll(value);
+  } else if (k == "c4.small_max" || k == "c4.cta_max" || k == "c4.mid_max") {
+    char *end = nullptr;
+    long long t = strtoll(value, &end, 10);
+    if (end == value || *end || t < -1) { set_error("%s: a wedge count >= 0 (or -1 = default), got '%s'", key, value); return GM_EINVAL; }
+    (k == "c4.small_max" ? options().c4_small_max : k == "c4.cta_max" ? options().c4_cta_max : options().c4_mid_max) = t;
   } else if (k == "motif.algo") {
     if (v != "auto" && v != "fast" && v != "list") { set_error("motif.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().motif_algo = v;
@@ -551,7 +574,10 @@ int gm_set_option(const char *key, const char *value) {
     if (v != "auto" && v != "bitmap" && v != "list") { set_error("clique.algo: unknown value '%s'", value); return GM_EINVAL; }
     options().clique_algo = v;
   } else if (k == "sched.chunk") {
-    options().chunk = atoi(value);
+    char *end = nullptr;
+    long t = strtol(value, &end, 10);
+    if (end == value || *end || t < 0 || t > (1 << 24)) { set_error("sched.chunk: partners per work item in [1, 2^24] (0 = default), got '%s'", value); return GM_EINVAL; }
+    options().chunk = int(t);
   } else if (k.rfind("batch.", 0) == 0) {
     return set_batch_option(k.c_str(), atoi(value));
   } else { set_error("unknown option '%s'", key); return GM_EINVAL; }

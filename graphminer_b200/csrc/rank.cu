@@ -293,7 +293,7 @@ int ensure_ranked(gm_graph *g) {
     g->rk_acol_len = acol_len;
     const int64_t cap = std::min<int64_t>(int64_t(nv), ne / 33 + 1);      // rows with more than 32 entries
     GM_CUDA(dmalloc(g, &g->rk_vinfo, sizeof(uint2) * size_t(nv)));
-    GM_CUDA(dmalloc(g, &g->rk_acol, sizeof(vidType) * size_t(acol_len > 0 ? acol_len : 4)));
+    GM_CUDA(dmalloc(g, &g->rk_acol, sizeof(vidType) * size_t(acol_len + 8)));   // + slack: the TMA pipeline reads whole 16-byte units (tc.algo=merge)
     GM_CUDA(dmalloc(g, &cnt, sizeof(unsigned) * nv1));
     GM_CUDA(dmalloc(g, &lists, sizeof(vidType) * size_t(cap) * 3));
     GM_CUDA(dmalloc(g, &g->rk_prow, sizeof(eidType) * nv1));

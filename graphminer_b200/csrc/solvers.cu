@@ -5,6 +5,9 @@
 
 #include <dlfcn.h>
 #include <algorithm>
+#include <condition_variable>
+#include <map>
+#include <mutex>
 #include <thread>
 
 namespace gm {
@@ -104,6 +107,27 @@ static int motif_common(gm_graph_t *g, int k, int formula, int raw, uint64_t *co
   return GM_OK;
 }
 
+// Multi-GPU formula 4-motif with the support exchange of gm_sgl_support_begin/finish: the support pass is the
+// only part of the fast formula path that is not partitioned by the source range.
+int gm_motif_support_begin(gm_graph_t *g) {
+  if (!g) { set_error("gm_motif_support_begin: null graph"); return GM_EINVAL; }
+  bool fast = false;
+  GM_TRY(prepare_motif4_fast(g, &fast, /*partial=*/true));
+  if (!fast) { set_error("gm_motif_support_begin: the graph has no edges or its DAG could not be ranked"); return GM_EUNSUPPORTED; }
+  g->last_alg_bytes = 0; g->last_alg_kind = 0;
+  GM_TRY(begin_timed(g));
+  g->support_launches = 0;
+  return run_support_pass(g, &g->support_launches);
+}
+int gm_motif_support_finish(gm_graph_t *g, uint64_t *counts) {
+  if (!g || !counts) { set_error("gm_motif_support_finish: null argument"); return GM_EINVAL; }
+  gm_graph *c = g->dag_child;
+  if (!c || !g->d_support || !c->rk_valid || !c->c4_lists_ready) { set_error("gm_motif_support_finish: call gm_motif_support_begin first"); return GM_EINVAL; }
+  int launches = g->support_launches;
+  GM_TRY(run_motif4_rest(g, &launches));
+  return end_timed(g, launches, 6, counts);            // RAW sums: add the shards, then gm_motif_formula_finish
+}
+
 int gm_motif(gm_graph_t *g, int k, uint64_t *counts) { return motif_common(g, k, 0, 0, counts); }
 int gm_motif_formula(gm_graph_t *g, int k, uint64_t *counts) { return motif_common(g, k, 1, 0, counts); }
 int gm_motif_formula_raw(gm_graph_t *g, int k, uint64_t *counts) { return motif_common(g, k, 1, 1, counts); }
@@ -113,14 +137,16 @@ int gm_motif_formula_finish(int k, uint64_t *counts) {
   return GM_OK;
 }
 
-// ---- NCCL all-reduce of the counters (loaded lazily so the library has no link-time NCCL dependency
-// and never clashes with the copy PyTorch bundles) ----------------------------------------------------
+// ---- NCCL (loaded lazily so the library has no link-time NCCL dependency and never clashes with the copy
+// PyTorch bundles).  Communicators are created once per device count and kept for the life of the process:
+// ncclCommInitAll costs ~100 ms, far more than any of the collectives below. -----------------------------
 namespace {
 struct Nccl {
   void *h = nullptr;
   int (*CommInitAll)(void **, int, const int *) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -132,15 +158,53 @@ struct Nccl {
     CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(h, "ncclCommInitAll"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(h, "ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(h, "ncclAllGather"));
     GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(h, "ncclGroupStart"));
     GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(h, "ncclGroupEnd"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-    ok = CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+    ok = CommInitAll && CommDestroy && AllReduce && AllGather && GroupStart && GroupEnd;
   }
+  const char *err(int e) const { return GetErrorString ? GetErrorString(e) : "error"; }
 };
 Nccl &nccl() { static Nccl n; return n; }
-constexpr int kNcclUint64 = 5;   // ncclUint64 (nccl.h: ncclDataType_t)
+constexpr int kNcclChar = 0;     // ncclInt8 / ncclChar (nccl.h: ncclDataType_t)
+constexpr int kNcclUint32 = 3;   // ncclUint32
+constexpr int kNcclUint64 = 5;   // ncclUint64
 constexpr int kNcclSum = 0;      // ncclSum
+
+// communicators over devices 0..n-1, created on first use; nullptr when NCCL is unavailable
+std::vector<void *> *nccl_world(int n) {
+  static std::mutex mu;
+  static std::map<int, std::vector<void *>> worlds;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = worlds.find(n);
+  if (it != worlds.end()) return it->second.empty() ? nullptr : &it->second;
+  std::vector<void *> &w = worlds[n];
+  Nccl &nc = nccl();
+  if (!nc.ok) return nullptr;
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; i++) devs[i] = i;
+  w.assign(n, nullptr);
+  int r = nc.CommInitAll(w.data(), n, devs.data());
+  if (r != 0) { set_error("ncclCommInitAll: %s", nc.err(r)); w.clear(); return nullptr; }
+  return &w;
+}
+
+// rendezvous of the per-device host threads that also agrees on "did everybody succeed so far": a thread
+// that failed must not leave the others waiting inside a collective
+struct Rendezvous {
+  std::mutex m; std::condition_variable cv;
+  int n, waiting = 0; unsigned gen = 0; bool ok_acc = true, ok_last = true;
+  explicit Rendezvous(int n_) : n(n_) {}
+  bool arrive(bool ok) {
+    std::unique_lock<std::mutex> lk(m);
+    ok_acc = ok_acc && ok;
+    if (++waiting == n) { ok_last = ok_acc; ok_acc = true; waiting = 0; gen++; cv.notify_all(); return ok_last; }
+    const unsigned my = gen;
+    cv.wait(lk, [&] { return gen != my; });
+    return ok_last;
+  }
+};
 }  // namespace
 
 int gm_allreduce_u64(uint64_t **d_bufs, const int *devices, int n_gpus, int n) {
@@ -148,20 +212,28 @@ int gm_allreduce_u64(uint64_t **d_bufs, const int *devices, int n_gpus, int n) {
   if (n_gpus == 1) return GM_OK;
   Nccl &nc = nccl();
   if (!nc.ok) { set_error("NCCL not loadable (libnccl.so.2)"); return GM_ENCCL; }
-  std::vector<void *> comms(n_gpus, nullptr);
-  int r = nc.CommInitAll(comms.data(), n_gpus, devices);
-  if (r != 0) { set_error("ncclCommInitAll: %s", nc.GetErrorString ? nc.GetErrorString(r) : "error"); return GM_ENCCL; }
+  bool iota = true;
+  for (int i = 0; i < n_gpus; i++) iota = iota && devices[i] == i;
+  std::vector<void *> own;
+  std::vector<void *> *comms = iota ? nccl_world(n_gpus) : nullptr;     // the cached world covers devices 0..n-1
+  if (!comms) {
+    if (iota) return GM_ENCCL;
+    own.assign(n_gpus, nullptr);
+    int r = nc.CommInitAll(own.data(), n_gpus, devices);
+    if (r != 0) { set_error("ncclCommInitAll: %s", nc.err(r)); return GM_ENCCL; }
+    comms = &own;
+  }
   int rc = GM_OK;
   nc.GroupStart();
   for (int i = 0; i < n_gpus; i++) {
     cudaSetDevice(devices[i]);
-    int e = nc.AllReduce(d_bufs[i], d_bufs[i], size_t(n), kNcclUint64, kNcclSum, comms[i], (cudaStream_t)0);
-    if (e != 0 && rc == GM_OK) { set_error("ncclAllReduce: %s", nc.GetErrorString ? nc.GetErrorString(e) : "error"); rc = GM_ENCCL; }
+    int e = nc.AllReduce(d_bufs[i], d_bufs[i], size_t(n), kNcclUint64, kNcclSum, (*comms)[i], (cudaStream_t)0);
+    if (e != 0 && rc == GM_OK) { set_error("ncclAllReduce: %s", nc.err(e)); rc = GM_ENCCL; }
   }
   int e = nc.GroupEnd();
-  if (e != 0 && rc == GM_OK) { set_error("ncclGroupEnd: %s", nc.GetErrorString ? nc.GetErrorString(e) : "error"); rc = GM_ENCCL; }
+  if (e != 0 && rc == GM_OK) { set_error("ncclGroupEnd: %s", nc.err(e)); rc = GM_ENCCL; }
   for (int i = 0; i < n_gpus; i++) { cudaSetDevice(devices[i]); cudaStreamSynchronize(0); }
-  for (int i = 0; i < n_gpus; i++) nc.CommDestroy(comms[i]);
+  for (void *c : own) nc.CommDestroy(c);
   return rc;
 }
 
@@ -173,28 +245,113 @@ struct HostJob {
   Kind kind; int k; const char *pattern; int formula; int ncounts;
 };
 
+int solve_on(const HostJob &j, gm_graph_t *g, uint64_t *counts) {
+  switch (j.kind) {
+    case K_TC: return gm_tc(g, counts);
+    case K_CLIQUE: return gm_kclique(g, j.k, counts);
+    case K_SGL: return gm_sgl(g, j.pattern, counts);
+    case K_MOTIF: return j.formula ? gm_motif_formula_raw(g, j.k, counts) : gm_motif(g, j.k, counts);
+  }
+  return GM_EINVAL;
+}
+
 int run_on_device(const HostJob &j, int device, int32_t begin, int32_t end, uint64_t *counts, std::string *err) {
   gm_graph_t *g = nullptr;
   int r = gm_graph_upload(j.rowptr, j.colidx, j.nv, j.ne, j.max_degree, device, &g);
   if (r == GM_OK) r = gm_graph_set_source_range(g, begin, end);
-  if (r == GM_OK) {
-    switch (j.kind) {
-      case K_TC: r = gm_tc(g, counts); break;
-      case K_CLIQUE: r = gm_kclique(g, j.k, counts); break;
-      case K_SGL: r = gm_sgl(g, j.pattern, counts); break;
-      case K_MOTIF: r = j.formula ? gm_motif_formula_raw(g, j.k, counts) : gm_motif(g, j.k, counts); break;
-    }
-  }
+  if (r == GM_OK) r = solve_on(j, g, counts);
   if (r != GM_OK && err) *err = gm_last_error();
   gm_graph_free(g);
   return r;
 }
 
-// Shard by contiguous source-vertex range over devices 0..n-1 (triangle/multigpu.cu:16-89 semantics:
-// one host thread per device; here every device holds the full CSR -- the replicated form of
-// clique/multigpu.cu:20-139 -- and the per-device counts are summed by one NCCL all-reduce).
+// One shard of a multi-GPU job, run by the host thread that owns `device` (triangle/multigpu.cu:66-81):
+//   1. placement: every device copies 1/n of the host CSR over its own PCIe link and the slices are exchanged
+//      with one in-place ncclAllGather each for rowptr and colidx over NVLink (the reference copies the whole
+//      graph, or its 1-hop partition, to every GPU from the host: triangle/multigpu.cu:45-56);
+//   2. the solver on the shard's source range; diamond and the formula 4-motif share their one non-partitioned
+//      step through an all-reduce of the per-edge support array (gm_sgl_support_* / gm_motif_support_*);
+//   3. one ncclAllReduce of the 64-bit counts on the shard's stream, then a single D2H read.
+struct ShardCtx {
+  const HostJob *job; int n; std::vector<void *> *comms; Rendezvous *rv; const int32_t *bounds;
+};
+
+int run_shard(const ShardCtx &cx, int dev, uint64_t *counts) {
+  const HostJob &j = *cx.job;
+  Nccl &nc = nccl();
+  const int n = cx.n;
+  void *comm = (*cx.comms)[dev];
+  gm_graph_t *g = nullptr;
+  unsigned long long *d_res = nullptr;
+  int rc = GM_OK;
+  auto step = [&](int r) { if (rc == GM_OK && r != GM_OK) rc = r; return rc == GM_OK; };   // first error wins
+  auto nccl_step = [&](int e, const char *what) { if (e != 0 && rc == GM_OK) { set_error("%s: %s", what, nc.err(e)); rc = GM_ENCCL; } return rc == GM_OK; };
+
+  // 1. placement
+  const size_t rp_bytes = sizeof(int64_t) * (size_t(j.nv) + 1), ci_bytes = sizeof(int32_t) * size_t(j.ne);
+  const size_t rp_chunk = ((rp_bytes + n - 1) / n + 15) & ~size_t(15), ci_chunk = ((ci_bytes + n - 1) / n + 15) & ~size_t(15);
+  step(graph_alloc_owned(j.nv, j.ne, j.max_degree, dev, rp_chunk * n, std::max<size_t>(ci_chunk * n, 16), &g));
+  if (rc == GM_OK) {
+    auto slice = [&](char *dst, const char *src, size_t bytes, size_t chunk) {
+      const size_t lo = std::min(bytes, chunk * dev), hi = std::min(bytes, chunk * (dev + 1));
+      return hi > lo ? cudaMemcpyAsync(dst + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, g->stream) : cudaSuccess;
+    };
+    if (slice(reinterpret_cast<char *>(g->d_rowptr), reinterpret_cast<const char *>(j.rowptr), rp_bytes, rp_chunk) != cudaSuccess ||
+        slice(reinterpret_cast<char *>(g->d_colidx), reinterpret_cast<const char *>(j.colidx), ci_bytes, ci_chunk) != cudaSuccess) {
+      set_error("sharded upload: %s", cudaGetErrorString(cudaGetLastError())); rc = GM_ECUDA;
+    }
+  }
+  if (cx.rv->arrive(rc == GM_OK)) {
+    char *rp = reinterpret_cast<char *>(g->d_rowptr), *ci = reinterpret_cast<char *>(g->d_colidx);
+    nccl_step(nc.AllGather(rp + rp_chunk * dev, rp, rp_chunk, kNcclChar, comm, g->stream), "ncclAllGather(rowptr)");
+    nccl_step(nc.AllGather(ci + ci_chunk * dev, ci, ci_chunk, kNcclChar, comm, g->stream), "ncclAllGather(colidx)");
+    step(graph_finish_owned(g));
+    trace_phase(g->stream, "sharded upload + all-gather");
+  } else if (rc == GM_OK) { set_error("another shard failed during placement"); rc = GM_ECUDA; }
+
+  // 2. the shard's pass; results stay on the device
+  if (rc == GM_OK) {
+    step(gm_graph_set_source_range(g, cx.bounds[dev], cx.bounds[dev + 1]));
+    if (rc == GM_OK && cudaMallocAsync(reinterpret_cast<void **>(&d_res), 8 * sizeof(unsigned long long), g->stream) != cudaSuccess) { set_error("out of device memory"); rc = GM_ENOMEM; }
+    if (rc == GM_OK) { cudaMemsetAsync(d_res, 0, 8 * sizeof(unsigned long long), g->stream); step(gm_graph_set_result_buffer(g, reinterpret_cast<uint64_t *>(d_res))); }
+  }
+  const bool diamond = j.kind == K_SGL && std::string(j.pattern) == "diamond" && options().sgl_algo != "list";
+  const bool motif4 = j.kind == K_MOTIF && j.formula && j.k == 4 && options().motif_algo != "list";
+  if (diamond || motif4) {
+    // every shard takes the same decision (same graph): GM_EUNSUPPORTED here means "no fast path" for all
+    int r = rc == GM_OK ? (diamond ? gm_sgl_support_begin(g) : gm_motif_support_begin(g)) : rc;
+    const bool fallback = r == GM_EUNSUPPORTED;
+    if (!fallback) step(r);
+    if (cx.rv->arrive(rc == GM_OK)) {
+      if (fallback) {
+        step(solve_on(j, g, counts));
+      } else {
+        uint32_t *sup = nullptr; int64_t len = 0;
+        step(gm_graph_support(g, &sup, &len));
+        if (rc == GM_OK) nccl_step(nc.AllReduce(sup, sup, size_t(len), kNcclUint32, kNcclSum, comm, g->stream), "ncclAllReduce(supports)");
+        if (rc == GM_OK) step(diamond ? gm_sgl_support_finish(g, counts) : gm_motif_support_finish(g, counts));
+      }
+    } else if (rc == GM_OK) { set_error("another shard failed in the support pass"); rc = GM_ECUDA; }
+  } else if (rc == GM_OK) {
+    step(solve_on(j, g, counts));
+  }
+  // 3. counts
+  if (cx.rv->arrive(rc == GM_OK)) {
+    nccl_step(nc.AllReduce(d_res, d_res, size_t(j.ncounts), kNcclUint64, kNcclSum, comm, g->stream), "ncclAllReduce(counts)");
+    if (rc == GM_OK && cudaMemcpyAsync(counts, d_res, sizeof(uint64_t) * j.ncounts, cudaMemcpyDeviceToHost, g->stream) != cudaSuccess) { set_error("D2H of the counts failed"); rc = GM_ECUDA; }
+    if (rc == GM_OK && cudaStreamSynchronize(g->stream) != cudaSuccess) { set_error("shard %d: %s", dev, cudaGetErrorString(cudaGetLastError())); rc = GM_ECUDA; }
+    if (g) trace_phase(g->stream, "shard pass + all-reduce");
+  } else if (rc == GM_OK) { set_error("another shard failed in its pass"); rc = GM_ECUDA; }
+  if (g) { gm_graph_set_result_buffer(g, nullptr); if (d_res) cudaFreeAsync(d_res, g->stream); }
+  gm_graph_free(g);
+  return rc;
+}
+
+// Shard by contiguous source-vertex range over devices 0..n-1, one host thread per device
+// (triangle/multigpu.cu:16-89 semantics).
 int run_host(const HostJob &j, int n_gpus, uint64_t *out) {
   if (!j.rowptr || j.nv < 0 || j.ne < 0 || !out) { set_error("host entry: bad arguments"); return GM_EINVAL; }
+  if (j.rowptr[j.nv] != j.ne) { set_error("host entry: rowptr[nv]=%lld != ne=%lld", (long long)j.rowptr[j.nv], (long long)j.ne); return GM_EINVAL; }
   int ndev = 0; gm_device_count(&ndev);
   if (ndev < 1) { set_error("no CUDA device available"); return GM_ECUDA; }
   if (n_gpus < 1) n_gpus = 1;
@@ -212,27 +369,21 @@ int run_host(const HostJob &j, int n_gpus, uint64_t *out) {
   std::vector<int> rcs(n_gpus, GM_OK);
   std::vector<std::string> errs(n_gpus);
   std::vector<std::thread> th;
-  for (int i = 0; i < n_gpus; i++)
-    th.emplace_back([&, i] { rcs[i] = run_on_device(j, i, bounds[i], bounds[i + 1], counts[i].data(), &errs[i]); });
-  for (auto &t : th) t.join();
-  for (int i = 0; i < n_gpus; i++) if (rcs[i] != GM_OK) { set_error("gpu %d: %s", i, errs[i].c_str()); return rcs[i]; }
-  // reduce: NCCL all-reduce over per-device buffers; host sum if NCCL cannot be loaded
-  std::vector<uint64_t *> dbufs(n_gpus, nullptr);
-  std::vector<int> devs(n_gpus);
-  bool staged = true;
-  for (int i = 0; i < n_gpus; i++) {
-    devs[i] = i;
-    if (cudaSetDevice(i) != cudaSuccess || cudaMalloc(&dbufs[i], 8 * sizeof(uint64_t)) != cudaSuccess ||
-        cudaMemcpy(dbufs[i], counts[i].data(), 8 * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) { staged = false; break; }
-  }
-  bool reduced = false;
-  if (staged && gm_allreduce_u64(dbufs.data(), devs.data(), n_gpus, j.ncounts) == GM_OK) {
-    cudaSetDevice(0);
-    reduced = cudaMemcpy(out, dbufs[0], sizeof(uint64_t) * j.ncounts, cudaMemcpyDeviceToHost) == cudaSuccess;
-  }
-  for (int i = 0; i < n_gpus; i++) if (dbufs[i]) { cudaSetDevice(i); cudaFree(dbufs[i]); }
-  cudaGetLastError();
-  if (!reduced) {
+  std::vector<void *> *comms = nccl_world(n_gpus);
+  if (comms) {
+    Rendezvous rv(n_gpus);
+    ShardCtx cx{&j, n_gpus, comms, &rv, bounds.data()};
+    for (int i = 0; i < n_gpus; i++)
+      th.emplace_back([&, i] { rcs[i] = run_shard(cx, i, counts[i].data()); if (rcs[i] != GM_OK) errs[i] = gm_last_error(); });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n_gpus; i++) if (rcs[i] != GM_OK) { set_error("gpu %d: %s", i, errs[i].c_str()); return rcs[i]; }
+    for (int c = 0; c < j.ncounts; c++) out[c] = counts[0][c];            // every shard holds the reduced counts
+  } else {
+    // no NCCL: replicated placement from the host, every shard repeats the non-partitioned steps, host sum
+    for (int i = 0; i < n_gpus; i++)
+      th.emplace_back([&, i] { rcs[i] = run_on_device(j, i, bounds[i], bounds[i + 1], counts[i].data(), &errs[i]); });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n_gpus; i++) if (rcs[i] != GM_OK) { set_error("gpu %d: %s", i, errs[i].c_str()); return rcs[i]; }
     for (int c = 0; c < j.ncounts; c++) { out[c] = 0; for (int i = 0; i < n_gpus; i++) out[c] += counts[i][c]; }
   }
   if (j.kind == K_MOTIF && j.formula) gm_motif_formula_finish(j.k, out);

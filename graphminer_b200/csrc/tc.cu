@@ -29,30 +29,60 @@ __device__ __forceinline__ void group_sync() {
   if (GT == 32) __syncwarp(); else __syncthreads();
 }
 
-// Stream one aligned row and count table hits.  Warp-collective.  Four coalesced 128-byte loads are
-// in flight per iteration; probes go two chunks at a time with the level-2 lookups of both deferred
-// into one (rarely taken, few-lane) branch.
-__device__ __forceinline__ uint32_t probe_pair(const RowTable &tab, uint32_t s1, uint32_t xa, uint32_t xb) {
-  uint32_t ta = tab.probe1(s1, xa), tb = tab.probe1(s1, xb);
-  uint32_t c = uint32_t(RowTable::is_hit(ta, xa)) + uint32_t(RowTable::is_hit(tb, xb));
-  bool qa = RowTable::needs_l2(ta, xa), qb = RowTable::needs_l2(tb, xb);
-  if (qa | qb) {
-    if (qa) c += tab.probe2(xa);
-    if (qb) c += tab.probe2(xb);
-  }
-  return c;
+// Stream one row (suffix) and count table hits.  Warp-collective.
+//
+// Round 2 rewrite after the round-1 profile (profiles/r01f_tc_s22.summary.txt: issue-bound, IPC 3.5, ~136 SASS
+// per 128 streamed elements).  Two things cost more than the probes themselves:
+//   * the bounds handling of the four coalesced loads compiled into a chain of branches -> predicated loads
+//     (`@p ld.global.nc`) into registers preset to the padding value, no branch;
+//   * a probe that misses on a FLAGGED level-1 slot (2.6 % of the probes) must look at level 2, and with 64
+//     probes per branch decision the warp took that divergent path on ~80 % of the pairs, for one or two
+//     lanes each time -> every lane now only REMEMBERS its flagged key (`px`, count `np`) and the warp
+//     resolves all of them together once per 128 elements: one level-2 probe sequence instead of four.
+__device__ __forceinline__ uint32_t ldg_or_pad(const vidType *p, bool live) {
+  uint32_t v = uint32_t(kVidMax);
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+               : "+r"(v) : "l"(p), "r"(int(live)));
+  return v;
+}
+
+// level-1 probe of x: count a hit, remember x when the slot says "someone was displaced from here".
+// Written in PTX so that it lowers to LOP3 (predicate out) / @!p IADD / ISETP.LT.AND / @p MOV / @p IADD:
+// nvcc's own lowering of the C form spent two instructions on each conditional increment.
+__device__ __forceinline__ void probe_l1(const RowTable &tab, uint32_t s1, uint32_t x, uint32_t &c, uint32_t &px, uint32_t &np) {
+  const uint32_t tw = tab.probe1(s1, x);
+  asm("{\n\t.reg .pred pm, pf;\n\t.reg .b32 t;\n\t"
+      "xor.b32 t, %3, %4;\n\tand.b32 t, t, 0x7fffffff;\n\tsetp.ne.u32 pm, t, 0;\n\t"
+      "@!pm add.u32 %0, %0, 1;\n\t"
+      "setp.lt.and.s32 pf, %3, 0, pm;\n\t"
+      "@pf mov.b32 %1, %4;\n\t"
+      "@pf add.u32 %2, %2, 1;\n\t}"
+      : "+r"(c), "+r"(px), "+r"(np) : "r"(tw), "r"(x));
 }
 
 __device__ __forceinline__ uint32_t stream_probe(const RowTable &tab, uint32_t s1, const vidType *list, int len, int lane) {
   uint32_t c = 0;
   const vidType *p = list + lane;
   for (int r = len - lane; r > -lane; r -= 128, p += 128) {        // r - (-lane) = elements left in the row
-    uint32_t x0 = r > 0 ? uint32_t(__ldg(p)) : uint32_t(kVidMax);
-    uint32_t x1 = r > 32 ? uint32_t(__ldg(p + 32)) : uint32_t(kVidMax);
-    uint32_t x2 = r > 64 ? uint32_t(__ldg(p + 64)) : uint32_t(kVidMax);
-    uint32_t x3 = r > 96 ? uint32_t(__ldg(p + 96)) : uint32_t(kVidMax);
-    c += probe_pair(tab, s1, x0, x1);
-    if (r + lane > 64) c += probe_pair(tab, s1, x2, x3);           // warp-uniform
+    const uint32_t x0 = ldg_or_pad(p, r > 0), x1 = ldg_or_pad(p + 32, r > 32);
+    const uint32_t x2 = ldg_or_pad(p + 64, r > 64), x3 = ldg_or_pad(p + 96, r > 96);
+    uint32_t px = 0, np = 0;
+    probe_l1(tab, s1, x0, c, px, np);
+    probe_l1(tab, s1, x1, c, px, np);
+    if (r + lane > 64) {                                           // warp-uniform
+      probe_l1(tab, s1, x2, c, px, np);
+      probe_l1(tab, s1, x3, c, px, np);
+    }
+    if (__any_sync(kFullMask, np != 0)) {
+      if (np == 1) {
+        c += tab.probe2(px);
+      } else if (np > 1) {                                          // two flagged slots in one lane: ~0.4 % of the lanes
+        const uint32_t xs[4] = {x0, x1, x2, x3};
+        #pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (RowTable::needs_l2(tab.probe1(s1, xs[u]), xs[u])) c += tab.probe2(xs[u]);
+      }
+    }
   }
   return c;
 }
@@ -174,6 +204,57 @@ __global__ void k_tc_alg_bytes(vidType vb, vidType ve, const eidType *rowptr, co
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+// ---- tc.algo=merge: the DAG edges as pairs of the TMA-staged ring pipeline (batch_kernels.cuh) -----------
+// pair of edge a -> b = (suffix of ranked row a behind b, ranked row b): merge-path or galloping search per
+// pair, lists bulk-copied into shared memory by cp.async.bulk -- the streaming form of the intersection, no
+// per-root table.  Wins where rows are short and little reuse exists (low-degree graphs); the table kernel
+// wins on R-MAT, where a hub row is probed by thousands of partners.
+__global__ void __launch_bounds__(256)
+k_merge_pairs(vidType nv, const uint2 *__restrict__ vinfo, const eidType *__restrict__ prow, const uint2 *__restrict__ prec,
+              int64_t *a_off, int32_t *a_len, int64_t *b_off, int32_t *b_len) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType b = vidType(t >> 3); const int sub = int(t & 7);
+  if (b >= nv) return;
+  const uint2 vb = vinfo[b];
+  for (eidType r = prow[b] + sub; r < prow[b + 1]; r += 8) {
+    const uint2 p = prec[r];
+    a_off[r] = int64_t(p.x); a_len[r] = int32_t(p.y);
+    b_off[r] = int64_t(vb.x) << 2; b_len[r] = int32_t(vb.y);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_sum_u64(int64_t n, const unsigned long long *__restrict__ in, AccType *total) {
+  AccType acc = 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) acc += in[i];
+  acc = warp_reduce(acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+
+static int prepare_tc_merge(gm_graph *g) {
+  if (g->mg_npairs >= 0) return GM_OK;
+  eidType nrec = 0;
+  GM_CUDA(cudaMemcpyAsync(&nrec, g->rk_prow + g->nv, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  const size_t n = size_t(nrec > 0 ? nrec : 1);
+  GM_CUDA(dmalloc(g, &g->mg_aoff, sizeof(int64_t) * n)); GM_CUDA(dmalloc(g, &g->mg_boff, sizeof(int64_t) * n));
+  GM_CUDA(dmalloc(g, &g->mg_alen, sizeof(int32_t) * n)); GM_CUDA(dmalloc(g, &g->mg_blen, sizeof(int32_t) * n));
+  GM_CUDA(dmalloc(g, &g->mg_out, sizeof(unsigned long long) * n));
+  if (nrec > 0) k_merge_pairs<<<unsigned((int64_t(g->nv) * 8 + 255) / 256), 256, 0, g->stream>>>(g->nv, g->rk_vinfo, g->rk_prow, g->rk_prec, g->mg_aoff, g->mg_alen, g->mg_boff, g->mg_blen);
+  GM_CUDA(cudaGetLastError());
+  g->mg_npairs = nrec;
+  trace_phase(g->stream, "tc.merge: pair descriptors");
+  return GM_OK;
+}
+
+static int run_tc_merge(gm_graph *g, int *launches) {
+  if (g->mg_npairs <= 0) return GM_OK;
+  GM_TRY(gm_intersect_batch(g->rk_acol, g->mg_aoff, g->mg_alen, g->mg_boff, g->mg_blen, nullptr, nullptr, nullptr, g->mg_npairs,
+                            GM_OP_INTERSECT_NUM, GM_ALGO_AUTO, reinterpret_cast<uint64_t *>(g->mg_out), nullptr, nullptr, g->device, g->stream));
+  k_sum_u64<<<g->num_sms * 8, 256, 0, g->stream>>>(g->mg_npairs, g->mg_out, g->d_counts);
+  *launches += 4;          // ring pipeline + long-pair pipeline + bsearch overflow + the sum
+  return GM_OK;
+}
+
 template <int GT, int MAXB1, int CAP, int MODE>
 static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *launches) {
   const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
@@ -228,9 +309,9 @@ int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break) {
 // the (degree,id) orientation (verified on device, rank.cu), else hash_rev.
 static int resolve_tc_algo(gm_graph *g, std::string *out) {
   std::string algo = options().tc_algo;
-  if (algo == "auto" || algo == "rank") {
+  if (algo == "auto" || algo == "rank" || algo == "merge") {
     GM_TRY(ensure_ranked(g));
-    algo = g->rk_valid ? "rank" : "hash_rev";
+    if (!g->rk_valid) algo = "hash_rev"; else if (algo == "auto") algo = "rank";
   }
   *out = algo;
   return GM_OK;
@@ -241,6 +322,7 @@ int prepare_tc(gm_graph *g) {
   GM_TRY(resolve_tc_algo(g, &algo));
   if (algo == "bs") return ensure_coo(g, 0);
   if (algo == "rank") return ensure_items(g, 3);
+  if (algo == "merge") return prepare_tc_merge(g);
   GM_TRY(ensure_aligned(g));
   return ensure_items(g, algo == "hash" ? 0 : 1);
 }
@@ -266,6 +348,8 @@ extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
       tc_warp_edge_bs<<<grid, 256, 0, g->stream>>>(g->view(0), g->d_counts);
       launches++;
     }
+  } else if (algo == "merge") {
+    GM_TRY(run_tc_merge(g, &launches));
   } else if (algo == "hash") {
     GM_TRY(run_tc_hash<0>(g, &launches));
   } else if (algo == "hash_rev") {

@@ -47,7 +47,11 @@ int gm_device_count(int *count);            /* cudaGetDeviceCount; 0 devices is 
  * (what print_device_info(0) does before the reference starts its timer, triangle/gpu_base.cu:26). */
 int gm_device_init(int device);
 /* Runtime knobs replacing the reference's compile-time macros (src/common.mk:72-114).
- * keys: "tc.algo" = auto|hash|hash_rev|bs|merge, "clique.algo" = auto|bitmap|list,
+ * keys: "tc.algo" = auto|rank|hash|hash_rev|bs|merge (auto = rank when the input is the (degree,id) orientation,
+ *       else hash_rev; rank = root tables + row suffixes on the rank-relabelled DAG; hash / hash_rev = root
+ *       tables with out- / in-neighbour partners; bs = warp per edge over gm::intersect_num; merge = every DAG
+ *       edge as one pair of the TMA-staged merge-path / galloping ring pipeline of gm_intersect_batch),
+ *       "clique.algo" = auto|bitmap|list,
  *       "motif.algo" = auto|fast|list (4-motif formula: supports + wedge-pair 4-cycles + bit-matrix
  *       4-cliques on the DAG, or the warp-per-edge operator-API kernel),
  *       "sgl.algo" = auto|support|list (diamond: per-edge triangle supports on the DAG, or the
@@ -55,7 +59,11 @@ int gm_device_init(int device);
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source
  *       (the reference's semantics, default) or by their destination (same total over a partition of
  *       the vertex set; keeps each root's table on one shard -- set before gm_graph_prepare),
- *       "batch.*" = tuning of the streaming pipeline.  Unknown key -> GM_EINVAL. */
+ *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.gt2" = 256|512, "sup.gt2" =
+ *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
+ *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers).
+ *       Unknown key or out-of-range value -> GM_EINVAL.  Options are process-global: set them before the
+ *       solver calls, not concurrently with them. */
 int gm_set_option(const char *key, const char *value);
 
 /* ---- host-side graph preparation (C++/OpenMP; no device needed) ---------------------------- */
@@ -139,6 +147,14 @@ int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total);
 int gm_sgl_support_begin(gm_graph_t *g);
 int gm_graph_support(gm_graph_t *g, uint32_t **d_support, int64_t *n);
 int gm_sgl_support_finish(gm_graph_t *g, uint64_t *total);
+/* The same exchange for the formula 4-motif solver (k = 4): only the support pass is shared between the
+ * shards; closed forms, 4-cycles and 4-cliques partition by the source range.
+ *   gm_motif_support_begin(g)            partial support pass of the shard's root range (asynchronous)
+ *   gm_graph_support(g, &d_sup, &n)      all-reduce in place (uint32, sum)
+ *   gm_motif_support_finish(g, counts)   the shard's six RAW sums; add the shards, then gm_motif_formula_finish
+ * Reference: src/motif/multigpu.cu:23-172 repeats the whole per-edge pass on every GPU's edge slice. */
+int gm_motif_support_begin(gm_graph_t *g);
+int gm_motif_support_finish(gm_graph_t *g, uint64_t *counts);
 /* MotifSolver, src/motif/gpu_base.cu:21-111.  Undirected input; k=3 -> counts[2] = {wedge, triangle}
  * (OMP order, motif/cpu_kernels/automine_base.h:13,18), k=4 -> counts[6] = {3-star, 4-path,
  * tailed-triangle, 4-cycle, diamond, 4-clique} (vertex-induced). */

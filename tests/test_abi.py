@@ -81,6 +81,14 @@ def test_bad_arguments_are_errors_not_exits():
         capi.set_option("no.such.option", "1")
     with pytest.raises(capi.GMError):
         capi.set_option("tc.algo", "bogus")
+    # every value include/gminer_b200.h documents is accepted, numeric options are range-checked
+    for v in ("auto", "rank", "hash", "hash_rev", "bs", "merge", "auto"):
+        capi.set_option("tc.algo", v)
+    for key, bad in (("sched.chunk", "-3"), ("sched.chunk", "x"), ("c4.small_max", "-2"), ("c4.cta_max", "1e3"),
+                     ("tc.gt2", "300"), ("sup.gt2", "0"), ("clique.gt1", "1024"), ("batch.ring", "7")):
+        with pytest.raises(capi.GMError):
+            capi.set_option(key, bad)
+    capi.set_option("sched.chunk", "0"); capi.set_option("c4.small_max", "-1")
     with pytest.raises(capi.GMError):
         capi.kclique_host(np.zeros(2, np.int64), np.zeros(0, np.int32), 9)
     with pytest.raises(capi.GMError):

@@ -41,7 +41,11 @@ def test_workloads_cover_baseline_configs():
     for w in ("tc", "clique4", "diamond", "motif4"):
         A.workload = w
         names[w] = bench.Workload(A, 1)
-    assert names["tc"].scale == 22 and "scale-22" in cfgs[1]
+    # default = the north_star Target size (TC on R-MAT scale 24 at every N); configs[1] is `--scale 22`
+    assert names["tc"].scale == 24 and "scale-24" in json.load(open(os.path.join(ROOT, "BASELINE.json")))["north_star"]
+    A.workload = "tc"; A.scale = 22
+    assert bench.Workload(A, 1).name == "tc_rmat_scale22" and "scale-22" in cfgs[1]
+    A.scale = 0
     assert names["clique4"].scale == 23 and "scale-23" in cfgs[2]
     assert bench.LJ_NV == 4_847_571 and "4.8M" in cfgs[3]
     assert bench.FR_NV == 65_608_366 and "65M" in cfgs[4]

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(__file__)
 KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
 GOLD = json.load(open(os.path.join(HERE, "golden", "rmat_counts.json")))
-TC_ALGOS = ["auto", "rank", "hash", "hash_rev", "bs"]
+TC_ALGOS = ["auto", "rank", "hash", "hash_rev", "bs", "merge"]
 
 
 @pytest.fixture(autouse=True)
@@ -515,3 +515,147 @@ def test_rectangle_both_algorithms(algo, citeseer, mico):
     ci = np.concatenate([np.delete(np.arange(n, dtype=np.int32), i) for i in range(n)])
     with capi.DeviceGraph(rp, ci, 0) as g:
         assert g.sgl("rectangle") == 3 * (n * (n - 1) * (n - 2) * (n - 3) // 24)
+
+
+# ---- round 2 ------------------------------------------------------------------------------------
+def _complete_dag(n):
+    """K_n already oriented: all degrees are equal, so the (degree, id) order is the id order"""
+    deg = np.arange(n - 1, -1, -1, dtype=np.int64)
+    rp = np.zeros(n + 1, np.int64); np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate([np.arange(i + 1, n, dtype=np.int32) for i in range(n)]) if n > 1 else np.zeros(0, np.int32)
+    return rp, ci, n - 1
+
+
+def test_tc_ranked_rows_of_every_size_class():
+    """rank.cu sorts the relabelled rows per size class: registers (d <= 32), a warp in shared memory (<= 256),
+    a CTA (<= 4096) and the segmented radix sort beyond; K_4500's DAG has rows of every length 0..4499."""
+    n = 4500
+    rp, ci, md = _complete_dag(n)
+    want = n * (n - 1) * (n - 2) // 6
+    for algo in ("rank", "merge", "hash_rev"):
+        capi.set_option("tc.algo", algo)
+        with capi.DeviceGraph(rp, ci, md) as g:
+            assert g.tc() == want, algo
+    # a scrambled labelling of the same DAG: ranks differ from ids, rows must really be sorted
+    rng = np.random.default_rng(5)
+    m = 1500
+    perm = rng.permutation(m).astype(np.int64)
+    rows = [[] for _ in range(m)]
+    for i in range(m):
+        for j in range(i + 1, m):
+            a, b = int(perm[i]), int(perm[j])
+            rows[min(a, b)].append(max(a, b))            # equal degrees: orientation by id
+    rp2 = np.zeros(m + 1, np.int64)
+    for i in range(m):
+        rp2[i + 1] = rp2[i] + len(rows[i])
+    ci2 = np.array([x for r in rows for x in sorted(r)], np.int32)
+    capi.set_option("tc.algo", "rank")
+    with capi.DeviceGraph(rp2, ci2, m - 1) as g:
+        assert g.tc() == m * (m - 1) * (m - 2) // 6
+
+
+def test_max_degree_is_recomputed_when_the_caller_value_is_stale(mico):
+    rp, ci, md = mico
+    orp, oci, omd = _dag(rp, ci)
+    capi.set_option("clique.algo", "list")                # per-warp frontiers are sized from max_degree
+    with capi.DeviceGraph(orp, oci, 1) as g:              # stale meta.txt value
+        assert g.info()["max_degree"] == omd
+        assert g.kclique(4) == KAT["mico"]["clique4"]
+
+
+@pytest.mark.parametrize("n,k", [(150, 6), (100, 7), (72, 8)])
+def test_kclique_dense_neighbourhood_beyond_32_bits(n, k):
+    """C(n,k) > 2^32 on one dense neighbourhood: the per-root / per-lane accumulators of the bit-matrix
+    kernel are 64-bit (round 1 held a root's whole sub-tree in uint32)"""
+    import math
+    rp, ci, md = _complete_dag(n)
+    want = math.comb(n, k)
+    assert want > 2 ** 32
+    with capi.DeviceGraph(rp, ci, md) as g:
+        assert g.kclique(k) == want
+
+
+def _need_devices(n):
+    if capi.device_count() < n:
+        pytest.skip(f"needs {n} CUDA devices")
+
+
+def test_host_entry_points_on_two_devices(citeseer, mico):
+    """gm_*_host(n_gpus=2): one host thread per device, sharded upload + NCCL all-gather, support exchange for
+    diamond and the formula 4-motif, NCCL all-reduce of the counts (solvers.cu run_shard)"""
+    _need_devices(2)
+    for name, (rp, ci, md) in (("citeseer", citeseer), ("mico", mico)):
+        k = KAT[name]
+        orp, oci, omd = _dag(rp, ci)
+        for rep in range(2):                              # second call: cached communicators and handle resources
+            assert capi.tc_host(orp, oci, omd, n_gpus=2) == k["tc"]
+            assert capi.kclique_host(orp, oci, 4, omd, n_gpus=2) == k["clique4"]
+            assert capi.sgl_host(rp, ci, "diamond", md, n_gpus=2) == k["diamond"]
+            assert capi.motif_host(rp, ci, 4, True, md, n_gpus=2) == k["motif4"]
+            assert capi.motif_host(rp, ci, 3, False, md, n_gpus=2) == k["motif3"]
+    rp, ci, md = citeseer
+    assert capi.sgl_host(rp, ci, "rectangle", md, n_gpus=2) == KAT["citeseer"]["rectangle"]
+    capi.set_option("sgl.algo", "list"); capi.set_option("motif.algo", "list")
+    assert capi.sgl_host(rp, ci, "diamond", md, n_gpus=2) == KAT["citeseer"]["diamond"]
+    assert capi.motif_host(rp, ci, 4, True, md, n_gpus=2) == KAT["citeseer"]["motif4"]
+
+
+def test_second_device_runs_every_kernel_family(citeseer):
+    """per-device shared-memory opt-in attributes (a process-wide "already set" flag broke device != 0)"""
+    _need_devices(2)
+    import torch
+    rp, ci, md = citeseer
+    orp, oci, omd = _dag(rp, ci)
+    with capi.DeviceGraph(orp, oci, omd, device=0) as g0, capi.DeviceGraph(orp, oci, omd, device=1) as g1:
+        assert g0.tc() == g1.tc() == KAT["citeseer"]["tc"]
+        assert g1.kclique(5) == KAT["citeseer"]["clique5"]
+    with capi.DeviceGraph(rp, ci, md, device=1) as g1:
+        assert g1.motif(4, formula=True) == KAT["citeseer"]["motif4"]
+        assert g1.sgl("diamond") == KAT["citeseer"]["diamond"]
+    a = np.unique(np.random.default_rng(0).integers(0, 4000, 900)).astype(np.int32)
+    b = np.unique(np.random.default_rng(1).integers(0, 4000, 700)).astype(np.int32)
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            pool = torch.from_numpy(np.concatenate([a, b, np.zeros(8, np.int32)])).cuda()
+            ao = torch.tensor([0], dtype=torch.int64, device="cuda"); bo = torch.tensor([len(a)], dtype=torch.int64, device="cuda")
+            al = torch.tensor([len(a)], dtype=torch.int32, device="cuda"); bl = torch.tensor([len(b)], dtype=torch.int32, device="cuda")
+            for algo in ("auto", "merge", "hash", "gallop", "bsearch"):
+                got = int(capi.intersect_batch(pool, ao, al, bo, bl, algo=algo).cpu()[0])
+                assert got == oracle.intersection_num(a, b), (dev, algo)
+
+
+def test_motif4_partitioned_support_exchange():
+    """gm_motif_support_begin / finish: shards enumerate the triangles of their root range only; summing the
+    support arrays (what the NCCL all-reduce does) and finishing every shard gives the whole-graph counts"""
+    import torch
+    rp, ci = _graph("rmat12")
+    nv = len(rp) - 1
+    want = oracle.motif_formula(rp, ci, 4)
+    bounds = [0, nv // 3, nv // 2, nv]
+    gs = [capi.DeviceGraph(rp, ci, 0) for _ in range(3)]
+    try:
+        sups = []
+        for g, b, e in zip(gs, bounds[:-1], bounds[1:]):
+            g.set_source_range(b, e)
+            g.motif_support_begin()
+            sups.append(g.support_tensor())
+        torch.cuda.synchronize()
+        total = sum(s.clone() for s in sups)
+        raw = [0] * 6
+        for g, s in zip(gs, sups):
+            s.copy_(total)
+            raw = [(x + y) & (2 ** 64 - 1) for x, y in zip(raw, g.motif_support_finish())]
+        assert capi.motif_formula_finish(4, raw) == want
+        # and again on the same handles (cached structures)
+        for g in gs:
+            g.motif_support_begin()
+        torch.cuda.synchronize()
+        total = sum(g.support_tensor().clone() for g in gs)
+        raw = [0] * 6
+        for g in gs:
+            g.support_tensor().copy_(total)
+            raw = [(x + y) & (2 ** 64 - 1) for x, y in zip(raw, g.motif_support_finish())]
+        assert capi.motif_formula_finish(4, raw) == want
+    finally:
+        for g in gs:
+            g.close()
