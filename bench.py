@@ -143,6 +143,7 @@ class Workload:
     def __init__(self, args, n):
         self.kind = k = args.workload
         self.n = n
+        self.options = dict(kv.split("=", 1) for kv in getattr(args, "option", []))
         self.oriented = k in ("tc", "clique4")
         self.scaling = "strong"                    # the same graph at every N, sharded by source-vertex range
         if self.oriented:
@@ -158,18 +159,23 @@ class Workload:
         self.metric = {"tc": "tc_edges_per_sec", "clique4": "kclique4_matches_per_sec",
                        "diamond": "sgl_diamond_matches_per_sec", "motif4": "motif4_matches_per_sec"}[k]
         self.unit = "edges/s" if k == "tc" else "matches/s"
-        self.prepare = {"tc": "tc", "clique4": "clique", "diamond": "sgl:diamond", "motif4": "motif"}[k]
+        self.prepare = {"tc": "tc", "clique4": "clique", "diamond": "sgl:diamond", "motif4": "motif:formula4"}[k]
         self.ncounts = 6 if k == "motif4" else 1
 
-    def build(self, torch, device):
+    def build(self, torch, device, on_device_generator=False):
         from graphminer_b200.rmat import shaped_graph
         if self.oriented:
             return build_graph(torch, self.scale, device, True)
         t0 = time.time()
-        if self.kind == "diamond":
-            rp, ci = shaped_graph(LJ_NV // self.div, LJ_SAMPLES // self.div, LJ_SEED, device=device)
+        nv, ns, seed, probs = ((LJ_NV, LJ_SAMPLES, LJ_SEED, (0.57, 0.19, 0.19, 0.05)) if self.kind == "diamond" else
+                               (FR_NV, FR_SAMPLES, FR_SEED, FR_PROBS))
+        if on_device_generator and device != "cpu":
+            # gm_gen_graph_*: the same graph bit for bit (tests/test_gpu_generator.py), but sized for the full
+            # 1.8 B-edge Friendster shape (the torch pipeline needs a dozen 14 GB temporaries there)
+            from graphminer_b200 import capi
+            rp, ci = capi.generate_graph(nv // self.div, ns // self.div, seed, probs, device=torch.device(device).index or 0)
         else:
-            rp, ci = shaped_graph(FR_NV // self.div, FR_SAMPLES // self.div, FR_SEED, probs=FR_PROBS, device=device)
+            rp, ci = shaped_graph(nv // self.div, ns // self.div, seed, probs=probs, device=device)
         if device != "cpu":
             torch.cuda.synchronize()
         log(f"[bench] {self.name}: nv={rp.numel() - 1} ne={ci.numel()} ({time.time() - t0:.1f}s)")
@@ -196,7 +202,7 @@ class Workload:
         try:
             return self.solve(g)
         finally:
-            capi.set_option(key, "auto")
+            capi.set_option(key, self.options.get(key, "auto"))
 
     def finish(self, counts):
         if self.kind == "motif4":
@@ -372,11 +378,9 @@ def run_ours(args):
     n = max(world, 1)
     wl = Workload(args, n)
 
-    rp, ci = wl.build(torch, dev)
+    rp, ci = wl.build(torch, dev, on_device_generator=True)
     nv, ne = rp.numel() - 1, ci.numel()
     max_deg = int((rp[1:] - rp[:-1]).max())
-    bounds = shard_bounds(torch, rp, ci, n, wl.kind)
-    b, e = bounds[rank], bounds[rank + 1]
 
     # an explicit (non-default) stream shared by torch, NCCL's stream dependencies and the library: a NULL
     # stream handle would make the library create its own stream, unordered against torch's
@@ -384,10 +388,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    for kv in args.option:
+        capi.set_option(*kv.split("=", 1))
     if wl.kind == "tc" and world > 1:
         capi.set_option("tc.shard", "dest")        # shard the edge set by destination: one table build per root overall
     g = capi.DeviceGraph.adopt(rp, ci, max_deg)
     g.set_stream(stream.cuda_stream)
+    # tc: destination weights of the ranked kernel (torch, plumbing); others: the scheduler.cc:14-19 estimate,
+    # computed on the device by the library (the 3.6 G-entry Friendster shape leaves no room for torch temporaries)
+    bounds = shard_bounds(torch, rp, ci, n, wl.kind) if wl.kind == "tc" else g.shard_bounds(n)
+    b, e = bounds[rank], bounds[rank + 1]
     g.set_source_range(b, e)
     g.prepare(wl.prepare)
     res_dev = torch.zeros(8, dtype=torch.int64, device=dev)
@@ -455,24 +465,29 @@ def run_ours(args):
     value = units / step_s
 
     # ---- end to end: HOST CSR in (pinned), count out; every copy inside the timed region ------------
-    h_rp = torch.empty(rp.shape, dtype=rp.dtype, pin_memory=True); h_rp.copy_(rp)
-    h_ci = torch.empty(ci.shape, dtype=ci.dtype, pin_memory=True); h_ci.copy_(ci)
-    torch.cuda.synchronize()
-    n_rp, n_ci = h_rp.numpy(), h_ci.numpy()
-    if world > 1:
+    if world == 1:
+        h_rp = torch.empty(rp.shape, dtype=rp.dtype, pin_memory=True); h_rp.copy_(rp)
+        h_ci = torch.empty(ci.shape, dtype=ci.dtype, pin_memory=True); h_ci.copy_(ci)
+        torch.cuda.synchronize()
+        n_rp, n_ci = h_rp.numpy(), h_ci.numpy()
+    else:
         # every rank copies 1/N of the host CSR over its own PCIe link; the slices are exchanged over NVLink
-        # (one all-gather each for rowptr and colidx) -- the H2D volume of the whole job is the CSR, once
+        # (one all-gather each for rowptr and colidx) -- the H2D volume of the whole job is the CSR, once.
+        # Only the rank's own slice is kept in (pinned) host memory.
         crp, cci = -(-(nv + 1) // world), -(-max(ne, 1) // world)
         d_rp_all = torch.empty(crp * world, dtype=rp.dtype, device=dev)
         d_ci_all = torch.empty(cci * world, dtype=ci.dtype, device=dev)
         rp_lo, rp_hi = min(rank * crp, nv + 1), min((rank + 1) * crp, nv + 1)
         ci_lo, ci_hi = min(rank * cci, ne), min((rank + 1) * cci, ne)
+        h_rp = torch.empty(rp_hi - rp_lo, dtype=rp.dtype, pin_memory=True); h_rp.copy_(rp[rp_lo:rp_hi])
+        h_ci = torch.empty(ci_hi - ci_lo, dtype=ci.dtype, pin_memory=True); h_ci.copy_(ci[ci_lo:ci_hi])
+        torch.cuda.synchronize()
 
     def e2e_step():
         if world == 1:
             return wl.host_solve(capi, n_rp, n_ci, max_deg)   # gm_*_host: upload + prepare + kernels + D2H (+ the formula fix-up)
-        d_rp_all[rp_lo:rp_hi].copy_(h_rp[rp_lo:rp_hi], non_blocking=True)
-        d_ci_all[ci_lo:ci_hi].copy_(h_ci[ci_lo:ci_hi], non_blocking=True)
+        d_rp_all[rp_lo:rp_hi].copy_(h_rp, non_blocking=True)
+        d_ci_all[ci_lo:ci_hi].copy_(h_ci, non_blocking=True)
         dist.all_gather_into_tensor(d_rp_all, d_rp_all[rank * crp:(rank + 1) * crp])
         dist.all_gather_into_tensor(d_ci_all, d_ci_all[rank * cci:(rank + 1) * cci])
         gg = capi.DeviceGraph.adopt(d_rp_all[:nv + 1], d_ci_all[:ne], max_deg)
@@ -514,6 +529,14 @@ def run_ours(args):
         c2 = [int(x) for x in c2.tolist()]
         assert c2 == counts, f"parity failure: timed solver {counts} != operator-API solver {c2}"
         parity["second_algorithm"] = {"algo": "tc.algo=bs (warp per edge, gm::intersect_num)", "range": [0, nv], "count": c2[0], "match": True}
+    if wl.kind != "tc" and world > 1 and rank == 0:
+        # no CPU leg at N>1 (spec): the timed solver against the operator-API solver on a small source range
+        n1 = min(nv, max(64, nv // 20000))
+        fast, second = gpu_range_counts(capi, g, wl, n1, nv)
+        g.set_source_range(b, e)
+        idx = range(wl.ncounts) if wl.kind != "motif4" else (0, 1, 2, 4)
+        assert all(fast[i] == second[i] for i in idx), f"parity failure on sources [0,{n1}): timed solver {fast}, operator-API solver {second}"
+        parity["second_algorithm"] = {"algo": "%s=%s" % wl.SECOND[wl.kind], "range": [0, n1], "match": True, "compared_indices": list(idx)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -653,6 +676,8 @@ def main():
     ap.add_argument("--no-stream", action="store_true", help="skip the streaming-intersection roofline leg")
     ap.add_argument("--scale", type=int, default=0, help="R-MAT scale (default: tc 24, clique4 23)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="gm_set_option before the run (experiments: tc.algo=merge, tc.gt2=256, ...)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the reference sample (the cpu_baseline leg)")
     ap.add_argument("--cpu-full-cap", type=float, default=75.0,
                     help="let the CPU reference finish the WHOLE graph when that is projected to take at most this long (full parity pin)")

@@ -34,7 +34,7 @@ SYMBOLS = [
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
     "gm_motif_formula_finish", "gm_last_stats", "gm_last_alg_bytes",
     "gm_tc_host", "gm_kclique_host", "gm_sgl_host", "gm_motif_host",
-    "gm_intersect_batch", "gm_allreduce_u64",
+    "gm_intersect_batch", "gm_allreduce_u64", "gm_gen_graph_begin", "gm_gen_graph_finish", "gm_graph_shard_bounds",
 ]
 
 
@@ -104,6 +104,9 @@ def lib():
     L.gm_intersect_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp,
                                      C.c_int, vp]
     L.gm_allreduce_u64.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.gm_gen_graph_begin.argtypes = [i32, i64, C.c_uint64, C.POINTER(C.c_uint32), C.c_int, vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gm_gen_graph_finish.argtypes = [vp, vp, vp]
+    L.gm_graph_shard_bounds.argtypes = [vp, C.c_int, _i32p]
     _lib = L
     return L
 
@@ -323,6 +326,12 @@ class DeviceGraph:
         check(f(self._h, k, out))
         return [int(x) for x in out[: (2 if k == 3 else 6)]]
 
+    def shard_bounds(self, n):
+        """work-balanced contiguous source ranges computed on the device (gm_host_shard_bounds semantics)"""
+        b = np.empty(n + 1, dtype=np.int32)
+        check(lib().gm_graph_shard_bounds(self._h, n, b))
+        return [int(x) for x in b]
+
     def last_stats(self):
         ms, n = C.c_float(0), C.c_int(0)
         check(lib().gm_last_stats(self._h, C.byref(ms), C.byref(n)))
@@ -368,6 +377,27 @@ def motif_host(rowptr, colidx, k, formula=False, max_degree=0, n_gpus=1):
     out = np.zeros(8, dtype=np.uint64)
     check(lib().gm_motif_host(rp, _pad(ci), nv, len(ci), int(max_degree), k, int(formula), n_gpus, out))
     return [int(x) for x in out[: (2 if k == 3 else 6)]]
+
+
+# ---- on-device synthetic graphs (bit-identical to rmat.py; sized for the 1.8 B-edge Friendster shape) ----
+def generate_graph(nv, n_samples, seed, probs=(0.57, 0.19, 0.19, 0.05), device=0):
+    """-> (rowptr int64[nv+1], colidx int32[ne]) torch CUDA tensors"""
+    import torch
+    a, b, c, _ = probs
+    th = (C.c_uint32 * 3)(int(a * 65536), int((a + b) * 65536), int((a + b + c) * 65536))
+    gen, ne = C.c_void_p(), C.c_int64(0)
+    dev = torch.device("cuda", device)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(lib().gm_gen_graph_begin(int(nv), int(n_samples), int(seed) & (2 ** 64 - 1), th, device, stream, C.byref(gen), C.byref(ne)))
+        try:
+            rp = torch.empty(nv + 1, dtype=torch.int64, device=dev)
+            ci = torch.empty(max(ne.value, 1), dtype=torch.int32, device=dev)[: ne.value]
+        except Exception:
+            lib().gm_gen_graph_finish(gen, None, None)
+            raise
+        check(lib().gm_gen_graph_finish(gen, rp.data_ptr(), ci.data_ptr() if ne.value else None))
+    return rp, ci
 
 
 # ---- batched operators on torch CUDA tensors ----

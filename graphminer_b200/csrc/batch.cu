@@ -49,6 +49,67 @@ __global__ void __launch_bounds__(256) batch_bsearch_kernel(BatchArgs p) {
   }
 }
 
+// ---- bounded / except / difference counts on the streaming pipeline --------------------------------------
+// Every counting operator reduces to |a' ∩ b'| on lists truncated at the bound plus O(log n) corrections:
+//   |{x ∈ a∩b : x < u}|              = |a' ∩ b'|,  a' = {x ∈ a : x < u}  (a prefix: lists are sorted)
+//   ... and x != anc [, anc2]        = |a' ∩ b'| - [anc ∈ a' ∩ b'] [- [anc2 ∈ a' ∩ b']]
+//   |{x ∈ a \ b \ {anc} : x < u}|    = |a'| - |a' ∩ b'| - [anc ∈ a' and anc ∉ b']
+// so set_difference.cuh:20-201 and the bounded forms of set_intersect.cuh:392-503 run through the same
+// TMA-staged merge-path / galloping cores as the plain count: a pre-pass truncates the lengths (one thread
+// per pair, two binary searches), the ring pipeline counts, a post-pass applies the corrections.
+__global__ void __launch_bounds__(256) batch_truncate_kernel(BatchArgs p, int32_t *ta, int32_t *tb) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= p.npairs) return;
+  const vidType u = p.bound[i];
+  ta[i] = lower_bound(p.pool + p.a_off[i], vidType(p.a_len[i]), u);
+  tb[i] = lower_bound(p.pool + p.b_off[i], vidType(p.b_len[i]), u);
+}
+template <int OP>
+__global__ void __launch_bounds__(256) batch_fixup_kernel(BatchArgs p, const int32_t *ta, const int32_t *tb) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= p.npairs) return;
+  const vidType *a = p.pool + p.a_off[i], *b = p.pool + p.b_off[i];
+  const vidType na = ta ? ta[i] : p.a_len[i], nb = tb ? tb[i] : p.b_len[i];
+  unsigned long long c = p.out[i];
+  auto in = [](const vidType *l, vidType n, vidType x) { return x >= 0 && binary_search(l, x, n); };
+  if (OP == GM_OP_INTERSECT_NUM_BOUND_EXCEPT || OP == GM_OP_INTERSECT_NUM_EXCEPT2) {
+    const vidType x = p.anc ? p.anc[i] : -1;
+    if (in(a, na, x) && in(b, nb, x)) c--;
+    if (OP == GM_OP_INTERSECT_NUM_EXCEPT2) {
+      const vidType y = p.anc2 ? p.anc2[i] : -1;
+      if (y != x && in(a, na, y) && in(b, nb, y)) c--;
+    }
+  } else if (OP == GM_OP_DIFFERENCE_NUM || OP == GM_OP_DIFFERENCE_NUM_BOUND) {
+    const vidType x = p.anc ? p.anc[i] : -1;
+    c = (unsigned long long)na - c - ((in(a, na, x) && !in(b, nb, x)) ? 1ull : 0ull);
+  }
+  p.out[i] = c;
+}
+
+static int launch_streaming_derived(int op, int algo, const BatchArgs &a, int sms, cudaStream_t s) {
+  const bool bounded = op == GM_OP_INTERSECT_NUM_BOUND || op == GM_OP_INTERSECT_NUM_BOUND_EXCEPT || op == GM_OP_DIFFERENCE_NUM_BOUND;
+  int32_t *ta = nullptr, *tb = nullptr;
+  const unsigned grid = unsigned((a.npairs + 255) / 256);
+  if (bounded) {
+    GM_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ta), sizeof(int32_t) * size_t(a.npairs) * 2, s));
+    tb = ta + a.npairs;
+    batch_truncate_kernel<<<grid, 256, 0, s>>>(a, ta, tb);
+  }
+  int rc = launch_batch_variant(algo, a.pool, a.a_off, bounded ? ta : a.a_len, a.b_off, bounded ? tb : a.b_len, a.npairs, a.out, sms, s);
+  if (rc == GM_OK) {
+    switch (op) {
+      case GM_OP_INTERSECT_NUM_BOUND: break;
+      case GM_OP_INTERSECT_NUM_BOUND_EXCEPT: batch_fixup_kernel<GM_OP_INTERSECT_NUM_BOUND_EXCEPT><<<grid, 256, 0, s>>>(a, ta, tb); break;
+      case GM_OP_INTERSECT_NUM_EXCEPT2: batch_fixup_kernel<GM_OP_INTERSECT_NUM_EXCEPT2><<<grid, 256, 0, s>>>(a, ta, tb); break;
+      case GM_OP_DIFFERENCE_NUM: batch_fixup_kernel<GM_OP_DIFFERENCE_NUM><<<grid, 256, 0, s>>>(a, ta, tb); break;
+      case GM_OP_DIFFERENCE_NUM_BOUND: batch_fixup_kernel<GM_OP_DIFFERENCE_NUM_BOUND><<<grid, 256, 0, s>>>(a, ta, tb); break;
+    }
+  }
+  if (ta) cudaFreeAsync(ta, s);
+  if (rc == GM_OK) GM_CUDA(cudaGetLastError());
+  return rc;
+}
+
 int set_batch_option(const char *key, int value) {
   BatchTuning &t = batch_tuning();
   const std::string k(key);
@@ -100,11 +161,14 @@ extern "C" int gm_intersect_batch(const int32_t *d_pool, const int64_t *d_a_off,
   // AUTO on the plain count takes the TMA pipeline with a per-pair merge/search choice when the pool
   // can be bulk-copied; every other op (and an unaligned pool) runs the operator API
   const bool pool_aligned = (reinterpret_cast<uintptr_t>(d_pool) & 15) == 0;
+  const bool counting = op >= GM_OP_INTERSECT_NUM && op <= GM_OP_DIFFERENCE_NUM_BOUND;
   if (algo == GM_ALGO_MERGE || algo == GM_ALGO_HASH || algo == GM_ALGO_GALLOP ||
-      (algo == GM_ALGO_AUTO && op == GM_OP_INTERSECT_NUM && pool_aligned)) {
-    if (op != GM_OP_INTERSECT_NUM) { set_error("gm_intersect_batch: algo %d implements GM_OP_INTERSECT_NUM only", algo); return GM_EUNSUPPORTED; }
-    return launch_batch_variant(algo, d_pool, d_a_off, d_a_len, d_b_off, d_b_len, npairs,
-                                reinterpret_cast<unsigned long long *>(d_out), sms, s);
+      (algo == GM_ALGO_AUTO && counting && pool_aligned)) {
+    if (!counting) { set_error("gm_intersect_batch: algo %d implements the counting operators only (op %d materialises)", algo, op); return GM_EUNSUPPORTED; }
+    if (op == GM_OP_INTERSECT_NUM)
+      return launch_batch_variant(algo, d_pool, d_a_off, d_a_len, d_b_off, d_b_len, npairs,
+                                  reinterpret_cast<unsigned long long *>(d_out), sms, s);
+    return launch_streaming_derived(op, algo, a, sms, s);
   }
   if (algo != GM_ALGO_AUTO && algo != GM_ALGO_BSEARCH) { set_error("gm_intersect_batch: unknown algo %d", algo); return GM_EINVAL; }
   int grid = int(std::min<int64_t>((npairs + 7) / 8, int64_t(sms) * 32));

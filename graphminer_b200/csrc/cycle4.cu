@@ -254,6 +254,61 @@ c4_cluster_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidTy
   if (lane == 0 && acc) atomicAdd(total, acc);
 }
 
+// tier 3 on LARGE graphs: the dense array of a cluster (4 bytes x |V|) no longer fits the L2 next to the others
+// (Friendster shape: 262 MB each), so a single cluster -- 16 of 148 SMs -- was left running (round-2 profile of
+// the shape / 4: 12.7 s per pass, superlinear).  Here every cluster owns an open-addressing table in global
+// memory sized by the ROOT (2^bits >= 2 W slots of {key, count}), independent of |V|: a few MB per root, so
+// all resident clusters stay L2-resident together.  Clearing = one coalesced sweep over the used slots.
+constexpr int kC4TabBits = 21;                       // slots per cluster: 2 * kC4MidMaxDefault
+__global__ void __launch_bounds__(kC4MidThreads)
+c4_cluster_hash_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
+                       const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
+                       const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *tabs,
+                       int *ticket, volatile int64_t *cur, AccType *total) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
+  const int cid = int(blockIdx.x) / csize;
+  const int lane = threadIdx.x & 31;
+  const int wid = crank * (kC4MidThreads / 32) + (threadIdx.x >> 5), nwarps = csize * (kC4MidThreads / 32);
+  uint32_t *keys = tabs + (size_t(cid) << (kC4TabBits + 1)), *cnts = keys + (size_t(1) << kC4TabBits);
+  AccType acc = 0;
+  while (true) {
+    cluster.sync();                                                 // previous root's slots cleared by every CTA
+    if (crank == 0 && threadIdx.x == 0) { cur[cid] = int64_t(atomicAdd(ticket, 1)); __threadfence(); }
+    cluster.sync();
+    const int64_t idx = cur[cid];
+    if (idx >= nroots) break;                                       // cluster-uniform
+    const vidType u = roots[idx];
+    const unsigned long long need = 2ull * W[u];
+    const int bits = min(kC4TabBits, max(10, 64 - __clzll((long long)(need - 1))));
+    const uint32_t mask = (1u << bits) - 1u;
+    auto insert = [&](uint32_t x) {
+      uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+      while (true) {
+        uint32_t k = *reinterpret_cast<volatile uint32_t *>(keys + h);
+        if (k == 0xffffffffu) k = atomicCAS(&keys[h], 0xffffffffu, x);
+        if (k == 0xffffffffu || k == x) { acc += atomicAdd(&cnts[h], 1u); break; }
+        h = (h + 1) & mask;
+      }
+    };
+    for (eidType e = inrow[u] + wid; e < inrow[u + 1]; e += nwarps) {
+      const uint2 r = incol[e];
+      const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+      for (int i = lane; i < nin; i += 32) insert(incol[vb + i].x);
+      const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
+      for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
+    }
+    cluster.sync();
+    for (uint32_t i = uint32_t(crank) * kC4MidThreads + threadIdx.x; i <= mask; i += uint32_t(csize) * kC4MidThreads) { keys[i] = 0xffffffffu; cnts[i] = 0u; }
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+__global__ void k_c4_init_tabs(uint32_t *tabs, size_t nwords) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nwords; i += size_t(gridDim.x) * blockDim.x)
+    tabs[i] = ((i >> kC4TabBits) & 1) ? 0u : 0xffffffffu;          // [keys | counts] per cluster
+}
+
 __global__ void __launch_bounds__(256)
 c4_heavy_kernel(vidType u, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
                 const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *L, AccType *total) {
@@ -325,8 +380,8 @@ void invalidate_range_structures_of_child(gm_graph *c) {
 
 void free_c4(gm_graph *c) {
   free_c4_lists(c);
-  dfree(c, c->c4_inrow); dfree(c, c->c4_incol); dfree(c, c->c4_dense); dfree(c, c->c4_cur);
-  c->c4_inrow = nullptr; c->c4_incol = nullptr; c->c4_dense = nullptr; c->c4_cur = nullptr;
+  dfree(c, c->c4_inrow); dfree(c, c->c4_incol); dfree(c, c->c4_dense); dfree(c, c->c4_cur); dfree(c, c->c4_tabs);
+  c->c4_inrow = nullptr; c->c4_incol = nullptr; c->c4_dense = nullptr; c->c4_cur = nullptr; c->c4_tabs = nullptr; c->c4_hash = false;
 }
 
 // c = the DAG child (ranked, full range); [fb, fe) = the parent's source range (original ids)
@@ -413,7 +468,16 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
       if (n > 0) { c->c4_clusters = n; c->c4_cluster_size = cs; }
     }
     int64_t arrays;
-    if (c->c4_clusters > 0) {
+    // dense arrays that cannot share the L2 (large |V|): per-cluster hash tables sized by the root instead
+    c->c4_hash = c->c4_clusters > 0 && int64_t(double(l2) * 0.8) / int64_t(arr_bytes) < 4 && mid_max <= (1ull << (kC4TabBits - 1)) &&
+                 options().c4_hash != 0;
+    if (options().c4_hash == 1 && c->c4_clusters > 0 && mid_max <= (1ull << (kC4TabBits - 1))) c->c4_hash = true;   // test hook
+    if (c->c4_hash) {
+      const size_t words = (size_t(c->c4_clusters) << (kC4TabBits + 1));
+      if (dmalloc(c, &c->c4_tabs, words * 4) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle cluster tables)"); return GM_ENOMEM; }
+      k_c4_init_tabs<<<c->num_sms * 8, 256, 0, c->stream>>>(c->c4_tabs, words);
+      arrays = 1;                                                   // the heavy tier keeps one dense array
+    } else if (c->c4_clusters > 0) {
       const int64_t fit = std::max<int64_t>(1, int64_t(double(l2) * 0.8) / int64_t(arr_bytes));
       c->c4_clusters = int(std::min<int64_t>(c->c4_clusters, fit));
       arrays = c->c4_clusters;
@@ -425,10 +489,10 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
     size_t free_b = 0, total_b = 0;
     GM_CUDA(cudaMemGetInfo(&free_b, &total_b));
     arrays = std::min<int64_t>(arrays, std::max<int64_t>(1, int64_t(double(free_b) * 0.5) / int64_t(arr_bytes)));
-    if (c->c4_clusters > 0) c->c4_clusters = int(arrays);
+    if (c->c4_clusters > 0 && !c->c4_hash) c->c4_clusters = int(arrays);
     c->c4_dense_ctas = int(arrays);
     if (dmalloc(c, &c->c4_dense, arr_bytes * size_t(arrays)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle counting arrays)"); return GM_ENOMEM; }
-    GM_CUDA(dmalloc(c, &c->c4_cur, sizeof(int64_t) * size_t(arrays)));
+    GM_CUDA(dmalloc(c, &c->c4_cur, sizeof(int64_t) * size_t(std::max<int64_t>(arrays, c->c4_clusters))));
     GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, arr_bytes * size_t(arrays), c->stream));
   }
   c->c4_fb = fb; c->c4_fe = fe; c->c4_lists_ready = true;
@@ -460,6 +524,12 @@ static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launch
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(c->c4_cluster_size); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (c->c4_hash) {
+      if (c->c4_cluster_size > 8) GM_CUDA(cudaFuncSetAttribute(c4_cluster_hash_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_hash_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const unsigned long long *)c->c4_W,
+                                 (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol, (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol,
+                                 c->c4_tabs, g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total));
+    } else
     GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol,
                                (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol, c->c4_dense, c->c4_dense_stride,
                                g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total));

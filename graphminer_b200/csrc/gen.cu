@@ -97,9 +97,51 @@ __global__ void k_rowptr_from_keys(const unsigned long long *__restrict__ keys, 
   rowptr[v] = lo;
 }
 
+// work estimate of scheduler.cc:14-19 per source vertex (+1), 8 lanes per vertex
+__global__ void __launch_bounds__(256) k_work_estimate(vidType nv, const eidType *__restrict__ rowptr, const vidType *__restrict__ colidx, double *w) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType v = vidType(t >> 3); const int sub = int(t & 7);
+  if (v >= nv) return;
+  const eidType b = rowptr[v], e = rowptr[v + 1], dv = e - b;
+  double s = 0;
+  for (eidType i = b + sub; i < e; i += 8) { const vidType u = colidx[i]; s += double(min(dv, rowptr[u + 1] - rowptr[u])); }
+  s += __shfl_xor_sync(kFullMask, s, 1); s += __shfl_xor_sync(kFullMask, s, 2); s += __shfl_xor_sync(kFullMask, s, 4);
+  if (sub == 0) w[v] = s + 1.0;
+}
+__global__ void k_find_cuts(vidType nv, const double *__restrict__ cw, int n, vidType *cuts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (i >= n) return;
+  const double target = cw[nv - 1] * double(i) / double(n);
+  vidType lo = 0, hi = nv;
+  while (lo < hi) { vidType mid = (lo + hi) >> 1; if (cw[mid] < target) lo = mid + 1; else hi = mid; }
+  cuts[i] = lo < nv ? lo + 1 : nv;                       // cw[v] = weight of [0, v]: the range ends behind v
+}
+
 }  // namespace gm
 
 using namespace gm;
+
+extern "C" int gm_graph_shard_bounds(gm_graph_t *g, int n, int32_t *bounds) {
+  if (!g || n < 1 || !bounds) { set_error("gm_graph_shard_bounds: bad arguments"); return GM_EINVAL; }
+  bounds[0] = 0; bounds[n] = g->nv;
+  if (n == 1 || g->nv == 0) { for (int i = 1; i < n; i++) bounds[i] = g->nv; return GM_OK; }
+  GM_CUDA(cudaSetDevice(g->device));
+  double *w = nullptr; vidType *cuts = nullptr;
+  GM_CUDA(dmalloc(g, &w, sizeof(double) * size_t(g->nv)));
+  GM_CUDA(dmalloc(g, &cuts, sizeof(vidType) * size_t(n + 1)));
+  k_work_estimate<<<unsigned((int64_t(g->nv) * 8 + 255) / 256), 256, 0, g->stream>>>(g->nv, g->d_rowptr, g->d_colidx, w);
+  size_t tmp = 0;
+  GM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp, w, w, int64_t(g->nv), g->stream));
+  GM_TRY(ensure_scratch(g, tmp));
+  GM_CUDA(cub::DeviceScan::InclusiveSum(g->d_scratch, tmp, w, w, int64_t(g->nv), g->stream));
+  k_find_cuts<<<(n + 255) / 256, 256, 0, g->stream>>>(g->nv, w, n, cuts);
+  std::vector<vidType> h(size_t(n) + 1, 0);
+  GM_CUDA(cudaMemcpyAsync(h.data(), cuts, sizeof(vidType) * size_t(n + 1), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  GM_CUDA(dfree(g, w)); GM_CUDA(dfree(g, cuts));
+  for (int i = 1; i < n; i++) bounds[i] = std::min<int32_t>(g->nv, std::max<int32_t>(h[size_t(i)], bounds[i - 1]));
+  return GM_OK;
+}
 
 struct gm_gen {
   int device = 0; cudaStream_t stream = nullptr;

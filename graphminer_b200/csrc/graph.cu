@@ -190,7 +190,7 @@ int ensure_aligned(gm_graph *g) {
   uint32_t total_units = 0;
   GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  if ((uint64_t(g->ne) + 3ull * uint64_t(nv)) / 4 >= (1ull << 32)) { dfree(g, units); set_error("graph too large for 32-bit aligned offsets"); return GM_EUNSUPPORTED; }
+  if ((uint64_t(g->ne) + 3ull * uint64_t(nv)) >= (1ull << 32)) { dfree(g, units); set_error("graph too large for 32-bit aligned element offsets"); return GM_EUNSUPPORTED; }
   g->acol_len = int64_t(total_units) * 4;
   GM_CUDA(dmalloc(g, &g->d_vinfo, sizeof(uint2) * size_t(nv > 0 ? nv : 1)));
   GM_CUDA(dmalloc(g, &g->d_acol, sizeof(vidType) * size_t(g->acol_len > 0 ? g->acol_len : 4)));
@@ -558,6 +558,12 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "tc.shard") {
     if (v != "source" && v != "dest") { set_error("tc.shard: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_shard = v;
+  } else if (k == "c4.hash") {
+    if (v != "-1" && v != "0" && v != "1") { set_error("c4.hash: -1 (auto), 0 or 1"); return GM_EINVAL; }
+    options().c4_hash = atoi(value);
+  } else if (k == "tc.pipe") {
+    if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
+    options().tc_pipe = v == "1";
   } else if (k == "tc.gt2") {
     int t = atoi(value);
     if (t != 256 && t != 512) { set_error("tc.gt2: 256 or 512"); return GM_EINVAL; }

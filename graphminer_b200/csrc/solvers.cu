@@ -53,8 +53,9 @@ int gm_graph_prepare(gm_graph_t *g, const char *what) {
   if (w == "sgl:rectangle" && options().sgl_algo != "list") { bool ok = false; GM_TRY(prepare_rectangle_fast(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
   else if (w == "sgl:diamond" && options().sgl_algo != "list") { bool ok = false; GM_TRY(prepare_diamond_support(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
   else if (w.rfind("sgl", 0) == 0 || w == "all") GM_TRY(ensure_coo(g, 1));
-  if (w == "motif" || w == "all") { GM_TRY(ensure_coo(g, 0)); GM_TRY(ensure_coo(g, 1)); }
-  if (w != "tc" && w != "clique" && w != "motif" && w != "all" && w.rfind("sgl", 0) != 0) { set_error("gm_graph_prepare: unknown target '%s'", what); return GM_EINVAL; }
+  if (w == "motif:formula4" && options().motif_algo != "list") { bool ok = false; GM_TRY(prepare_motif4_fast(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
+  else if (w.rfind("motif", 0) == 0 || w == "all") { GM_TRY(ensure_coo(g, 0)); GM_TRY(ensure_coo(g, 1)); }
+  if (w != "tc" && w != "clique" && w.rfind("motif", 0) != 0 && w != "all" && w.rfind("sgl", 0) != 0) { set_error("gm_graph_prepare: unknown target '%s'", what); return GM_EINVAL; }
   return GM_OK;
 }
 

@@ -119,42 +119,92 @@ struct WallTimer {
 }  // namespace gm
 
 // ---- the four solver symbols -------------------------------------------------------------------------
+// One GPU: exactly the reference's timed region -- the graph is copied and its task lists are built BEFORE the
+// timer starts (GraphGPU gg(g); gg.init_edgelist(g): triangle/gpu_base.cu:33-35), the timer brackets the solver
+// kernels (gpu_base.cu:54-65; here: CUDA events on the launch stream, gm_last_stats).  The end-to-end time of the
+// whole call is printed on an extra line.  Several GPUs: the host entry point (placement + pass + reduction).
+namespace gm {
+template <typename Solve>
+inline int run_timed(Graph &g, int n_gpu, const char *prepare, const char *tag, Solve solve, double *seconds) {
+  warm_devices(n_gpu);
+  WallTimer t;
+  gm_graph_t *h = nullptr;
+  int rc = gm_graph_upload(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), 0, &h);
+  if (rc == GM_OK) rc = gm_graph_prepare(h, prepare);
+  if (rc == GM_OK) rc = solve(h);
+  float ms = 0.f; int launches = 0;
+  if (rc == GM_OK) rc = gm_last_stats(h, &ms, &launches);
+  gm_graph_free(h);
+  if (rc != GM_OK) return rc;
+  *seconds = double(ms) / 1e3;
+  std::cout << "runtime [" << tag << "] = " << *seconds << " sec\n";
+  std::cout << "end-to-end (upload + preparation + " << launches << " kernel launches) = " << t.seconds() << " sec\n";
+  return GM_OK;
+}
+}  // namespace gm
+
 inline void TCSolver(gm::Graph &g, uint64_t &total, int n_gpu, int /*chunk_size*/) {
-  gm::warm_devices(n_gpu);
-  gm::WallTimer t;
-  gm::die_on(gm_tc_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), n_gpu, &total), "TCSolver");
-  double s = t.seconds();
-  std::cout << "runtime [gpu_base] = " << s << " sec\n";
+  double s = 0;
+  if (n_gpu <= 1) {
+    gm::die_on(gm::run_timed(g, n_gpu, "tc", "gpu_base", [&](gm_graph_t *h) { return gm_tc(h, &total); }, &s), "TCSolver");
+  } else {
+    gm::warm_devices(n_gpu);
+    gm::WallTimer t;
+    gm::die_on(gm_tc_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), n_gpu, &total), "TCSolver");
+    s = t.seconds();
+    std::cout << "runtime [gpu_base] = " << s << " sec\n";
+  }
   std::cout << "throughput = " << double(g.E()) / s / 1e9 << " billion Traversed Edges Per Second (TEPS)\n";
 }
 
 inline void CliqueSolver(gm::Graph &g, int k, uint64_t &total, int n_gpu, int /*chunk_size*/) {
-  gm::warm_devices(n_gpu);
-  gm::WallTimer t;
-  int rc = gm_kclique_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), k, n_gpu, &total);
+  int rc; double s = 0;
+  if (n_gpu <= 1) {
+    rc = (k < 3 || k > 8) ? GM_EUNSUPPORTED
+                          : gm::run_timed(g, n_gpu, "clique", "gpu_base", [&](gm_graph_t *h) { return gm_kclique(h, k, &total); }, &s);
+  } else {
+    gm::warm_devices(n_gpu);
+    gm::WallTimer t;
+    rc = gm_kclique_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), k, n_gpu, &total);
+    if (rc == GM_OK) std::cout << "runtime [gpu_base] = " << t.seconds() << " sec\n";
+  }
   if (rc == GM_EUNSUPPORTED) { std::cout << "Not supported right now\n"; total = 0; return; }   // clique/gpu_base.cu:69-71
   gm::die_on(rc, "CliqueSolver");
-  std::cout << "runtime [gpu_base] = " << t.seconds() << " sec\n";
 }
 
 inline void SglSolver(gm::Graph &g, gm::Pattern &p, uint64_t &total, int n_gpu, int /*chunk_size*/) {
-  gm::warm_devices(n_gpu);
-  gm::WallTimer t;
-  int rc = gm_sgl_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), p.get_name().c_str(), n_gpu, &total);
+  int rc; double s = 0;
+  const std::string name = p.get_name();
+  if (n_gpu <= 1) {
+    const bool known = name == "diamond" || name == "rectangle" || name == "4cycle" || name == "house" || name == "pentagon";
+    rc = !known ? GM_EUNSUPPORTED
+                : gm::run_timed(g, n_gpu, ("sgl:" + name).c_str(), "cuda_base", [&](gm_graph_t *h) { return gm_sgl(h, name.c_str(), &total); }, &s);
+  } else {
+    gm::warm_devices(n_gpu);
+    gm::WallTimer t;
+    rc = gm_sgl_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), name.c_str(), n_gpu, &total);
+    if (rc == GM_OK) std::cout << "runtime [cuda_base] = " << t.seconds() << " sec\n";
+  }
   if (rc == GM_EUNSUPPORTED) { std::cout << "Not implemented\n"; total = 0; return; }          // sgl/omp_base.cc:52-54
   gm::die_on(rc, "SglSolver");
-  std::cout << "runtime [cuda_base] = " << t.seconds() << " sec\n";
 }
 
 inline void MotifSolverImpl(gm::Graph &g, int k, std::vector<uint64_t> &accum, int n_gpu, int formula) {
-  gm::warm_devices(n_gpu);
-  gm::WallTimer t;
   uint64_t c[8] = {0};
-  int rc = gm_motif_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), k, formula, n_gpu, c);
+  int rc; double s = 0;
+  if (n_gpu <= 1) {
+    rc = (k != 3 && k != 4) ? GM_EUNSUPPORTED
+                            : gm::run_timed(g, n_gpu, formula && k == 4 ? "motif:formula4" : "motif", "cuda_base",
+                                            [&](gm_graph_t *h) { return formula ? gm_motif_formula(h, k, c) : gm_motif(h, k, c); }, &s);
+  } else {
+    gm::warm_devices(n_gpu);
+    gm::WallTimer t;
+    rc = gm_motif_host(g.out_rowptr(), g.out_colidx(), g.V(), g.E(), g.get_max_degree(), k, formula, n_gpu, c);
+    if (rc == GM_OK) std::cout << "runtime [cuda_base] = " << t.seconds() << " sec\n";
+  }
   if (rc == GM_EUNSUPPORTED) { std::cout << "Not supported right now\n"; return; }              // motif/gpu_base.cu:99-101
   gm::die_on(rc, "MotifSolver");
   for (size_t i = 0; i < accum.size() && i < 8; i++) accum[i] = c[i];
-  std::cout << "runtime [cuda_base] = " << t.seconds() << " sec\n";
 }
 #ifdef GM_MOTIF_FORMULA
 inline void MotifSolver(gm::Graph &g, int k, std::vector<uint64_t> &accum, int n_gpu, int) { MotifSolverImpl(g, k, accum, n_gpu, 1); }

@@ -22,6 +22,9 @@ struct GroupCfg {
   static constexpr int kCtaThreads = GT < 256 ? 256 : GT;
   static constexpr int kGroupsPerCta = kCtaThreads / GT;
   static constexpr int kWarpsPerGroup = GT / 32;
+  // resident CTAs the register allocation must allow: 1536 threads per SM for the two main classes (the
+  // prefetching stream loop holds two blocks of elements in registers: ~42 registers per thread)
+  static constexpr int kMinCtas = GT == 256 ? 8 : GT == 512 ? 4 : 1;
 };
 
 template <int GT>
@@ -60,29 +63,68 @@ __device__ __forceinline__ void probe_l1(const RowTable &tab, uint32_t s1, uint3
       : "+r"(c), "+r"(px), "+r"(np) : "r"(tw), "r"(x));
 }
 
-__device__ __forceinline__ uint32_t stream_probe(const RowTable &tab, uint32_t s1, const vidType *list, int len, int lane) {
+// probes of one block of up to 128 streamed elements (4 per lane); `left` = elements from the block start
+__device__ __forceinline__ uint32_t probe_block(const RowTable &tab, uint32_t s1, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, int left) {
+  uint32_t c = 0, px = 0, np = 0;
+  probe_l1(tab, s1, x0, c, px, np);
+  probe_l1(tab, s1, x1, c, px, np);
+  if (left > 64) {                                                 // warp-uniform
+    probe_l1(tab, s1, x2, c, px, np);
+    probe_l1(tab, s1, x3, c, px, np);
+  }
+  if (__any_sync(kFullMask, np != 0)) {
+    if (np == 1) {
+      c += tab.probe2(px);
+    } else if (np > 1) {                                            // two flagged slots in one lane: ~0.4 % of the lanes
+      const uint32_t xs[4] = {x0, x1, x2, x3};
+      #pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (RowTable::needs_l2(tab.probe1(s1, xs[u]), xs[u])) c += tab.probe2(xs[u]);
+    }
+  }
+  return c;
+}
+
+// Stream the rows (suffixes) of up to 32 partners -- lane j holds {element offset, length} of partner j -- and
+// count table hits.  Warp-collective.  The rows are cut into blocks of 128 elements and the loads of block
+// k+1 are issued BEFORE block k is probed, across partner boundaries: most suffixes are shorter than one
+// block, so a loop per partner leaves a single set of loads in flight per warp and the warp waits out the
+// full global-memory latency once per partner (the round-1 profile's 31-34 % long-scoreboard stalls).
+__device__ __forceinline__ uint32_t stream_partners(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane) {
   uint32_t c = 0;
-  const vidType *p = list + lane;
-  for (int r = len - lane; r > -lane; r -= 128, p += 128) {        // r - (-lane) = elements left in the row
-    const uint32_t x0 = ldg_or_pad(p, r > 0), x1 = ldg_or_pad(p + 32, r > 32);
-    const uint32_t x2 = ldg_or_pad(p + 64, r > 64), x3 = ldg_or_pad(p + 96, r > 96);
-    uint32_t px = 0, np = 0;
-    probe_l1(tab, s1, x0, c, px, np);
-    probe_l1(tab, s1, x1, c, px, np);
-    if (r + lane > 64) {                                           // warp-uniform
-      probe_l1(tab, s1, x2, c, px, np);
-      probe_l1(tab, s1, x3, c, px, np);
+  int j = 0;
+  uint32_t off = __shfl_sync(kFullMask, pv.x, 0);
+  int rem = int(__shfl_sync(kFullMask, pv.y, 0));
+  const vidType *p = acol + off + lane;
+  uint32_t y0 = ldg_or_pad(p, rem > lane), y1 = ldg_or_pad(p + 32, rem > lane + 32);
+  uint32_t y2 = ldg_or_pad(p + 64, rem > lane + 64), y3 = ldg_or_pad(p + 96, rem > lane + 96);
+  while (true) {
+    const uint32_t x0 = y0, x1 = y1, x2 = y2, x3 = y3;
+    const int left = rem;
+    rem -= 128; off += 128;
+    if (rem <= 0 && ++j < np) { off = __shfl_sync(kFullMask, pv.x, j); rem = int(__shfl_sync(kFullMask, pv.y, j)); }
+    const bool more = j < np;                                        // warp-uniform
+    if (more) {
+      p = acol + off + lane;
+      y0 = ldg_or_pad(p, rem > lane); y1 = ldg_or_pad(p + 32, rem > lane + 32);
+      y2 = ldg_or_pad(p + 64, rem > lane + 64); y3 = ldg_or_pad(p + 96, rem > lane + 96);
     }
-    if (__any_sync(kFullMask, np != 0)) {
-      if (np == 1) {
-        c += tab.probe2(px);
-      } else if (np > 1) {                                          // two flagged slots in one lane: ~0.4 % of the lanes
-        const uint32_t xs[4] = {x0, x1, x2, x3};
-        #pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (RowTable::needs_l2(tab.probe1(s1, xs[u]), xs[u])) c += tab.probe2(xs[u]);
-      }
-    }
+    c += probe_block(tab, s1, x0, x1, x2, x3, left);
+    if (!more) break;
+  }
+  return c;
+}
+
+// the same without the cross-partner prefetch (tc.pipe=0: A/B switch for profiling)
+__device__ __forceinline__ uint32_t stream_partners_simple(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane) {
+  uint32_t c = 0;
+  for (int j = 0; j < np; j++) {
+    const uint32_t off = __shfl_sync(kFullMask, pv.x, j);
+    const int len = int(__shfl_sync(kFullMask, pv.y, j));
+    const vidType *p = acol + off + lane;
+    for (int rem = len; rem > 0; rem -= 128, p += 128)
+      c += probe_block(tab, s1, ldg_or_pad(p, rem > lane), ldg_or_pad(p + 32, rem > lane + 32),
+                       ldg_or_pad(p + 64, rem > lane + 64), ldg_or_pad(p + 96, rem > lane + 96), rem);
   }
   return c;
 }
@@ -98,8 +140,8 @@ __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, c
 // MODE 1: partners = in-neighbours (prow/pcol = reverse adjacency)
 // MODE 2: RANKED graph (rank.cu): g's aligned view holds the rank-relabelled rows, partners are
 //         records {element offset of the row suffix to stream, its length} in prec
-template <int GT, int MAXB1, int CAP, int MODE>
-__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads)
+template <int GT, int MAXB1, int CAP, int MODE, bool PIPE>
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
 tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
                const uint2 *__restrict__ prec,
                const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
@@ -156,11 +198,17 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
         uint2 pv = make_uint2(0, 0);
         if (q < mine) pv = MODE == 2 ? __ldg(R + q * W + gwarp) : g.info(__ldg(P + q * W + gwarp));
         int np = min(32, mine - pb);
-        for (int j = 0; j < np; j++) {
-          uint32_t off = __shfl_sync(kFullMask, pv.x, j);
-          int len = int(__shfl_sync(kFullMask, pv.y, j));
-          const vidType *list = g.d_acol + (MODE == 2 ? size_t(off) : (size_t(off) << 2));
-          c += fits ? stream_probe(tab, s1, list, len, lane) : stream_bsearch(rrow, d, list, len, lane);
+        if (fits) {
+          // ranked rows: pv = {element offset, length} of the suffix; whole aligned rows: offsets in 16-byte units
+          const uint2 ev = MODE == 2 ? pv : make_uint2(pv.x << 2, pv.y);
+          c += PIPE ? stream_partners(tab, s1, g.d_acol, ev, np, lane) : stream_partners_simple(tab, s1, g.d_acol, ev, np, lane);
+        } else {
+          for (int j = 0; j < np; j++) {
+            uint32_t off = __shfl_sync(kFullMask, pv.x, j);
+            int len = int(__shfl_sync(kFullMask, pv.y, j));
+            const vidType *list = g.d_acol + (MODE == 2 ? size_t(off) : (size_t(off) << 2));
+            c += stream_bsearch(rrow, d, list, len, lane);
+          }
         }
       }
       acc += c;
@@ -260,7 +308,7 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
   const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
-  auto kern = tc_hash_kernel<GT, MAXB1, CAP, MODE>;
+  auto kern = options().tc_pipe ? tc_hash_kernel<GT, MAXB1, CAP, MODE, true> : tc_hash_kernel<GT, MAXB1, CAP, MODE, false>;
   size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
   GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int occ = 0;

@@ -41,6 +41,31 @@ struct GraphGPU {
   __device__ eidType edge_begin(vidType v) const { return d_rowptr[v]; }
   __device__ eidType edge_end(vidType v) const { return d_rowptr[v + 1]; }
 
+  // ---- vertex-id flavoured intersections (graph_gpu.h:213-323).  All return a PER-THREAD partial count of
+  // |N(src) ∩ N(dst)|: keys of the shorter list are dealt to the lanes of the warp (warp_*) or to the threads
+  // of the CTA (cta_*; every thread of the block must call, blockDim.x <= 1024).  The _cache forms search
+  // through pivots: here the warp keeps them in registers (WarpIndex) and the CTA in a shared table with
+  // barriers on both sides (the reference's cta_intersect_cache reuses its table without the trailing barrier).
+  __device__ vidType warp_intersect(vidType src, vidType dst) const {
+    return intersect_num(N(src), get_degree(src), N(dst), get_degree(dst));
+  }
+  __device__ vidType warp_intersect_cache(vidType src, vidType dst) const { return warp_intersect(src, dst); }
+  __device__ vidType cta_intersect_cache(vidType src, vidType dst) const {
+    __shared__ vidType gm_cta_pivots[1024];
+    const vidType *keys = N(src), *srch = N(dst);
+    vidType nk = get_degree(src), ns = get_degree(dst);
+    if (nk > ns) { const vidType *t = keys; keys = srch; srch = t; const vidType tn = nk; nk = ns; ns = tn; }
+    if (nk == 0) return 0;                                   // block-uniform
+    gm_cta_pivots[threadIdx.x] = srch[(long long)threadIdx.x * ns / blockDim.x];
+    __syncthreads();
+    vidType count = 0;
+    for (vidType i = threadIdx.x; i < nk; i += blockDim.x)
+      count += detail::search_2phase(srch, gm_cta_pivots, int(blockDim.x), keys[i], ns) ? 1 : 0;
+    __syncthreads();                                         // the table is free for the next call
+    return count;
+  }
+  __device__ vidType cta_intersect(vidType src, vidType dst) const { return cta_intersect_cache(src, dst); }
+
   // aligned view
   __device__ uint2 info(vidType v) const { return __ldg(d_vinfo + v); }
   __device__ const vidType *NA(uint2 vi) const { return d_acol + (size_t(vi.x) << 2); }

@@ -105,11 +105,66 @@ struct WarpIndex {
   }
 };
 
-// Reference-compatible name: membership with an externally cached pivot table (search.cuh:53-78).
+// ---- the reference's remaining search names (search.cuh:15-121), same arguments and results ----------
+// strided linear search (search.cuh:15-25): `len` probes from bin[idx] with the given stride
+template <typename T = vidType>
+__device__ __forceinline__ int linear_search(T v, const T *bin, T len, T idx, T stride) {
+  for (T step = 0, i = idx; step < len; step++, i += stride) if (bin[i] == v) return 1;
+  return 0;
+}
+// membership in a sorted list whose deleted entries were overwritten with NEGATIVE values (search.cuh:41-51):
+// a negative probe sends the search to the left, exactly as the reference does
+template <typename T = vidType>
+__device__ __forceinline__ bool binary_search_enhanced(const T *list, T key, T size) {
+  int l = 0, r = int(size) - 1;
+  while (r >= l) {
+    const int mid = l + ((r - l) >> 1);
+    const T val = list[mid];
+    if (val == key) return true;
+    if (val >= 0 && val < key) l = mid + 1; else r = mid - 1;
+  }
+  return false;
+}
+// index of key, or of the first entry above it (search.cuh:108-121); 0 for an empty list
+template <typename T = vidType>
+__device__ __forceinline__ T binary_search_bound(const T *list, T key, T size) { return lower_bound(list, size, key); }
+
+namespace detail {
+// phase 1 over `np` cached pivots (pivot(i) = list[i * size / np]), phase 2 inside the bucket it selects
+template <typename T>
+__device__ __forceinline__ bool search_2phase(const T *list, const T *pivots, int np, T key, T size) {
+  if (size <= 0) return false;
+  int lo = 0, hi = np;                                   // largest i with pivot(i) <= key lies in [lo, hi)
+  if (pivots[0] > key) return false;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    const T y = pivots[mid];
+    if (y == key) return true;
+    if (y < key) lo = mid; else hi = mid;
+  }
+  if (pivots[lo] == key) return true;
+  long long b = (long long)lo * size / np + 1, e = (long long)(lo + 1) * size / np;   // bucket behind its pivot
+  while (b < e) {
+    const long long mid = (b + e) >> 1;
+    const T v = list[mid];
+    if (v == key) return true;
+    if (v < key) b = mid + 1; else e = mid;
+  }
+  return false;
+}
+}  // namespace detail
+
+// Reference names: membership with an externally cached pivot table (search.cuh:53-105).  `cache` is the
+// CTA's __shared__ array the caller filled as the reference does: per warp 32 pivots at
+// cache[warp_in_cta * 32 + i] = list[i * size / 32] (set_intersect.cuh:86-87), or for the _cta form
+// blockDim.x pivots cache[i] = list[i * size / blockDim.x] (graph_gpu.h:315).
 template <typename T = vidType>
 __device__ __forceinline__ bool binary_search_2phase(const T *list, const T *cache, T key, T size) {
-  (void)cache;
-  return binary_search(list, key, size);
+  return detail::search_2phase(list, cache + ((threadIdx.x >> 5) << 5), 32, key, size);
+}
+template <typename T = vidType>
+__device__ __forceinline__ bool binary_search_2phase_cta(const T *list, const T *cache, T key, T size) {
+  return detail::search_2phase(list, cache, int(blockDim.x), key, size);
 }
 
 namespace detail {

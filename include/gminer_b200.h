@@ -37,7 +37,8 @@ extern "C" {
 #define GM_EIO (-5)       /* file error */
 #define GM_ENCCL (-6)     /* NCCL error / library not loadable */
 
-typedef struct gm_graph gm_graph_t;   /* opaque device-resident graph (replaces class GraphGPU, include/graph_gpu.h:6-210) */
+typedef struct gm_graph gm_graph_t;
+typedef struct gm_gen gm_gen_t;       /* a generated edge set waiting to be written out as CSR (gm_gen_graph_*) */   /* opaque device-resident graph (replaces class GraphGPU, include/graph_gpu.h:6-210) */
 
 /* ---- library ---------------------------------------------------------------------------- */
 const char *gm_last_error(void);
@@ -59,9 +60,11 @@ int gm_device_init(int device);
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source
  *       (the reference's semantics, default) or by their destination (same total over a partition of
  *       the vertex set; keeps each root's table on one shard -- set before gm_graph_prepare),
- *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.gt2" = 256|512, "sup.gt2" =
+ *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.pipe" = 1|0 (cross-partner
+ *       prefetch in the TC stream loop), "tc.gt2" = 256|512, "sup.gt2" =
  *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
- *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers).
+ *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers), "c4.hash" = -1|0|1
+ *       (cluster tier on dense |V|-sized arrays or per-root hash tables; auto by |V|).
  *       Unknown key or out-of-range value -> GM_EINVAL.  Options are process-global: set them before the
  *       solver calls, not concurrently with them. */
 int gm_set_option(const char *key, const char *value);
@@ -123,7 +126,8 @@ int gm_graph_set_result_buffer(gm_graph_t *g, uint64_t *d_out);
 int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end);
 /* Build the auxiliary device structures a solver needs (padded 16-byte-aligned CSR, COO task list
  * = GraphGPU::init_edgelist graph_gpu.h:124-178, degree-binned work items) ahead of the timed
- * call.  what: "tc", "clique", "sgl:<pattern>", "motif", or "all".  Solvers call it lazily. */
+ * call.  what: "tc", "clique", "sgl:<pattern>", "motif" (task lists of the operator-API kernels),
+ * "motif:formula4" (DAG, supports, 4-cycle tiers of the fast formula path), or "all".  Solvers call it lazily. */
 int gm_graph_prepare(gm_graph_t *g, const char *what);
 int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, int *device);
 
@@ -220,6 +224,21 @@ int gm_intersect_batch(const int32_t *d_pool, const int64_t *d_a_off, const int3
                        int64_t npairs, int op, int algo, uint64_t *d_out,
                        int32_t *d_out_pool, const int64_t *d_out_off,
                        int device, void *cuda_stream);
+
+/* ---- synthetic inputs (bench / test infrastructure; the reference ships no generator) ---------------- */
+/* The R-MAT / "shaped" R-MAT workloads of SURVEY.md §8(d) generated ON THE DEVICE, bit-identical to
+ * graphminer_b200/rmat.py: n_samples Graph500-style pairs over the next power of two >= nv with rejection of
+ * ids >= nv, a seed-dependent id permutation, self-loops dropped, symmetrised, sorted, de-duplicated.
+ * thresholds = the cumulative quadrant probabilities {a, a+b, a+b+c} scaled to 2^16 (integers, so that host
+ * floating point cannot change the graph).  Two calls: _begin generates, sorts and de-duplicates the keys and
+ * reports ne; _finish writes rowptr (int64[nv+1]) and colidx (int32[ne]) into caller-provided DEVICE arrays
+ * in the reference's CSR layout (graph.cc:19-41) and frees the generator (NULL arrays: just free it). */
+int gm_gen_graph_begin(int32_t nv, int64_t n_samples, uint64_t seed, const uint32_t thresholds[3],
+                       int device, void *cuda_stream, gm_gen_t **gen, int64_t *ne);
+int gm_gen_graph_finish(gm_gen_t *gen, int64_t *d_rowptr, int32_t *d_colidx);
+/* Device-side twin of gm_host_shard_bounds(balance = 1) for a graph that only lives in HBM: n+1 boundaries of
+ * contiguous source ranges with equal sum of sum_{u in N(v)} min(d(v), d(u)) (scheduler.cc:14-19). */
+int gm_graph_shard_bounds(gm_graph_t *g, int n, int32_t *bounds);
 
 /* ---- multi-GPU reduction ------------------------------------------------------------------ */
 /* Sum `n` uint64 values across `n_gpus` device buffers with NCCL (ncclAllReduce, ncclUint64,

@@ -81,17 +81,21 @@ def test_intersect_num_all_variants(batch, algo):
     assert got.tolist() == want
 
 
-def test_counting_ops(batch):
+@pytest.mark.parametrize("algo", ["bsearch", "auto", "merge", "gallop", "hash"])
+def test_counting_ops(batch, algo):
+    """bounded / except / difference counts: the operator API (bsearch) and the streaming cores (merge-path,
+    galloping, hash behind the TMA pipeline: lists truncated at the bound + O(log n) corrections)"""
     P, B, A, A2 = batch["pairs"], batch["h_bound"], batch["h_anc"], batch["h_anc2"]
-    assert run(batch, "intersect_num_bound").tolist() == [oracle.intersection_num(a, b, upper=u) for (a, b), u in zip(P, B)]
-    assert run(batch, "intersect_num_bound_except").tolist() == [
+    assert run(batch, "intersect_num_bound", algo).tolist() == [oracle.intersection_num(a, b, upper=u) for (a, b), u in zip(P, B)]
+    assert run(batch, "intersect_num_bound_except", algo).tolist() == [
         oracle.intersection_num(a, b, upper=u, ancestors=(x,)) for (a, b), u, x in zip(P, B, A)]
-    assert run(batch, "intersect_num_except2").tolist() == [
+    assert run(batch, "intersect_num_except2", algo).tolist() == [
         oracle.intersection_num(a, b, ancestors=(x, y)) for (a, b), x, y in zip(P, A, A2)]
-    assert run(batch, "difference_num").tolist() == [oracle.difference_num(a, b, x) for (a, b), x in zip(P, A)]
-    assert run(batch, "difference_num_bound").tolist() == [
+    assert run(batch, "difference_num", algo).tolist() == [oracle.difference_num(a, b, x) for (a, b), x in zip(P, A)]
+    assert run(batch, "difference_num_bound", algo).tolist() == [
         oracle.difference_num(a, b, x, upper=u) for (a, b), u, x in zip(P, B, A)]
-    assert run(batch, "count_smaller").tolist() == [oracle.bounded(a, u) for (a, _), u in zip(P, B)]
+    if algo in ("bsearch", "auto"):
+        assert run(batch, "count_smaller", algo).tolist() == [oracle.bounded(a, u) for (a, _), u in zip(P, B)]
 
 
 @pytest.mark.parametrize("op", ["intersect_set", "intersect_set_bound", "difference_set", "difference_set_bound"])

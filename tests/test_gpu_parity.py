@@ -31,6 +31,7 @@ def _reset_options():
     capi.set_option("c4.small_max", -1)
     capi.set_option("c4.mid_max", -1)
     capi.set_option("c4.cta_max", -1)
+    capi.set_option("c4.hash", -1)
 
 
 def _graph(name):
@@ -442,11 +443,14 @@ def test_motif4_formula_both_algorithms(algo, citeseer, mico):
         assert g.motif(4, formula=True) == [0, 0, 0, 0, 0, 15]
 
 
+@pytest.mark.parametrize("hash_tier", [0, 1])
 @pytest.mark.parametrize("small_max,cta_max,mid_max", [(0, -1, -1), (0, 0, -1), (0, 0, 0), (16, 100, 300), (512, 600, 2000)])
-def test_motif4_cycle_tiers(small_max, cta_max, mid_max):
-    """the four 4-cycle tiers (warp table / CTA table / cluster on a dense array / whole-grid dense array)
-    must agree: thresholds are pushed down so that small graphs reach every code path"""
+def test_motif4_cycle_tiers(small_max, cta_max, mid_max, hash_tier):
+    """the four 4-cycle tiers (warp table / CTA table / cluster on a dense array or -- large graphs -- on per-root
+    hash tables / whole-grid dense array) must agree: thresholds are pushed down so that small graphs reach every
+    code path"""
     capi.set_option("motif.algo", "fast")
+    capi.set_option("c4.hash", hash_tier)
     capi.set_option("c4.small_max", small_max)
     capi.set_option("c4.cta_max", cta_max)
     capi.set_option("c4.mid_max", mid_max)
