@@ -483,38 +483,6 @@ def run_ours(args):
         h_ci = torch.empty(ci_hi - ci_lo, dtype=ci.dtype, pin_memory=True); h_ci.copy_(ci[ci_lo:ci_hi])
         torch.cuda.synchronize()
 
-    def e2e_step():
-        if world == 1:
-            return wl.host_solve(capi, n_rp, n_ci, max_deg)   # gm_*_host: upload + prepare + kernels + D2H (+ the formula fix-up)
-        d_rp_all[rp_lo:rp_hi].copy_(h_rp, non_blocking=True)
-        d_ci_all[ci_lo:ci_hi].copy_(h_ci, non_blocking=True)
-        dist.all_gather_into_tensor(d_rp_all, d_rp_all[rank * crp:(rank + 1) * crp])
-        dist.all_gather_into_tensor(d_ci_all, d_ci_all[rank * cci:(rank + 1) * cci])
-        gg = capi.DeviceGraph.adopt(d_rp_all[:nv + 1], d_ci_all[:ne], max_deg)
-        try:
-            gg.set_stream(stream.cuda_stream)
-            gg.set_source_range(b, e)
-            gg.set_result_buffer(res_dev)
-            return solve_sharded(gg)
-        finally:
-            gg.close()
-
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(2):
-        got = e2e_step()
-        assert got == counts, f"end-to-end path disagrees: {got} != {counts}"
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        got = e2e_step()
-    sync_all()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-    assert got == counts
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        del d_rp_all, d_ci_all
-    e2e_value = units / float(e2e_s)
-
     # ---- parity (outside the timed regions) -------------------------------------------------------
     # (1) the operator-API solver (the reference's warp-per-edge schedule) on the whole graph for TC;
     # (2) the reference's own CPU code on a source range [0,n1) -- the whole graph when it is fast enough --
@@ -533,7 +501,6 @@ def run_ours(args):
         # no CPU leg at N>1 (spec): the timed solver against the operator-API solver on a small source range
         n1 = min(nv, max(64, nv // 20000))
         fast, second = gpu_range_counts(capi, g, wl, n1, nv)
-        g.set_source_range(b, e)
         idx = range(wl.ncounts) if wl.kind != "motif4" else (0, 1, 2, 4)
         assert all(fast[i] == second[i] for i in idx), f"parity failure on sources [0,{n1}): timed solver {fast}, operator-API solver {second}"
         parity["second_algorithm"] = {"algo": "%s=%s" % wl.SECOND[wl.kind], "range": [0, n1], "match": True, "compared_indices": list(idx)}
@@ -564,8 +531,43 @@ def run_ours(args):
                   "reference_cpu_range" if parity["reference_cpu"] else
                   "second_algorithm" if parity["second_algorithm"] else "none")
 
+    # the timed handle goes before the end-to-end passes build their own (the Friendster-shaped graph leaves no
+    # room for two sets of auxiliary structures)
     g.close()
     del g, rp, ci
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        if world == 1:
+            return wl.host_solve(capi, n_rp, n_ci, max_deg)   # gm_*_host: upload + prepare + kernels + D2H (+ the formula fix-up)
+        d_rp_all[rp_lo:rp_hi].copy_(h_rp, non_blocking=True)
+        d_ci_all[ci_lo:ci_hi].copy_(h_ci, non_blocking=True)
+        dist.all_gather_into_tensor(d_rp_all, d_rp_all[rank * crp:(rank + 1) * crp])
+        dist.all_gather_into_tensor(d_ci_all, d_ci_all[rank * cci:(rank + 1) * cci])
+        gg = capi.DeviceGraph.adopt(d_rp_all[:nv + 1], d_ci_all[:ne], max_deg)
+        try:
+            gg.set_stream(stream.cuda_stream)
+            gg.set_source_range(b, e)
+            gg.set_result_buffer(res_dev)
+            return solve_sharded(gg)
+        finally:
+            gg.close()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2 if step_s < 2.0 else 1):
+        got = e2e_step()
+        assert got == counts, f"end-to-end path disagrees: {got} != {counts}"
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        got = e2e_step()
+    sync_all()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    assert got == counts
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        del d_rp_all, d_ci_all
+    e2e_value = units / float(e2e_s)
     torch.cuda.empty_cache()
     stream_rf = None
     if rank == 0 and world == 1 and not args.no_stream:

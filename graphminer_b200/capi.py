@@ -28,7 +28,7 @@ ALGOS = {"auto": 0, "bsearch": 1, "merge": 2, "hash": 3, "gallop": 4}
 SYMBOLS = [
     "gm_last_error", "gm_version", "gm_device_count", "gm_device_init", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
-    "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
+    "gm_host_alloc", "gm_host_free", "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
     "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_motif_support_begin", "gm_motif_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
     "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
@@ -71,6 +71,8 @@ def lib():
     L.gm_host_partition_part.argtypes = [i32, _i64p, _i32p, i32, i32, vp, vp, vp, C.POINTER(i32),
                                          C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     L.gm_host_shard_bounds.argtypes = [i32, _i64p, _i32p, C.c_int, C.c_int, _i32p]
+    L.gm_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.gm_host_free.argtypes = [vp]
     L.gm_host_read_meta.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]
     L.gm_host_read_graph.argtypes = [C.c_char_p, i32, i64, _i64p, _i32p]
     L.gm_host_write_graph.argtypes = [C.c_char_p, i32, i64, i32, _i64p, _i32p]
@@ -189,6 +191,23 @@ def read_graph(prefix: str):
     ci = np.empty(max(1, ne.value), dtype=np.int32)
     check(lib().gm_host_read_graph(prefix.encode(), nv.value, ne.value, rp, ci))
     return rp, ci[:ne.value], md.value
+
+
+def read_graph_pinned(prefix: str):
+    """Reference on-disk format read straight into page-locked arrays (gm_host_alloc).  Returns
+    (rowptr, colidx, max_degree, pinned); the arrays are numpy views that own their memory through a finaliser."""
+    import weakref
+    nv, ne, md = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+    check(lib().gm_host_read_meta(prefix.encode(), C.byref(nv), C.byref(ne), C.byref(md)))
+    out, pinned_all = [], True
+    for n, ct, dt in ((nv.value + 1, C.c_int64, np.int64), (max(ne.value, 1), C.c_int32, np.int32)):
+        p, pin = C.c_void_p(), C.c_int(0)
+        check(lib().gm_host_alloc(n * C.sizeof(ct), C.byref(p), C.byref(pin)))
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n,))
+        weakref.finalize(a, lib().gm_host_free, p)
+        out.append(a); pinned_all = pinned_all and bool(pin.value)
+    check(lib().gm_host_read_graph(prefix.encode(), nv.value, ne.value, out[0], out[1]))
+    return out[0], out[1][: ne.value], md.value, pinned_all
 
 
 def sort_neighbors(rowptr, colidx):

@@ -260,17 +260,18 @@ c4_cluster_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidTy
 // memory sized by the ROOT (2^bits >= 2 W slots of {key, count}), independent of |V|: a few MB per root, so
 // all resident clusters stay L2-resident together.  Clearing = one coalesced sweep over the used slots.
 constexpr int kC4TabBits = 21;                       // slots per cluster: 2 * kC4MidMaxDefault
+constexpr unsigned long long kC4Empty = ~0ull;
 __global__ void __launch_bounds__(kC4MidThreads)
 c4_cluster_hash_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
                        const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
-                       const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *tabs,
+                       const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, unsigned long long *tabs,
                        int *ticket, volatile int64_t *cur, AccType *total) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
   const int cid = int(blockIdx.x) / csize;
   const int lane = threadIdx.x & 31;
   const int wid = crank * (kC4MidThreads / 32) + (threadIdx.x >> 5), nwarps = csize * (kC4MidThreads / 32);
-  uint32_t *keys = tabs + (size_t(cid) << (kC4TabBits + 1)), *cnts = keys + (size_t(1) << kC4TabBits);
+  unsigned long long *tab = tabs + (size_t(cid) << kC4TabBits);      // slot = key << 32 | count: ONE atomic per wedge
   AccType acc = 0;
   while (true) {
     cluster.sync();                                                 // previous root's slots cleared by every CTA
@@ -284,10 +285,14 @@ c4_cluster_hash_kernel(const vidType *__restrict__ roots, int64_t nroots, const 
     const uint32_t mask = (1u << bits) - 1u;
     auto insert = [&](uint32_t x) {
       uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+      const unsigned long long mine = (unsigned long long)x << 32;
       while (true) {
-        uint32_t k = *reinterpret_cast<volatile uint32_t *>(keys + h);
-        if (k == 0xffffffffu) k = atomicCAS(&keys[h], 0xffffffffu, x);
-        if (k == 0xffffffffu || k == x) { acc += atomicAdd(&cnts[h], 1u); break; }
+        unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(tab + h);
+        if (s == kC4Empty) {
+          s = atomicCAS(&tab[h], kC4Empty, mine | 1ull);           // claim the slot with count 1: the old count was 0
+          if (s == kC4Empty) break;
+        }
+        if ((s >> 32) == x) { acc += atomicAdd(&tab[h], 1ull) & 0xffffffffull; break; }
         h = (h + 1) & mask;
       }
     };
@@ -299,14 +304,10 @@ c4_cluster_hash_kernel(const vidType *__restrict__ roots, int64_t nroots, const 
       for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
     }
     cluster.sync();
-    for (uint32_t i = uint32_t(crank) * kC4MidThreads + threadIdx.x; i <= mask; i += uint32_t(csize) * kC4MidThreads) { keys[i] = 0xffffffffu; cnts[i] = 0u; }
+    for (uint32_t i = uint32_t(crank) * kC4MidThreads + threadIdx.x; i <= mask; i += uint32_t(csize) * kC4MidThreads) tab[i] = kC4Empty;
   }
   acc = warp_reduce(acc);
   if (lane == 0 && acc) atomicAdd(total, acc);
-}
-__global__ void k_c4_init_tabs(uint32_t *tabs, size_t nwords) {
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nwords; i += size_t(gridDim.x) * blockDim.x)
-    tabs[i] = ((i >> kC4TabBits) & 1) ? 0u : 0xffffffffu;          // [keys | counts] per cluster
 }
 
 __global__ void __launch_bounds__(256)
@@ -473,9 +474,9 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
                  options().c4_hash != 0;
     if (options().c4_hash == 1 && c->c4_clusters > 0 && mid_max <= (1ull << (kC4TabBits - 1))) c->c4_hash = true;   // test hook
     if (c->c4_hash) {
-      const size_t words = (size_t(c->c4_clusters) << (kC4TabBits + 1));
-      if (dmalloc(c, &c->c4_tabs, words * 4) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle cluster tables)"); return GM_ENOMEM; }
-      k_c4_init_tabs<<<c->num_sms * 8, 256, 0, c->stream>>>(c->c4_tabs, words);
+      const size_t bytes = (size_t(c->c4_clusters) << kC4TabBits) * sizeof(unsigned long long);
+      if (dmalloc(c, &c->c4_tabs, bytes) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (4-cycle cluster tables)"); return GM_ENOMEM; }
+      GM_CUDA(cudaMemsetAsync(c->c4_tabs, 0xff, bytes, c->stream));
       arrays = 1;                                                   // the heavy tier keeps one dense array
     } else if (c->c4_clusters > 0) {
       const int64_t fit = std::max<int64_t>(1, int64_t(double(l2) * 0.8) / int64_t(arr_bytes));

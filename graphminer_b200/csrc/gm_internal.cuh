@@ -47,7 +47,7 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
- int tc_pipe = 1;                   // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
+  int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)
   int clique_gt1 = 256;              // threads per group of the d <= 512 class of the k-clique bit-matrix kernel (256 | 512)
@@ -126,7 +126,7 @@ struct gm_graph {
   int c4_clusters = 0, c4_cluster_size = 0; int64_t *c4_cur = nullptr;
   std::vector<gm::vidType> c4_heavy;
   uint32_t *c4_dense = nullptr; size_t c4_dense_stride = 0; int c4_dense_ctas = 0;
-  uint32_t *c4_tabs = nullptr; bool c4_hash = false;                 // per-cluster hash tables of the mid tier on large graphs
+  unsigned long long *c4_tabs = nullptr; bool c4_hash = false;                 // per-cluster hash tables of the mid tier on large graphs
   bool c4_lists_ready = false; gm::vidType c4_fb = 0, c4_fe = 0;
 
   // scratch + results

@@ -529,6 +529,38 @@ int gm_device_init(int device) {
   return GM_OK;
 }
 
+// ---- loader-side host memory ---------------------------------------------------------
+static std::mutex g_pin_mu;
+static std::vector<void *> g_pinned;
+int gm_host_alloc(size_t bytes, void **ptr, int *pinned) {
+  if (!ptr) { set_error("gm_host_alloc: null argument"); return GM_EINVAL; }
+  void *p = nullptr;
+  int ndev = 0; gm_device_count(&ndev);
+  if (ndev > 0 && cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pinned.push_back(p);
+    if (pinned) *pinned = 1;
+  } else {
+    cudaGetLastError();
+    p = malloc(bytes ? bytes : 1);
+    if (!p) { set_error("gm_host_alloc: out of host memory (%zu bytes)", bytes); return GM_ENOMEM; }
+    if (pinned) *pinned = 0;
+  }
+  *ptr = p;
+  return GM_OK;
+}
+int gm_host_free(void *ptr) {
+  if (!ptr) return GM_OK;
+  bool was_pinned = false;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pinned.size(); i++)
+      if (g_pinned[i] == ptr) { g_pinned[i] = g_pinned.back(); g_pinned.pop_back(); was_pinned = true; break; }
+  }
+  if (was_pinned) { cudaFreeHost(ptr); cudaGetLastError(); } else free(ptr);
+  return GM_OK;
+}
+
 int gm_device_count(int *count) {
   if (!count) { set_error("count is NULL"); return GM_EINVAL; }
   int n = 0;

@@ -372,6 +372,12 @@ int run_sgl(gm_graph *g, int pattern, int *launches) {
   return GM_OK;
 }
 
+int run_motif3_degree_sum(gm_graph *g, int *launches) {
+  vidType n = g->src_end - g->src_begin;
+  if (n > 0) { motif3_formula_vertex<<<(n + 255) / 256, 256, 0, g->stream>>>(g->view(0), g->src_begin, g->src_end, g->d_counts); (*launches)++; }
+  return GM_OK;
+}
+
 int run_motif(gm_graph *g, int k, int formula, int *launches) {
   int grid; vidType *scratch;
   int64_t md = std::max<int64_t>(g->max_degree, 1);

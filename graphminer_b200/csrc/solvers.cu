@@ -12,6 +12,8 @@
 
 namespace gm {
 int prepare_tc(gm_graph *g);
+int run_tc_prepared(gm_graph *g, int *launches);
+int run_motif3_degree_sum(gm_graph *g, int *launches);
 int run_kclique_list(gm_graph *g, int k, int *launches);
 int run_kclique_bitmap(gm_graph *g, int k, int *launches, bool *handled);
 int prepare_kclique_bitmap(gm_graph *g);
@@ -91,20 +93,55 @@ int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total) {
   return end_timed(g, launches, 1, total);
 }
 
+// 3-motif on the whole graph without touching an undirected hub row: triangles = one TC pass on the
+// device-oriented DAG child (ranked table kernel), wedges from the degree sum (omp_formula.cc:39-41).
+static int prepare_motif3_fast(gm_graph *g, bool *ok) {
+  *ok = false;
+  if (g->nv == 0 || g->ne == 0 || g->src_begin != 0 || g->src_end != g->nv) return GM_OK;
+  GM_TRY(ensure_dag_child(g));
+  gm_graph *c = g->dag_child;
+  if (c->src_begin != 0 || c->src_end != c->nv) return GM_OK;      // the child serves a partial support pass right now
+  GM_TRY(prepare_tc(c));
+  *ok = true;
+  return GM_OK;
+}
+static int run_motif3_fast(gm_graph *g, int *launches) {
+  gm_graph *c = g->dag_child;
+  GM_TRY(run_motif3_degree_sum(g, launches));                        // counters[0] = sum d(d-1)
+  unsigned long long *save = c->d_counts;
+  c->d_counts = g->d_counts + 1;                                     // counters[1] = triangles
+  GM_CUDA(cudaMemsetAsync(c->d_ticket, 0, 8 * sizeof(int), g->stream));
+  int r = run_tc_prepared(c, launches);
+  c->d_counts = save;
+  return r;
+}
+
+// The base form (MotifSolver of motif/gpu_base.cu: every pattern enumerated per edge) and the formula form
+// (gpu_formula.cu) return the SAME vertex-induced counts; with motif.algo=auto|fast both run on the DAG
+// machinery (supports, wedge-pair 4-cycles, bit-matrix 4-cliques, ranked TC) whenever the handle covers the
+// whole graph, and keep the reference's per-edge schedule (operator-API kernels) for a shard's source range,
+// whose partition of the patterns the fast path does not reproduce (base form) -- shards of the formula form
+// return raw sums through the fast path as before.
 static int motif_common(gm_graph_t *g, int k, int formula, int raw, uint64_t *counts) {
   if (!g || !counts) { set_error("gm_motif: null argument"); return GM_EINVAL; }
   if (k != 3 && k != 4) { set_error("motif: k=%d not supported (k in {3,4})", k); return GM_EUNSUPPORTED; }
   if (g->d_result && formula && !raw) { set_error("gm_motif_formula: device-side results need gm_motif_formula_raw + gm_motif_formula_finish"); return GM_EUNSUPPORTED; }
-  bool fast = false;
-  if (k == 4 && formula && options().motif_algo != "list") GM_TRY(prepare_motif4_fast(g, &fast));
-  if (!fast) GM_TRY(ensure_coo(g, formula ? 1 : 0));
+  const bool allow_fast = options().motif_algo != "list";
+  const bool whole = g->src_begin == 0 && g->src_end == g->nv;
+  const bool base_via_formula = !formula && allow_fast && whole && !g->d_result;   // needs the host-side fix-up
+  bool fast4 = false, fast3 = false;
+  if (k == 4 && allow_fast && (formula || base_via_formula)) GM_TRY(prepare_motif4_fast(g, &fast4));
+  if (k == 3 && allow_fast && whole && (raw || !g->d_result)) GM_TRY(prepare_motif3_fast(g, &fast3));
+  const bool as_formula = formula || fast4 || fast3;
+  if (!fast4 && !fast3) GM_TRY(ensure_coo(g, as_formula ? 1 : 0));
   int launches = 0;
   g->last_alg_bytes = 0; g->last_alg_kind = 0;
   GM_TRY(begin_timed(g));
-  if (fast) GM_TRY(run_motif4_fast(g, &launches));
-  else GM_TRY(run_motif(g, k, formula, &launches));
+  if (fast4) GM_TRY(run_motif4_fast(g, &launches));
+  else if (fast3) GM_TRY(run_motif3_fast(g, &launches));
+  else GM_TRY(run_motif(g, k, as_formula, &launches));
   GM_TRY(end_timed(g, launches, k == 3 ? 2 : 6, counts));
-  if (formula && !raw) formula_fixup(k, counts);
+  if (as_formula && !raw) formula_fixup(k, counts);
   return GM_OK;
 }
 
@@ -412,6 +449,8 @@ int gm_sgl_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_
 int gm_motif_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne, int32_t max_degree,
                   int k, int use_formula, int n_gpus, uint64_t *counts) {
   if (k != 3 && k != 4) { set_error("motif: k=%d not supported (k in {3,4})", k); return GM_EUNSUPPORTED; }
+  // same counts either way (see motif_common): shards of the 4-motif exchange supports through the formula path
+  if (k == 4 && n_gpus > 1 && options().motif_algo != "list") use_formula = 1;
   HostJob j{rowptr, colidx, nv, ne, max_degree, K_MOTIF, k, nullptr, use_formula, k == 3 ? 2 : 6};
   return run_host(j, n_gpus, counts);
 }

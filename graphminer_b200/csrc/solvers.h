@@ -9,6 +9,7 @@
 // gm::Pattern carrying exactly what those solvers read.  Errors follow the reference's CLI
 // behaviour: message on stderr + exit(1) (the C ABI underneath never exits).
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -35,11 +36,21 @@ class Graph {
   std::string name_, path_;
   vidType nv_ = 0, max_degree_ = 0;
   eidType ne_ = 0;
-  std::vector<eidType> rowptr_;
-  std::vector<vidType> colidx_;
+  // page-locked arrays (gm_host_alloc): the solvers' upload is then a straight DMA from where the loader put
+  // the file (the reference reads into new[] / mmap'd pageable arrays, custom_alloc.h:33-44)
+  eidType *rowptr_ = nullptr;
+  vidType *colidx_ = nullptr;
+  template <typename T> static T *alloc(size_t n) {
+    void *p = nullptr; int pinned = 0;
+    die_on(gm_host_alloc(sizeof(T) * (n > 0 ? n : 1), &p, &pinned), "host allocation");
+    return static_cast<T *>(p);
+  }
 
  public:
   Graph() {}
+  Graph(const Graph &) = delete;
+  Graph &operator=(const Graph &) = delete;
+  ~Graph() { gm_host_free(rowptr_); gm_host_free(colidx_); }
   explicit Graph(const std::string &prefix, bool use_dag = false) {
     size_t i = prefix.rfind('/');
     if (i != std::string::npos) path_ = prefix.substr(0, i);
@@ -47,31 +58,34 @@ class Graph {
     if (i != std::string::npos) name_ = path_.substr(i + 1);
     std::cout << "input file path: " << path_ << ", graph name: " << name_ << "\n";
     die_on(gm_host_read_meta(prefix.c_str(), &nv_, &ne_, &max_degree_), "reading graph meta");
-    rowptr_.resize(size_t(nv_) + 1);
-    colidx_.resize(size_t(ne_));
-    die_on(gm_host_read_graph(prefix.c_str(), nv_, ne_, rowptr_.data(), colidx_.data()), "reading graph");
+    rowptr_ = alloc<eidType>(size_t(nv_) + 1);
+    colidx_ = alloc<vidType>(size_t(ne_));
+    die_on(gm_host_read_graph(prefix.c_str(), nv_, ne_, rowptr_, colidx_), "reading graph");
     if (use_dag) orientation();
   }
-  Graph(vidType nv, std::vector<eidType> rowptr, std::vector<vidType> colidx, vidType max_degree)
-      : nv_(nv), max_degree_(max_degree), ne_(eidType(colidx.size())), rowptr_(std::move(rowptr)), colidx_(std::move(colidx)) {}
+  Graph(vidType nv, const std::vector<eidType> &rowptr, const std::vector<vidType> &colidx, vidType max_degree)
+      : nv_(nv), max_degree_(max_degree), ne_(eidType(colidx.size())) {
+    rowptr_ = alloc<eidType>(rowptr.size()); colidx_ = alloc<vidType>(colidx.size());
+    std::copy(rowptr.begin(), rowptr.end(), rowptr_); std::copy(colidx.begin(), colidx.end(), colidx_);
+  }
 
   // Graph::orientation (graph.cc:233-279)
   void orientation() {
     std::cout << "Orientation enabled, using DAG\n";
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<eidType> rp(size_t(nv_) + 1);
-    std::vector<vidType> ci(size_t(ne_) > 0 ? size_t(ne_) : 1);
-    int64_t ne = gm_host_orient(nv_, rowptr_.data(), colidx_.data(), rp.data(), ci.data(), &max_degree_);
+    eidType *rp = alloc<eidType>(size_t(nv_) + 1);
+    vidType *ci = alloc<vidType>(size_t(ne_));
+    int64_t ne = gm_host_orient(nv_, rowptr_, colidx_, rp, ci, &max_degree_);
     if (ne < 0) die_on(int(ne), "orientation");
-    ci.resize(size_t(ne));
-    rowptr_.swap(rp); colidx_.swap(ci); ne_ = ne;
+    gm_host_free(rowptr_); gm_host_free(colidx_);
+    rowptr_ = rp; colidx_ = ci; ne_ = ne;
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "Time on generating the DAG: " << s << " sec\n";
   }
   // Graph::sort_neighbors (graph.cc:138-146)
   void sort_neighbors() {
     std::cout << "Sorting the neighbor lists (used for pattern mining)\n";
-    die_on(gm_host_sort_neighbors(nv_, rowptr_.data(), colidx_.data()), "sort_neighbors");
+    die_on(gm_host_sort_neighbors(nv_, rowptr_, colidx_), "sort_neighbors");
   }
   vidType V() const { return nv_; }
   eidType E() const { return ne_; }
@@ -83,8 +97,8 @@ class Graph {
   vidType get_degree(vidType v) const { return vidType(rowptr_[v + 1] - rowptr_[v]); }
   eidType edge_begin(vidType v) const { return rowptr_[v]; }
   eidType edge_end(vidType v) const { return rowptr_[v + 1]; }
-  const eidType *out_rowptr() const { return rowptr_.data(); }
-  const vidType *out_colidx() const { return colidx_.data(); }
+  const eidType *out_rowptr() const { return rowptr_; }
+  const vidType *out_colidx() const { return colidx_; }
   std::string get_name() const { return name_; }
   void print_meta_data() const {
     std::cout << "|V|: " << nv_ << ", |E|: " << ne_ << ", Max Degree: " << max_degree_ << "\n";

@@ -379,14 +379,12 @@ int prepare_tc(gm_graph *g) {
 
 using namespace gm;
 
-extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
-  if (!g || !total) { set_error("gm_tc: null argument"); return GM_EINVAL; }
-  GM_TRY(prepare_tc(g));
-  g->last_alg_kind = 1;                       // computed on demand by gm_last_alg_bytes
+// the kernels of one TC pass on a prepared graph, accumulating into g->d_counts[0] (also used on the DAG child
+// of an undirected graph by the 3-motif fast path, solvers.cu)
+namespace gm {
+int run_tc_prepared(gm_graph *g, int *launches) {
   std::string algo;
   GM_TRY(resolve_tc_algo(g, &algo));
-  int launches = 0;
-  GM_TRY(begin_timed(g));
   if (algo == "bs") {
     if (g->nnz[0] > 0) {
       int occ = 0;
@@ -394,16 +392,27 @@ extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
       int64_t want = (g->nnz[0] + 7) / 8;
       int grid = int(std::min<int64_t>(want, int64_t(occ) * g->num_sms * 4));
       tc_warp_edge_bs<<<grid, 256, 0, g->stream>>>(g->view(0), g->d_counts);
-      launches++;
+      (*launches)++;
     }
   } else if (algo == "merge") {
-    GM_TRY(run_tc_merge(g, &launches));
+    GM_TRY(run_tc_merge(g, launches));
   } else if (algo == "hash") {
-    GM_TRY(run_tc_hash<0>(g, &launches));
+    GM_TRY(run_tc_hash<0>(g, launches));
   } else if (algo == "hash_rev") {
-    GM_TRY(run_tc_hash<1>(g, &launches));
+    GM_TRY(run_tc_hash<1>(g, launches));
   } else {
-    GM_TRY(run_tc_hash<2>(g, &launches));
+    GM_TRY(run_tc_hash<2>(g, launches));
   }
+  return GM_OK;
+}
+}  // namespace gm
+
+extern "C" int gm_tc(gm_graph_t *g, uint64_t *total) {
+  if (!g || !total) { set_error("gm_tc: null argument"); return GM_EINVAL; }
+  GM_TRY(prepare_tc(g));
+  g->last_alg_kind = 1;                       // computed on demand by gm_last_alg_bytes
+  int launches = 0;
+  GM_TRY(begin_timed(g));
+  GM_TRY(run_tc_prepared(g, &launches));
   return end_timed(g, launches, 1, total);
 }

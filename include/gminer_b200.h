@@ -23,6 +23,7 @@
 #ifndef GMINER_B200_H_
 #define GMINER_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -60,8 +61,8 @@ int gm_device_init(int device);
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source
  *       (the reference's semantics, default) or by their destination (same total over a partition of
  *       the vertex set; keeps each root's table on one shard -- set before gm_graph_prepare),
- *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.pipe" = 1|0 (cross-partner
- *       prefetch in the TC stream loop), "tc.gt2" = 256|512, "sup.gt2" =
+ *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.pipe" = 0|1 (cross-partner
+ *       prefetch in the TC stream loop; measured slower, off by default), "tc.gt2" = 256|512, "sup.gt2" =
  *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
  *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers), "c4.hash" = -1|0|1
  *       (cluster tier on dense |V|-sized arrays or per-root hash tables; auto by |V|).
@@ -96,6 +97,12 @@ int gm_host_read_meta(const char *prefix, int32_t *nv, int64_t *ne, int32_t *max
 int gm_host_read_graph(const char *prefix, int32_t nv, int64_t ne, int64_t *rowptr, int32_t *colidx);
 int gm_host_write_graph(const char *prefix, int32_t nv, int64_t ne, int32_t max_degree,
                         const int64_t *rowptr, const int32_t *colidx);
+/* Page-locked host arrays for the loader: a graph read straight into them (gm_host_read_graph reads with
+ * parallel pread into whatever it is given) is uploaded by DMA at the full PCIe rate, without the staging copy
+ * pageable memory costs -- the reference reads into new[] / mmap'd pageable arrays (include/custom_alloc.h:33-44).
+ * Without a CUDA device the memory comes from malloc and *pinned is 0.  gm_host_free takes either kind. */
+int gm_host_alloc(size_t bytes, void **ptr, int *pinned);
+int gm_host_free(void *ptr);
 /* Graph::sort_neighbors, src/common/graph.cc:138-146: sort every adjacency row in place (the
  * `adj_sorted = 0` path of triangle/main.cc:21-22). */
 int gm_host_sort_neighbors(int32_t nv, const int64_t *rowptr, int32_t *colidx);

@@ -120,3 +120,18 @@ def test_loader_sort_and_check(tmp_path):
         f.truncate(max(0, ci.nbytes - 4))
     with pytest.raises(capi.GMError):
         capi.read_graph(prefix)
+
+
+def test_pinned_loader_roundtrip(tmp_path):
+    """gm_host_alloc / gm_host_free + the loader reading straight into that memory (malloc fallback without a GPU)"""
+    rng = np.random.default_rng(9)
+    nv = 3000
+    deg = rng.integers(0, 9, nv)
+    rp = np.zeros(nv + 1, np.int64); np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(nv, d, replace=False)) for d in deg]).astype(np.int32)
+    prefix = str(tmp_path / "graph")
+    capi.write_graph(prefix, rp, ci, int(deg.max()))
+    got_rp, got_ci, md, pinned = capi.read_graph_pinned(prefix)
+    assert np.array_equal(got_rp, rp) and np.array_equal(got_ci, ci) and md == int(deg.max())
+    assert pinned == (capi.device_count() > 0)
+    del got_rp, got_ci                                   # finalisers hand the arrays back to gm_host_free
