@@ -614,21 +614,38 @@ batch_ring_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ 
   }
 }
 
-// pairs too long for the largest stage: operator API straight from global memory
+// Pairs too long for the largest stage (hub x hub: more than 4,608 staged elements): one CTA per pair.
+// 1,024 evenly spaced pivots of the longer list go to shared memory once (coalesced gather), the keys of
+// the shorter list are dealt to all 256 threads, and every key needs one bisection over the pivots in shared
+// memory plus log2(n / 1024) probes of a bucket that the neighbouring threads' keys keep in L1/L2 -- the
+// reference's CTA-centric scheme (GraphGPU::cta_intersect_cache, graph_gpu.h:297-323; bs_cta_edge.cuh:2-16)
+// with four times the pivots and a barrier on both sides of the table.  (Round 1 sent these pairs to one
+// warp each, searching from global memory.)
+constexpr int kBigPivots = 1024;
 __global__ void __launch_bounds__(256)
-batch_list_bsearch_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
-                          const int64_t *__restrict__ b_off, const int32_t *__restrict__ b_len,
-                          const int32_t *__restrict__ plist, const unsigned *__restrict__ pcount,
-                          unsigned long long *__restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = (int64_t(gridDim.x) * blockDim.x) >> 5;
+batch_list_cta_kernel(const vidType *__restrict__ pool, const int64_t *__restrict__ a_off, const int32_t *__restrict__ a_len,
+                      const int64_t *__restrict__ b_off, const int32_t *__restrict__ b_len,
+                      const int32_t *__restrict__ plist, const unsigned *__restrict__ pcount,
+                      unsigned long long *__restrict__ out) {
+  __shared__ vidType pivots[kBigPivots];
+  __shared__ unsigned s_count;
   const int64_t n = int64_t(*pcount);
-  for (int64_t i = gw; i < n; i += nw) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
     const int p = plist[i];
-    unsigned long long c = intersect_num(pool + a_off[p], vidType(a_len[p]), pool + b_off[p], vidType(b_len[p]));
-    c = warp_reduce(c);
-    if (lane == 0) out[p] = c;
+    const vidType *K = pool + a_off[p]; int nk = a_len[p];
+    const vidType *S = pool + b_off[p]; int ns = b_len[p];
+    if (nk > ns) { const vidType *t = K; K = S; S = t; const int tn = nk; nk = ns; ns = tn; }
+    if (threadIdx.x == 0) s_count = 0;
+    for (int t = threadIdx.x; t < kBigPivots; t += 256) pivots[t] = ns > 0 ? S[(long long)t * ns / kBigPivots] : 0;
+    __syncthreads();
+    unsigned c = 0;
+    for (int k = threadIdx.x; k < nk; k += 256)
+      c += detail::search_2phase(S, pivots, kBigPivots, __ldg(K + k), vidType(ns)) ? 1u : 0u;
+    c = __reduce_add_sync(kFullMask, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
+    __syncthreads();
+    if (threadIdx.x == 0) out[p] = s_count;
+    __syncthreads();                                         // pivots and counter are reused by the next pair
   }
 }
 
@@ -719,8 +736,8 @@ static int launch_pipeline(const vidType *pool, const int64_t *a_off, const int3
   }
 #undef GM_PIPE
   if (rc == GM_OK) {
-    int grid = int(std::min<int64_t>((npairs + 7) / 8, int64_t(sms) * 8));
-    batch_list_bsearch_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, over_list, over_count, out);
+    int grid = int(std::min<int64_t>(npairs, int64_t(sms) * 8));
+    batch_list_cta_kernel<<<grid, 256, 0, s>>>(pool, a_off, a_len, b_off, b_len, over_list, over_count, out);
   }
   cudaFreeAsync(lists, s); cudaFreeAsync(counts, s);
   return rc;

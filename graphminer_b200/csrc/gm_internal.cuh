@@ -79,6 +79,7 @@ struct gm_graph {
 
   gm::eidType *d_rowptr = nullptr;
   gm::vidType *d_colidx = nullptr;
+  unsigned *d_indeg = nullptr;           // in-degrees counted while the CSR was uploaded (graph_upload_ex), consumed by rank.cu
 
   // aligned view (built by prepare)
   uint2 *d_vinfo = nullptr;
@@ -171,6 +172,8 @@ inline cudaError_t dfree(gm_graph *g, void *p) { return p ? cudaFreeAsync(p, g->
 // on g->stream and then calls graph_finish_owned (solvers.cu: sharded upload + all-gather)
 int graph_alloc_owned(int32_t nv, int64_t ne, int32_t max_degree, int device, size_t rowptr_bytes, size_t colidx_bytes, gm_graph **out);
 int graph_finish_owned(gm_graph *g);
+int graph_upload_ex(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne, int32_t max_degree, int device,
+                    bool want_indeg, gm_graph **out);
 int ensure_aligned(gm_graph *g);
 int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);

@@ -489,6 +489,62 @@ static void finish_common(gm_graph *g, vidType *d_md) {
   dfree(g, d_md);
 }
 
+__global__ void k_indeg_edges(int64_t n, const vidType *__restrict__ col, unsigned *indeg) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) atomicAdd(&indeg[col[i]], 1u);
+}
+
+// gm_graph_upload; with want_indeg the column indices travel in chunks and the in-degree count of every
+// chunk (the first step of the rank relabelling, rank.cu) runs on a side stream while the next chunk is still
+// on the PCIe bus -- the end-to-end entry points of the DAG solvers use it
+int graph_upload_ex(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne, int32_t max_degree, int device,
+                    bool want_indeg, gm_graph **out) {
+  if (!out || nv < 0 || ne < 0 || (!rowptr && nv >= 0) || (!colidx && ne > 0)) { set_error("gm_graph_upload: bad arguments"); return GM_EINVAL; }
+  if (rowptr[nv] != ne) { set_error("gm_graph_upload: rowptr[nv]=%lld != ne=%lld", (long long)rowptr[nv], (long long)ne); return GM_EINVAL; }
+  int ndev = 0; gm_device_count(&ndev);
+  if (device < 0 || device >= ndev) { set_error("gm_graph_upload: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
+  trace_phase(nullptr, nullptr);
+  gm_graph *g = new gm_graph();
+  g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
+  int r = [&]() -> int {
+    GM_TRY(acquire_res(g));
+    GM_CUDA(dmalloc(g, &g->d_rowptr, sizeof(eidType) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &g->d_colidx, sizeof(vidType) * size_t(ne > 0 ? ne : 1)));
+    // stream-ordered copies: with pinned host arrays the call returns while the DMA runs and the
+    // device-side preparation queues up behind it; the host arrays are only borrowed until the
+    // synchronisation at the end of this function
+    GM_CUDA(cudaMemcpyAsync(g->d_rowptr, rowptr, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyHostToDevice, g->stream));
+    want_indeg = want_indeg && nv > 0 && ne >= (int64_t(1) << 22);
+    if (want_indeg) {
+      GM_CUDA(dmalloc(g, &g->d_indeg, sizeof(unsigned) * (size_t(nv) + 1)));
+      GM_CUDA(cudaMemsetAsync(g->d_indeg, 0, sizeof(unsigned) * (size_t(nv) + 1), g->stream));
+      GM_CUDA(cudaEventRecord(g->fork_ev, g->stream));
+      GM_CUDA(cudaStreamWaitEvent(g->side[0], g->fork_ev, 0));
+      const int nchunk = 8;
+      const int64_t chunk = (ne + nchunk - 1) / nchunk;
+      for (int64_t lo = 0, k = 0; lo < ne; lo += chunk, k++) {
+        const int64_t n = std::min(chunk, ne - lo);
+        GM_CUDA(cudaMemcpyAsync(g->d_colidx + lo, colidx + lo, sizeof(vidType) * size_t(n), cudaMemcpyHostToDevice, g->stream));
+        GM_CUDA(cudaEventRecord(g->join_ev[k % 3], g->stream));
+        GM_CUDA(cudaStreamWaitEvent(g->side[0], g->join_ev[k % 3], 0));
+        k_indeg_edges<<<g->num_sms * 8, 256, 0, g->side[0]>>>(n, g->d_colidx + lo, g->d_indeg);
+      }
+      GM_CUDA(cudaEventRecord(g->join_ev[0], g->side[0]));
+      GM_CUDA(cudaStreamWaitEvent(g->stream, g->join_ev[0], 0));
+    } else if (ne > 0) {
+      GM_CUDA(cudaMemcpyAsync(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice, g->stream));
+    }
+    vidType *d_md = nullptr;
+    GM_TRY(init_common(g, &d_md));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    finish_common(g, d_md);
+    trace_phase(g->stream, want_indeg ? "upload (H2D CSR) + in-degrees" : "upload (H2D CSR)");
+    return GM_OK;
+  }();
+  if (r != GM_OK) { gm_graph_free(g); return r; }
+  *out = g;
+  return GM_OK;
+}
+
 int graph_alloc_owned(int32_t nv, int64_t ne, int32_t max_degree, int device, size_t rowptr_bytes, size_t colidx_bytes, gm_graph **out) {
   gm_graph *g = new gm_graph();
   g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
@@ -624,32 +680,7 @@ int gm_set_option(const char *key, const char *value) {
 
 int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
                     int32_t max_degree, int device, gm_graph_t **out) {
-  if (!out || nv < 0 || ne < 0 || (!rowptr && nv >= 0) || (!colidx && ne > 0)) { set_error("gm_graph_upload: bad arguments"); return GM_EINVAL; }
-  if (rowptr[nv] != ne) { set_error("gm_graph_upload: rowptr[nv]=%lld != ne=%lld", (long long)rowptr[nv], (long long)ne); return GM_EINVAL; }
-  int ndev = 0; gm_device_count(&ndev);
-  if (device < 0 || device >= ndev) { set_error("gm_graph_upload: device %d not available (%d CUDA devices)", device, ndev); return GM_ECUDA; }
-  trace_phase(nullptr, nullptr);
-  gm_graph *g = new gm_graph();
-  g->device = device; g->nv = nv; g->ne = ne; g->max_degree = max_degree; g->own_csr = true;
-  int r = [&]() -> int {
-    GM_TRY(acquire_res(g));
-    GM_CUDA(dmalloc(g, &g->d_rowptr, sizeof(eidType) * (size_t(nv) + 1)));
-    GM_CUDA(dmalloc(g, &g->d_colidx, sizeof(vidType) * size_t(ne > 0 ? ne : 1)));
-    // stream-ordered copies: with pinned host arrays the call returns while the DMA runs and the
-    // device-side preparation queues up behind it; the host arrays are only borrowed until the
-    // synchronisation at the end of this function
-    GM_CUDA(cudaMemcpyAsync(g->d_rowptr, rowptr, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyHostToDevice, g->stream));
-    if (ne > 0) GM_CUDA(cudaMemcpyAsync(g->d_colidx, colidx, sizeof(vidType) * size_t(ne), cudaMemcpyHostToDevice, g->stream));
-    vidType *d_md = nullptr;
-    GM_TRY(init_common(g, &d_md));
-    GM_CUDA(cudaStreamSynchronize(g->stream));
-    finish_common(g, d_md);
-    trace_phase(g->stream, "upload (H2D CSR)");
-    return GM_OK;
-  }();
-  if (r != GM_OK) { gm_graph_free(g); return r; }
-  *out = g;
-  return GM_OK;
+  return gm::graph_upload_ex(rowptr, colidx, nv, ne, max_degree, device, false, out);
 }
 
 int gm_graph_adopt(const int64_t *d_rowptr, const int32_t *d_colidx, int32_t nv, int64_t ne,
@@ -682,7 +713,7 @@ int gm_graph_free(gm_graph_t *g) {
   free_aux(g);
   free_c4(g);
   if (g->dag_child) { gm_graph_free(g->dag_child); g->dag_child = nullptr; }
-  dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support);
+  dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support); dfree(g, g->d_indeg);
   if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
   dfree(g, g->d_counts); dfree(g, g->d_ticket); dfree(g, g->d_scratch); dfree(g, g->d_gmat);
   // complete the stream-ordered frees now: the blocks return to the pool free of stream dependencies, so

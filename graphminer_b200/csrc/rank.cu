@@ -111,31 +111,46 @@ __device__ __forceinline__ void group_sort(uint32_t *s, int P, int tid) {
   }
 }
 
-// warp per new vertex: rows of up to 32 entries are finished here, longer ones queued by size class
+// warp per new vertex: rows of up to 32 entries are finished here, longer ones queued by size class.
+// A warp works on kRowsInFlight rows at once: the chain vinfo -> orig_of -> rowptr -> colidx -> rank[] is five
+// dependent loads per row, and with one row per warp the kernel sat at the memory latency (9.6 ms for the
+// 16.8 M rows of R-MAT scale 24); the loads of the rows of a batch are issued back to back instead.
+constexpr int kRowsInFlight = 4;
 __global__ void __launch_bounds__(256)
 k_rows_small(RowCtx c) {
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i < c.nv; i += nw) {
-    const uint2 vi = c.vinfo[i];
-    const int d = int(vi.y);
-    if (d == 0) continue;
-    if (d > 32) {
-      if (lane == 0) {
-        const int cls = d <= kMidMax ? 0 : d <= kBigMax ? 1 : 2;
-        c.lists[cls * c.cap + atomicAdd(&c.nlist[cls], 1u)] = vidType(i);
+  for (int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i0 < c.nv; i0 += nw * kRowsInFlight) {
+    uint2 vi[kRowsInFlight]; vidType v[kRowsInFlight]; const vidType *row[kRowsInFlight]; uint32_t x[kRowsInFlight];
+    #pragma unroll
+    for (int k = 0; k < kRowsInFlight; k++) { const int64_t i = i0 + k * nw; vi[k] = i < c.nv ? c.vinfo[i] : make_uint2(0, 0); }
+    #pragma unroll
+    for (int k = 0; k < kRowsInFlight; k++) v[k] = (vi[k].y > 0 && vi[k].y <= 32) ? c.orig_of[i0 + k * nw] : 0;
+    #pragma unroll
+    for (int k = 0; k < kRowsInFlight; k++) row[k] = c.colidx + c.rowptr[v[k]];
+    #pragma unroll
+    for (int k = 0; k < kRowsInFlight; k++) x[k] = (vi[k].y <= 32 && lane < int(vi[k].y)) ? uint32_t(__ldg(row[k] + lane)) : 0u;
+    #pragma unroll
+    for (int k = 0; k < kRowsInFlight; k++) x[k] = (vi[k].y <= 32 && lane < int(vi[k].y)) ? uint32_t(c.rank[x[k]]) : uint32_t(kVidMax);
+    #pragma unroll
+    for (int k = 0; k < kRowsInFlight; k++) {
+      const int64_t i = i0 + k * nw;
+      const int d = int(vi[k].y);
+      if (d == 0) continue;                                 // warp-uniform (also rows beyond nv)
+      if (d > 32) {
+        if (lane == 0) {
+          const int cls = d <= kMidMax ? 0 : d <= kBigMax ? 1 : 2;
+          c.lists[cls * c.cap + atomicAdd(&c.nlist[cls], 1u)] = vidType(i);
+        }
+        continue;
       }
-      continue;
+      const uint32_t y = warp_sort32(x[k], lane);
+      const int padded = (d + 3) & ~3;
+      if (lane < padded) c.acol[(size_t(vi[k].x) << 2) + lane] = vidType(y);
+      if (lane < d && vidType(y) <= vidType(i)) atomicOr(c.bad, 1);
+      const bool keep_src = v[k] >= c.src_begin && v[k] < c.src_end;
+      if (lane < d - 1 && rec_kept(c, keep_src, vidType(y))) atomicAdd(&c.cnt[y], 1u);
     }
-    const vidType v = c.orig_of[i];
-    const vidType *row = c.colidx + c.rowptr[v];
-    uint32_t x = lane < d ? uint32_t(c.rank[__ldg(row + lane)]) : uint32_t(kVidMax);
-    x = warp_sort32(x, lane);
-    const int padded = (d + 3) & ~3;
-    if (lane < padded) c.acol[(size_t(vi.x) << 2) + lane] = vidType(x);
-    if (lane < d && vidType(x) <= vidType(i)) atomicOr(c.bad, 1);
-    const bool keep_src = v >= c.src_begin && v < c.src_end;
-    if (lane < d - 1 && rec_kept(c, keep_src, vidType(x))) atomicAdd(&c.cnt[x], 1u);
   }
 }
 
@@ -256,7 +271,12 @@ int ensure_ranked(gm_graph *g) {
   };
   int rc = [&]() -> int {
     const size_t nv1 = size_t(nv) + 1;
-    GM_CUDA(dmalloc(g, &indeg, sizeof(unsigned) * nv1));
+    if (g->d_indeg) { indeg = g->d_indeg; g->d_indeg = nullptr; }        // counted during the upload
+    else {
+      GM_CUDA(dmalloc(g, &indeg, sizeof(unsigned) * nv1));
+      GM_CUDA(cudaMemsetAsync(indeg, 0, sizeof(unsigned) * nv1, g->stream));
+      k_indeg_all<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, indeg);
+    }
     GM_CUDA(dmalloc(g, &k0, sizeof(unsigned) * nv1));
     GM_CUDA(dmalloc(g, &k1, sizeof(unsigned) * nv1));
     GM_CUDA(dmalloc(g, &id0, sizeof(vidType) * nv1));
@@ -266,13 +286,11 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(dmalloc(g, &g->rk_nrow, sizeof(eidType) * nv1));
     GM_CUDA(dmalloc(g, &bad, sizeof(int)));
     GM_CUDA(dmalloc(g, &nlist, sizeof(unsigned) * 4));
-    GM_CUDA(cudaMemsetAsync(indeg, 0, sizeof(unsigned) * nv1, g->stream));
     GM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), g->stream));
     GM_CUDA(cudaMemsetAsync(nlist, 0, sizeof(unsigned) * 4, g->stream));
     GM_CUDA(cudaMemsetAsync(units + nv, 0, sizeof(uint32_t), g->stream));
     GM_CUDA(cudaMemsetAsync(g->rk_nrow + nv, 0, sizeof(eidType), g->stream));
     // 1. rank = position in the stable sort by total degree
-    k_indeg_all<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, indeg);
     k_vertex_keys<<<nblk(nv), 256, 0, g->stream>>>(nv, g->d_rowptr, indeg, k0, id0);
     {
       size_t tmp = 0;
@@ -307,7 +325,7 @@ int ensure_ranked(gm_graph *g) {
     c.full_range = g->src_begin == 0 && g->src_end == nv;
     c.bad = bad; c.lists = lists; c.nlist = nlist; c.cap = cap;
     const int wide = g->num_sms * 8;
-    k_rows_small<<<unsigned(std::min<int64_t>(nblk(int64_t(nv) * 32), int64_t(wide) * 4)), 256, 0, g->stream>>>(c);
+    k_rows_small<<<unsigned(std::min<int64_t>(nblk((int64_t(nv) + kRowsInFlight - 1) / kRowsInFlight * 32), int64_t(wide) * 4)), 256, 0, g->stream>>>(c);
     k_rows_group<32, kMidMax, 0><<<wide, 256, 0, g->stream>>>(c);
     k_rows_group<256, kBigMax, 1><<<wide, 256, 0, g->stream>>>(c);
     unsigned h_nlist[4] = {0, 0, 0, 0};

@@ -295,7 +295,8 @@ int solve_on(const HostJob &j, gm_graph_t *g, uint64_t *counts) {
 
 int run_on_device(const HostJob &j, int device, int32_t begin, int32_t end, uint64_t *counts, std::string *err) {
   gm_graph_t *g = nullptr;
-  int r = gm_graph_upload(j.rowptr, j.colidx, j.nv, j.ne, j.max_degree, device, &g);
+  // the DAG solvers relabel by rank first: count the in-degrees while the column indices are still arriving
+  int r = graph_upload_ex(j.rowptr, j.colidx, j.nv, j.ne, j.max_degree, device, j.kind == K_TC || j.kind == K_CLIQUE, &g);
   if (r == GM_OK) r = gm_graph_set_source_range(g, begin, end);
   if (r == GM_OK) r = solve_on(j, g, counts);
   if (r != GM_OK && err) *err = gm_last_error();

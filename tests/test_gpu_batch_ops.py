@@ -176,3 +176,19 @@ def test_pipeline_all_size_classes_at_scale():
         bad = torch.nonzero(got != want)
         assert bad.numel() == 0, (algo, bad[:5].tolist(), got[bad[:5, 0]].tolist(), want[bad[:5, 0]].tolist(),
                                   al[bad[:5, 0]].tolist(), bl[bad[:5, 0]].tolist())
+
+
+@pytest.mark.parametrize("algo", ["auto", "merge", "gallop"])
+def test_hub_pairs_take_the_cta_kernel(algo):
+    """pairs beyond the largest TMA stage (4,608 staged elements) are intersected by one CTA each with a
+    1,024-pivot shared-memory index (batch_list_cta_kernel)"""
+    rng = np.random.default_rng(21)
+    pairs = []
+    for na, nb, hi in ((20000, 30000, 60000), (5000, 200000, 400000), (4700, 10, 9000), (100000, 100000, 120000), (6000, 0, 10)):
+        pairs.append((np.unique(rng.integers(0, hi, na)).astype(np.int32), np.unique(rng.integers(0, hi, nb)).astype(np.int32)))
+    pairs.append((pairs[0][0], pairs[0][0]))                        # identical hub rows
+    pool, ao, al, bo, bl = pack(pairs)
+    t = lambda x: torch.from_numpy(x).cuda()
+    out = capi.intersect_batch(t(pool), t(ao), t(al), t(bo), t(bl), algo=algo)
+    torch.cuda.synchronize()
+    assert out.cpu().tolist() == [oracle.intersection_num(a, b) for a, b in pairs]

@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--gb", type=float, default=8.0)
     ap.add_argument("--algos", default="bsearch,merge,hash,gallop")
     ap.add_argument("--skew", action="store_true")
+    ap.add_argument("--op", default="intersect_num", help="intersect_num | intersect_num_bound | difference_num | difference_num_bound | ...")
     ap.add_argument("--reps", type=int, default=11)
     ap.add_argument("--json", default="")
     ap.add_argument("--sweep", default="", help="';'-separated sets of ','-separated gm_set_option key=value pairs; every set is timed")
@@ -79,13 +80,17 @@ def main():
     print(f"pairs={ao.numel()} elements={nel} ({nel * 4 / 1e9:.2f} GB algorithmic) avg |a|={float(al.float().mean()):.1f} "
           f"|b|={float(bl.float().mean()):.1f} max={int(torch.maximum(al, bl).max())} pool={pool.numel() * 4 / 1e9:.2f} GB", flush=True)
     res, ref = {}, None
+    bound = None
+    if "bound" in a.op:                              # bound = the median of list a: half of every pair is cut away
+        bound = pool[(ao + (al.long() // 2)).clamp(max=pool.numel() - 1)].contiguous()
+    run = lambda algo: capi.intersect_batch(pool, ao, al, bo, bl, op=a.op, algo=algo, bound=bound)
     for oset in (a.sweep.split(";") if a.sweep else [""]):
         for kv in filter(None, oset.split(",")):
             k, v = kv.split("="); capi.set_option(k, v)
         if oset:
             print(f" [{oset}]", flush=True)
         for algo in a.algos.split(","):
-            out = capi.intersect_batch(pool, ao, al, bo, bl, algo=algo); torch.cuda.synchronize()     # warm-up
+            out = run(algo); torch.cuda.synchronize()     # warm-up
             if ref is None:
                 ref = out
             else:
@@ -95,7 +100,7 @@ def main():
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.reps)]
             for e0, e1 in evs:
                 e0.record()
-                capi.intersect_batch(pool, ao, al, bo, bl, algo=algo)
+                run(algo)
                 e1.record()
             torch.cuda.synchronize()
             times = sorted(e0.elapsed_time(e1) for e0, e1 in evs)

@@ -10,8 +10,8 @@ only reads the per-step numbers this script writes:
 
     python tools/ncu_traffic.py <workload name> <launches.csv> [--kernels REGEX] [--out profiles/traffic.json]
 
-Per step = totals over the matching launches / number of solver passes in the capture (= launches of the
-most frequent matching kernel: every pass launches each size class once).  IPC of the pass = warp
+Per step = totals over the matching launches / number of solver passes in the capture (= the most common
+launch count among the matching kernels: every pass launches each size class once).  IPC of the pass = warp
 instructions / (SM cycles x SMs), the cycle-weighted mean over its kernels (they are serialised under ncu).
 """
 import csv
@@ -85,7 +85,10 @@ def main():
             p["sms_est"] = max(p["sms_est"], round(l["smsp__inst_executed.sum"] / (ipc * l["sm__cycles_elapsed.avg"])))
     if not per:
         sys.exit("no launch matches " + kre.pattern)
-    passes = max(int(p["launches"]) for p in per.values())
+    # every pass launches each size class once; a tier that launches per root (c4_heavy_kernel) has many launches
+    # per pass: the MOST COMMON launch count among the kernels is the number of passes
+    counts = sorted(int(p["launches"]) for p in per.values())
+    passes = max(set(counts), key=lambda c: (counts.count(c), -c))
     sms = max(int(p["sms_est"]) for p in per.values()) or 148
     tot = defaultdict(float)
     kernels = {}
