@@ -91,10 +91,15 @@ __global__ void k_c4_classify(vidType nv, const eidType *__restrict__ inrow, con
 struct ClsIs { const unsigned char *cls; unsigned char k; __device__ bool operator()(const vidType &u) const { return cls[u] == k; } };
 
 // ---- tier 1: warp per root, shared-memory table -------------------------------------------------------
+// ATTR (all tiers): after the counting pass every wedge u-v-w hands the number of 4-cycles it closes,
+// L[w] - 1, to its two edges: sq[(u,v)] and sq[(v,w)] (indexed like the supports, i.e. by aligned DAG slot) --
+// the per-edge 4-cycle counts the house pattern needs (run_house_fast).
+template <bool ATTR>
 __global__ void __launch_bounds__(128)
 c4_small_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
                 const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
-                const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, int *ticket, AccType *total) {
+                const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, int *ticket, AccType *total,
+                unsigned long long *__restrict__ sq) {
   __shared__ uint32_t s_keys[4][kC4SmallSlots];             // 4 warps x (4 + 4) KB
   __shared__ uint32_t s_cnts[4][kC4SmallSlots];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -128,6 +133,32 @@ c4_small_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigne
         const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
         for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
       }
+      if (ATTR) {
+        __syncwarp();
+        auto closes = [&](uint32_t x) -> uint32_t {                 // L[x] - 1
+          uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+          while (keys[h] != x) h = (h + 1) & mask;
+          return cnts[h] - 1u;
+        };
+        for (eidType e = inrow[u]; e < inrow[u + 1]; e++) {
+          const uint2 r = incol[e];
+          const size_t vbase = size_t(vinfo[r.x].x) << 2;
+          const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+          unsigned long long mine = 0;
+          for (int i = lane; i < nin; i += 32) {
+            const uint2 w = incol[vb + i];
+            const uint32_t c = closes(w.x);
+            if (c) { mine += c; atomicAdd(&sq[(size_t(vinfo[w.x].x) << 2) + w.y], (unsigned long long)c); }
+          }
+          const vidType *row = acol + vbase;
+          for (int i = lane; i < int(r.y); i += 32) {
+            const uint32_t c = closes(uint32_t(row[i]));
+            if (c) { mine += c; atomicAdd(&sq[vbase + i], (unsigned long long)c); }
+          }
+          mine = warp_reduce(mine);
+          if (lane == 0 && mine) atomicAdd(&sq[vbase + r.y], mine);
+        }
+      }
     }
   }
   acc = warp_reduce(acc);
@@ -135,10 +166,12 @@ c4_small_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigne
 }
 
 // ---- tier 2: CTA per root, shared-memory table (keys u32, counters packed 16-bit) ---------------------------
+template <bool ATTR>
 __global__ void __launch_bounds__(kC4MidThreads)
 c4_cta_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
               const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
-              const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, int *ticket, AccType *total) {
+              const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, int *ticket, AccType *total,
+              unsigned long long *__restrict__ sq) {
   extern __shared__ uint32_t c4_smem[];
   uint32_t *keys = c4_smem, *cnts = c4_smem + kC4CtaSlots;      // cnts: two 16-bit counters per word
   __shared__ int64_t s_next;
@@ -177,6 +210,32 @@ c4_cta_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned 
       const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
       for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
     }
+    if (ATTR) {
+      __syncthreads();
+      auto closes = [&](uint32_t x) -> uint32_t {                   // L[x] - 1
+        uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+        while (keys[h] != x) h = (h + 1) & mask;
+        return ((cnts[h >> 1] >> ((h & 1u) << 4)) & 0xffffu) - 1u;
+      };
+      for (eidType e = inrow[u] + wid; e < inrow[u + 1]; e += NW) {
+        const uint2 r = incol[e];
+        const size_t vbase = size_t(vinfo[r.x].x) << 2;
+        const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+        unsigned long long mine = 0;
+        for (int i = lane; i < nin; i += 32) {
+          const uint2 w = incol[vb + i];
+          const uint32_t c = closes(w.x);
+          if (c) { mine += c; atomicAdd(&sq[(size_t(vinfo[w.x].x) << 2) + w.y], (unsigned long long)c); }
+        }
+        const vidType *row = acol + vbase;
+        for (int i = lane; i < int(r.y); i += 32) {
+          const uint32_t c = closes(uint32_t(row[i]));
+          if (c) { mine += c; atomicAdd(&sq[vbase + i], (unsigned long long)c); }
+        }
+        mine = warp_reduce(mine);
+        if (lane == 0 && mine) atomicAdd(&sq[vbase + r.y], mine);
+      }
+    }
   }
   acc = warp_reduce(acc);
   if (lane == 0 && acc) atomicAdd(total, acc);
@@ -184,30 +243,43 @@ c4_cta_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned 
 
 // ---- tiers 2 and 3: dense counting array in global memory -------------------------------------------------
 // PHASE 0: L[w]++ and accumulate the old values; PHASE 1: L[w] = 0.  `nwarps` warps share the in-edges of u.
+// PHASE 2 (between the two): L[w] - 1 of every wedge to its two edges (see ATTR above).
 template <int PHASE>
 __device__ __forceinline__ AccType c4_dense_pass(vidType u, int wid, int nwarps, int lane, uint32_t *L,
-                                                 const eidType *inrow, const uint2 *incol, const uint2 *vinfo, const vidType *acol) {
+                                                 const eidType *inrow, const uint2 *incol, const uint2 *vinfo, const vidType *acol,
+                                                 unsigned long long *sq = nullptr) {
   AccType acc = 0;
   for (eidType e = inrow[u] + wid; e < inrow[u + 1]; e += nwarps) {
     const uint2 r = incol[e];
+    const size_t vbase = size_t(vinfo[r.x].x) << 2;
     const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+    unsigned long long mine = 0;
     for (int i = lane; i < nin; i += 32) {
-      const uint32_t x = incol[vb + i].x;
-      if (PHASE == 0) acc += atomicAdd(&L[x], 1u); else L[x] = 0u;
+      if (PHASE == 0) acc += atomicAdd(&L[incol[vb + i].x], 1u);     // 4-byte loads: only the vertex of the record
+      else if (PHASE == 1) L[incol[vb + i].x] = 0u;
+      else {
+        const uint2 w = incol[vb + i];
+        const uint32_t c = __ldcg(&L[w.x]) - 1u;
+        if (c) { mine += c; atomicAdd(&sq[(size_t(vinfo[w.x].x) << 2) + w.y], (unsigned long long)c); }
+      }
     }
-    const vidType *row = acol + (size_t(vinfo[r.x].x) << 2);
+    const vidType *row = acol + vbase;
     for (int i = lane; i < int(r.y); i += 32) {
       const uint32_t x = uint32_t(row[i]);
-      if (PHASE == 0) acc += atomicAdd(&L[x], 1u); else L[x] = 0u;
+      if (PHASE == 0) acc += atomicAdd(&L[x], 1u);
+      else if (PHASE == 1) L[x] = 0u;
+      else { const uint32_t c = __ldcg(&L[x]) - 1u; if (c) { mine += c; atomicAdd(&sq[vbase + i], (unsigned long long)c); } }
     }
+    if (PHASE == 2) { mine = warp_reduce(mine); if (lane == 0 && mine) atomicAdd(&sq[vbase + r.y], mine); }
   }
   return acc;
 }
 
+template <bool ATTR>
 __global__ void __launch_bounds__(kC4MidThreads)
 c4_mid_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
               const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *dense, size_t stride,
-              int *ticket, AccType *total) {
+              int *ticket, AccType *total, unsigned long long *__restrict__ sq) {
   __shared__ int64_t s_next;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t *L = dense + size_t(blockIdx.x) * stride;
@@ -221,6 +293,7 @@ c4_mid_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *
     const vidType u = roots[idx];
     acc += c4_dense_pass<0>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol);
     __syncthreads();
+    if (ATTR) { c4_dense_pass<2>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol, sq); __syncthreads(); }
     c4_dense_pass<1>(u, wid, kC4MidThreads / 32, lane, L, inrow, incol, vinfo, acol);
   }
   acc = warp_reduce(acc);
@@ -228,10 +301,11 @@ c4_mid_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *
 }
 
 // tier 3: one cluster per root; cur[cluster] carries the ticket from the cluster's first CTA to the others
-__global__ void __launch_bounds__(kC4MidThreads)
+template <bool ATTR>
+__global__ void __launch_bounds__(kC4MidThreads, 3)
 c4_cluster_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
                   const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *dense, size_t stride,
-                  int *ticket, volatile int64_t *cur, AccType *total) {
+                  int *ticket, volatile int64_t *cur, AccType *total, unsigned long long *__restrict__ sq) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
   const int cid = int(blockIdx.x) / csize;
@@ -248,6 +322,7 @@ c4_cluster_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidTy
     const vidType u = roots[idx];
     acc += c4_dense_pass<0>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol);
     cluster.sync();
+    if (ATTR) { c4_dense_pass<2>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol, sq); cluster.sync(); }
     c4_dense_pass<1>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol);
   }
   acc = warp_reduce(acc);
@@ -261,11 +336,12 @@ c4_cluster_kernel(const vidType *__restrict__ roots, int64_t nroots, const eidTy
 // all resident clusters stay L2-resident together.  Clearing = one coalesced sweep over the used slots.
 constexpr int kC4TabBits = 21;                       // slots per cluster: 2 * kC4MidMaxDefault
 constexpr unsigned long long kC4Empty = ~0ull;
+template <bool ATTR>
 __global__ void __launch_bounds__(kC4MidThreads)
 c4_cluster_hash_kernel(const vidType *__restrict__ roots, int64_t nroots, const unsigned long long *__restrict__ W,
                        const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
                        const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, unsigned long long *tabs,
-                       int *ticket, volatile int64_t *cur, AccType *total) {
+                       int *ticket, volatile int64_t *cur, AccType *total, unsigned long long *__restrict__ sq) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
   const int cid = int(blockIdx.x) / csize;
@@ -304,21 +380,52 @@ c4_cluster_hash_kernel(const vidType *__restrict__ roots, int64_t nroots, const 
       for (int i = lane; i < int(r.y); i += 32) insert(uint32_t(row[i]));
     }
     cluster.sync();
+    if (ATTR) {
+      auto closes = [&](uint32_t x) -> uint32_t {                   // L[x] - 1
+        uint32_t h = (x * 0x9E3779B1u) >> (32 - bits);
+        unsigned long long t = __ldcg(&tab[h]);                      // the counts were written by atomics: read them at the L2
+        while ((t >> 32) != x) { h = (h + 1) & mask; t = __ldcg(&tab[h]); }
+        return uint32_t(t & 0xffffffffull) - 1u;
+      };
+      for (eidType e = inrow[u] + wid; e < inrow[u + 1]; e += nwarps) {
+        const uint2 r = incol[e];
+        const size_t vbase = size_t(vinfo[r.x].x) << 2;
+        const eidType vb = inrow[r.x]; const int nin = int(inrow[r.x + 1] - vb);
+        unsigned long long mine = 0;
+        for (int i = lane; i < nin; i += 32) {
+          const uint2 w = incol[vb + i];
+          const uint32_t c = closes(w.x);
+          if (c) { mine += c; atomicAdd(&sq[(size_t(vinfo[w.x].x) << 2) + w.y], (unsigned long long)c); }
+        }
+        const vidType *row = acol + vbase;
+        for (int i = lane; i < int(r.y); i += 32) {
+          const uint32_t c = closes(uint32_t(row[i]));
+          if (c) { mine += c; atomicAdd(&sq[vbase + i], (unsigned long long)c); }
+        }
+        mine = warp_reduce(mine);
+        if (lane == 0 && mine) atomicAdd(&sq[vbase + r.y], mine);
+      }
+      cluster.sync();
+    }
     for (uint32_t i = uint32_t(crank) * kC4MidThreads + threadIdx.x; i <= mask; i += uint32_t(csize) * kC4MidThreads) tab[i] = kC4Empty;
   }
   acc = warp_reduce(acc);
   if (lane == 0 && acc) atomicAdd(total, acc);
 }
 
+template <int PHASE>     // 0 count, 2 attribute (a second launch: the whole grid must have finished counting)
 __global__ void __launch_bounds__(256)
 c4_heavy_kernel(vidType u, const eidType *__restrict__ inrow, const uint2 *__restrict__ incol,
-                const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *L, AccType *total) {
+                const uint2 *__restrict__ vinfo, const vidType *__restrict__ acol, uint32_t *L, AccType *total,
+                unsigned long long *__restrict__ sq) {
   const int lane = threadIdx.x & 31;
   const int wid = int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
   const int nwarps = int((int64_t(gridDim.x) * blockDim.x) >> 5);
-  AccType acc = c4_dense_pass<0>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol);
-  acc = warp_reduce(acc);
-  if (lane == 0 && acc) atomicAdd(total, acc);
+  AccType acc = c4_dense_pass<PHASE>(u, wid, nwarps, lane, L, inrow, incol, vinfo, acol, sq);
+  if (PHASE == 0) {
+    acc = warp_reduce(acc);
+    if (lane == 0 && acc) atomicAdd(total, acc);
+  }
 }
 
 // ---- closed forms from the supports (motif4_rest.cuh:16-28) ------------------------------------------------
@@ -463,9 +570,9 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(cs); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      if (cs > 8 && cudaFuncSetAttribute(c4_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cs > 8 && cudaFuncSetAttribute(c4_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, c4_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaOccupancyMaxActiveClusters(&n, c4_cluster_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
       if (n > 0) { c->c4_clusters = n; c->c4_cluster_size = cs; }
     }
     int64_t arrays;
@@ -484,7 +591,7 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
       arrays = c->c4_clusters;
     } else {
       int occ = 0;
-      GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c4_mid_kernel, kC4MidThreads, 0));
+      GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c4_mid_kernel<false>, kC4MidThreads, 0));
       arrays = int64_t(std::max(occ, 1)) * c->num_sms;
     }
     size_t free_b = 0, total_b = 0;
@@ -502,19 +609,23 @@ static int ensure_c4(gm_graph *c, vidType fb, vidType fe) {
 }
 
 // all tiers of the wedge-pair 4-cycle count for the roots selected by ensure_c4; tickets g->d_ticket[0..2]
-static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launches) {
+static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launches, unsigned long long *sq = nullptr) {
   if (c->c4_nsmall > 0) {
     int grid = int(std::min<int64_t>((c->c4_nsmall + 15) / 16, int64_t(c->num_sms) * 6));
-    c4_small_kernel<<<grid, 128, 0, g->stream>>>(c->c4_small, c->c4_nsmall, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
-                                                 g->d_ticket + 0, total);
+    auto k = sq ? c4_small_kernel<true> : c4_small_kernel<false>;
+    k<<<grid, 128, 0, g->stream>>>(c->c4_small, c->c4_nsmall, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                   g->d_ticket + 0, total, sq);
     (*launches)++;
+    trace_phase(g->stream, "4-cycle: warp tier");
   }
   if (c->c4_ncta > 0) {
     // per-device function attribute: set on every launch (one host thread per device in gm_motif_host)
-    GM_CUDA(cudaFuncSetAttribute(c4_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem));
+    auto k = sq ? c4_cta_kernel<true> : c4_cta_kernel<false>;
+    GM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4CtaSmem));
     int grid = int(std::min<int64_t>(c->c4_ncta, int64_t(c->num_sms)));
-    c4_cta_kernel<<<grid, kC4MidThreads, kC4CtaSmem, g->stream>>>(c->c4_cta, c->c4_ncta, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
-                                                                  g->d_ticket + 2, total);
+    k<<<grid, kC4MidThreads, kC4CtaSmem, g->stream>>>(c->c4_cta, c->c4_ncta, c->c4_W, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                      g->d_ticket + 2, total, sq);
+    trace_phase(g->stream, "4-cycle: CTA tier");
     (*launches)++;
   }
   if (c->c4_nmid > 0 && c->c4_clusters > 0) {
@@ -522,30 +633,65 @@ static int launch_c4_tiers(gm_graph *g, gm_graph *c, AccType *total, int *launch
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(nclusters * c->c4_cluster_size)); cfg.blockDim = dim3(kC4MidThreads);
     cfg.dynamicSmemBytes = 0; cfg.stream = g->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = unsigned(c->c4_cluster_size); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (!c->c4_hash && options().c4_persist) {
+      // The counting arrays are meant to live in the L2 while the wedge streams (in-rows, out-row prefixes) pass
+      // through it; without help the streams evict them (ncu: 216 GB of DRAM traffic per pass on the Friendster
+      // shape / 16, IPC 0.12): pin the arrays with a persisting access-policy window for this launch.
+      int dev = c->device, max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      const size_t bytes = c->c4_dense_stride * 4 * size_t(nclusters);
+      if (max_persist > 0 && max_window > 0) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(max_persist));
+        at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[1].val.accessPolicyWindow.base_ptr = c->c4_dense;
+        at[1].val.accessPolicyWindow.num_bytes = std::min(bytes, size_t(max_window));
+        at[1].val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(max_persist) / double(std::min(bytes, size_t(max_window)))));
+        at[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[1].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        cfg.numAttrs = 2;
+      }
+      cudaGetLastError();
+    }
+    auto clamp_clusters = [&](auto kern) {                           // the ATTR variants may hold fewer clusters
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0 && n < nclusters) cfg.gridDim = dim3(unsigned(n * c->c4_cluster_size));
+      cudaGetLastError();
+    };
     if (c->c4_hash) {
-      if (c->c4_cluster_size > 8) GM_CUDA(cudaFuncSetAttribute(c4_cluster_hash_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_hash_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const unsigned long long *)c->c4_W,
+      auto hk = sq ? c4_cluster_hash_kernel<true> : c4_cluster_hash_kernel<false>;
+      if (c->c4_cluster_size > 8) GM_CUDA(cudaFuncSetAttribute(hk, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      clamp_clusters(hk);
+      GM_CUDA(cudaLaunchKernelEx(&cfg, hk, (const vidType *)c->c4_mid, c->c4_nmid, (const unsigned long long *)c->c4_W,
                                  (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol, (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol,
-                                 c->c4_tabs, g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total));
-    } else
-    GM_CUDA(cudaLaunchKernelEx(&cfg, c4_cluster_kernel, (const vidType *)c->c4_mid, c->c4_nmid, (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol,
+                                 c->c4_tabs, g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total, sq));
+    } else {
+      auto dk = sq ? c4_cluster_kernel<true> : c4_cluster_kernel<false>;
+      if (c->c4_cluster_size > 8) GM_CUDA(cudaFuncSetAttribute(dk, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      clamp_clusters(dk);
+    GM_CUDA(cudaLaunchKernelEx(&cfg, dk, (const vidType *)c->c4_mid, c->c4_nmid, (const eidType *)c->c4_inrow, (const uint2 *)c->c4_incol,
                                (const uint2 *)c->rk_vinfo, (const vidType *)c->rk_acol, c->c4_dense, c->c4_dense_stride,
-                               g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total));
+                               g->d_ticket + 1, (volatile int64_t *)c->c4_cur, total, sq));
+    }
     (*launches)++;
+    trace_phase(g->stream, c->c4_hash ? "4-cycle: cluster tier (hash tables)" : "4-cycle: cluster tier (dense arrays)");
   } else if (c->c4_nmid > 0) {
     int grid = int(std::min<int64_t>(c->c4_nmid, int64_t(c->c4_dense_ctas)));
-    c4_mid_kernel<<<grid, kC4MidThreads, 0, g->stream>>>(c->c4_mid, c->c4_nmid, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
-                                                         c->c4_dense, c->c4_dense_stride, g->d_ticket + 1, total);
+    auto mk = sq ? c4_mid_kernel<true> : c4_mid_kernel<false>;
+    mk<<<grid, kC4MidThreads, 0, g->stream>>>(c->c4_mid, c->c4_nmid, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol,
+                                                         c->c4_dense, c->c4_dense_stride, g->d_ticket + 1, total, sq);
     (*launches)++;
   }
   for (vidType u : c->c4_heavy) {
-    c4_heavy_kernel<<<c->num_sms * 8, 256, 0, g->stream>>>(u, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol, c->c4_dense, total);
+    c4_heavy_kernel<0><<<c->num_sms * 8, 256, 0, g->stream>>>(u, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol, c->c4_dense, total, nullptr);
+    if (sq) { c4_heavy_kernel<2><<<c->num_sms * 8, 256, 0, g->stream>>>(u, c->c4_inrow, c->c4_incol, c->rk_vinfo, c->rk_acol, c->c4_dense, total, sq); (*launches)++; }
     GM_CUDA(cudaMemsetAsync(c->c4_dense, 0, c->c4_dense_stride * 4, g->stream));
     (*launches)++;
   }
+  if (!c->c4_heavy.empty()) trace_phase(g->stream, "4-cycle: heavy roots");
   return GM_OK;
 }
 
@@ -594,6 +740,57 @@ int run_rectangle_fast(gm_graph *g, int *launches) {
   return GM_OK;
 }
 
+// ---- sgl house on the DAG machinery ---------------------------------------------------------------------------
+// house (edge-induced, src/sgl/cpu_kernels/house.h:1-17) = a triangle (v0,v1,v2) and a 4-cycle (v0,v1,v3,v4) sharing
+// the edge (v0,v1), v2 not on the cycle.  With t(e) = triangles through e and sq(e) = 4-cycles through e:
+//     per edge e and triangle apex v2:  sq(e) - [cycles through e that use v2]
+//                                     = sq(e) - (t(v0 v2) - 1) - (t(v1 v2) - 1)
+//     house = sum_e t(e) sq(e) - sum_triangles sum_{e in it} (t(e') + t(e'') - 2)
+//           = sum_e [ t(e) sq(e) - 2 t(e)^2 + 2 t(e) ]                     (sum over undirected edges, mod 2^64)
+// t(e) = the support pass (support.cu), sq(e) = the wedge-pair 4-cycle count with every wedge u-v-w handing
+// L[w] - 1 to its two edges (ATTR above).  The reference enumerates, per edge, every v3 in N(v1) and intersects
+// N(v0) with N(v3) (house_edge_warp_nested.cuh:3-38).  Whole graph only: the identity sums over all edges.
+__global__ void __launch_bounds__(256)
+k_house_sum(int64_t n, const uint32_t *__restrict__ sup, const unsigned long long *__restrict__ sq, AccType *total) {
+  AccType acc = 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const AccType t = sup[i];
+    if (t) acc += t * sq[i] + 2ull * t - 2ull * t * t;              // padding slots hold 0 supports
+  }
+  acc = warp_reduce(acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+
+int prepare_house_fast(gm_graph *g, bool *ok) {
+  *ok = false;
+  if (g->nv == 0 || g->ne == 0 || g->src_begin != 0 || g->src_end != g->nv) return GM_OK;
+  bool sup = false;
+  GM_TRY(prepare_diamond_support(g, &sup));
+  if (!sup) return GM_OK;
+  gm_graph *c = g->dag_child;
+  GM_TRY(ensure_c4(c, 0, g->nv));
+  if (!g->d_sq || g->sq_len != g->support_len) {
+    if (g->d_sq) GM_CUDA(dfree(g, g->d_sq));
+    g->d_sq = nullptr;
+    if (dmalloc(g, &g->d_sq, sizeof(unsigned long long) * size_t(g->support_len > 0 ? g->support_len : 1)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (per-edge 4-cycle counts)"); return GM_ENOMEM; }
+    g->sq_len = g->support_len;
+  }
+  *ok = true;
+  return GM_OK;
+}
+
+int run_house_fast(gm_graph *g, int *launches) {
+  gm_graph *c = g->dag_child;
+  GM_TRY(run_support_pass(g, launches));
+  GM_CUDA(cudaMemsetAsync(g->d_ticket, 0, 8 * sizeof(int), g->stream));
+  GM_CUDA(cudaMemsetAsync(g->d_sq, 0, sizeof(unsigned long long) * size_t(g->sq_len), g->stream));
+  GM_TRY(launch_c4_tiers(g, c, g->d_counts + 7, launches, g->d_sq));        // the cycle total itself is not needed: scratch counter
+  k_house_sum<<<g->num_sms * 8, 256, 0, g->stream>>>(g->sq_len, g->d_support, g->d_sq, g->d_counts);
+  (*launches)++;
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
 int run_motif4_fast(gm_graph *g, int *launches) {
   // 1. supports (full graph)
   GM_TRY(run_support_pass(g, launches));
@@ -603,6 +800,7 @@ int run_motif4_fast(gm_graph *g, int *launches) {
 // everything after the support pass: closed forms over the owned edges, 4-cycles, 4-cliques
 int run_motif4_rest(gm_graph *g, int *launches) {
   gm_graph *c = g->dag_child;
+  trace_phase(g->stream, "supports");
   GM_CUDA(cudaMemsetAsync(g->d_ticket, 0, 8 * sizeof(int), g->stream));        // tickets are reused below
   if (c->nv > 0) {
     k_motif4_closed<<<nblk(int64_t(c->nv) * 8), 256, 0, g->stream>>>(c->nv, c->rk_vinfo, c->rk_acol, c->rk_orig, g->d_support,
@@ -624,6 +822,7 @@ int run_motif4_rest(gm_graph *g, int *launches) {
     c->d_counts = save;
     GM_TRY(r);
   }
+  trace_phase(g->stream, "4-cliques (bit matrix)");
   // 4. the wedge pairs count EVERY 4-cycle; the formula wants the chordless ones: a diamond holds one
   // 4-cycle, a 4-clique three, and (vertex-induced) diamonds = raw[4]/2 - 6 raw[5] (gpu_formula.cu:86-93).
   // Shard-wise the three terms are partitioned differently, so a shard's value may wrap; the sum over the

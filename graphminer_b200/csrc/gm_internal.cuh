@@ -47,10 +47,12 @@ struct ItemList {
 struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
+  int tc_short = 16;               // TC: partner suffixes of at most this many elements are walked by one lane each (0: all warp-wide)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)
   int clique_gt1 = 256;              // threads per group of the d <= 512 class of the k-clique bit-matrix kernel (256 | 512)
+  int c4_persist = 0;                // dense cluster tier: pin the counting arrays in the L2 with a persisting access-policy window
   int c4_hash = -1;                  // mid tier of the 4-cycle count: -1 auto (by |V|), 0 dense arrays, 1 per-root hash tables
   long long c4_small_max = -1, c4_cta_max = -1, c4_mid_max = -1;   // 4-cycle tier thresholds (wedges per root); -1 = defaults
   std::string motif_algo = "auto";   // 4-motif formula: auto|fast (supports + wedge-pair 4-cycles + bit-matrix 4-cliques) | list
@@ -120,6 +122,7 @@ struct gm_graph {
   gm_graph *dag_child = nullptr;
   gm::eidType *dag_rowptr = nullptr; gm::vidType *dag_colidx = nullptr;
   uint32_t *d_support = nullptr; int64_t support_len = 0;
+  unsigned long long *d_sq = nullptr; int64_t sq_len = 0;              // per-edge 4-cycle counts (house, cycle4.cu)
   // 4-cycle counting on the ranked DAG (cycle4.cu; lives in the child handle)
   gm::eidType *c4_inrow = nullptr; uint2 *c4_incol = nullptr;        // in-rows {v, position of u in v's out-row}
   unsigned long long *c4_W = nullptr;                               // wedges per root
@@ -187,6 +190,8 @@ int prepare_motif4_fast(gm_graph *g, bool *ok, bool partial = false);
 int run_motif4_fast(gm_graph *g, int *launches);
 int run_motif4_rest(gm_graph *g, int *launches);
 int prepare_rectangle_fast(gm_graph *g, bool *ok);
+int prepare_house_fast(gm_graph *g, bool *ok);
+int run_house_fast(gm_graph *g, int *launches);
 int run_rectangle_fast(gm_graph *g, int *launches);
 void invalidate_range_structures_of_child(gm_graph *c);
 void free_c4(gm_graph *c);

@@ -646,9 +646,16 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "tc.shard") {
     if (v != "source" && v != "dest") { set_error("tc.shard: unknown value '%s'", value); return GM_EINVAL; }
     options().tc_shard = v;
+  } else if (k == "c4.persist") {
+    if (v != "0" && v != "1") { set_error("c4.persist: 0 or 1"); return GM_EINVAL; }
+    options().c4_persist = v == "1";
   } else if (k == "c4.hash") {
     if (v != "-1" && v != "0" && v != "1") { set_error("c4.hash: -1 (auto), 0 or 1"); return GM_EINVAL; }
     options().c4_hash = atoi(value);
+  } else if (k == "tc.short") {
+    char *end = nullptr; long t = strtol(value, &end, 10);
+    if (end == value || *end || t < 0 || t > 1024) { set_error("tc.short: suffix length in [0, 1024] (0 = off), got '%s'", value); return GM_EINVAL; }
+    options().tc_short = int(t);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";
@@ -713,7 +720,7 @@ int gm_graph_free(gm_graph_t *g) {
   free_aux(g);
   free_c4(g);
   if (g->dag_child) { gm_graph_free(g->dag_child); g->dag_child = nullptr; }
-  dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support); dfree(g, g->d_indeg);
+  dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support); dfree(g, g->d_indeg); dfree(g, g->d_sq);
   if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
   dfree(g, g->d_counts); dfree(g, g->d_ticket); dfree(g, g->d_scratch); dfree(g, g->d_gmat);
   // complete the stream-ordered frees now: the blocks return to the pool free of stream dependencies, so

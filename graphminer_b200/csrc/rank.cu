@@ -58,7 +58,8 @@ __global__ void k_ranked_vinfo(vidType nv, const eidType *nrow, const uint32_t *
 }
 
 // ---- per-row sorting ----------------------------------------------------------------------------------
-constexpr int kMidMax = 256;      // warp per row, bitonic network in shared memory
+constexpr int kMidMax = 256;      // warp per row, bitonic network in shared memory (8 rows per CTA)
+constexpr int kMid2Max = 2048;    // still a warp per row (4 rows per CTA, 8 KB each): no CTA barrier per network stage
 constexpr int kBigMax = 4096;     // CTA per row
 struct RowCtx {
   vidType nv;
@@ -68,8 +69,9 @@ struct RowCtx {
   vidType *acol;
   unsigned *cnt;                                     // partner records per new root
   vidType src_begin, src_end; int by_dest, full_range;
+  int derived_cnt;                                   // cnt was preset from the in-degrees: only the LAST element of a row corrects it
   int *bad;
-  vidType *lists;                                    // [0, cap): mid rows, [cap, 2cap): big rows, [2cap, 3cap): huge rows
+  vidType *lists;                                    // four lists of cap entries: rows <= 256, <= 2048, <= 4096, longer
   unsigned *nlist;                                   // their lengths
   int64_t cap;
 };
@@ -80,6 +82,16 @@ __device__ __forceinline__ bool rec_kept(const RowCtx &c, bool keep_src, vidType
   if (!c.by_dest) return keep_src;
   const vidType ob = c.orig_of[b];
   return ob >= c.src_begin && ob < c.src_end;
+}
+
+// cnt[b] = in-degree of b (every row that contains b) when the shard keeps b's records, else 0; each row then
+// takes one back for its last element, whose suffix is empty -- one atomic per row instead of one per edge
+__global__ void k_cnt_from_indeg(RowCtx c, const unsigned *__restrict__ indeg) {
+  const vidType i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.nv) return;
+  const vidType o = c.orig_of[i];
+  const bool kept = c.full_range || (o >= c.src_begin && o < c.src_end);
+  c.cnt[i] = kept ? indeg[o] : 0u;
 }
 
 // ascending bitonic sort of one key per lane
@@ -139,7 +151,7 @@ k_rows_small(RowCtx c) {
       if (d == 0) continue;                                 // warp-uniform (also rows beyond nv)
       if (d > 32) {
         if (lane == 0) {
-          const int cls = d <= kMidMax ? 0 : d <= kBigMax ? 1 : 2;
+          const int cls = d <= kMidMax ? 0 : d <= kMid2Max ? 1 : d <= kBigMax ? 2 : 3;
           c.lists[cls * c.cap + atomicAdd(&c.nlist[cls], 1u)] = vidType(i);
         }
         continue;
@@ -149,16 +161,17 @@ k_rows_small(RowCtx c) {
       if (lane < padded) c.acol[(size_t(vi[k].x) << 2) + lane] = vidType(y);
       if (lane < d && vidType(y) <= vidType(i)) atomicOr(c.bad, 1);
       const bool keep_src = v[k] >= c.src_begin && v[k] < c.src_end;
-      if (lane < d - 1 && rec_kept(c, keep_src, vidType(y))) atomicAdd(&c.cnt[y], 1u);
+      if (c.derived_cnt) { if (lane == d - 1 && rec_kept(c, keep_src, vidType(y))) atomicSub(&c.cnt[y], 1u); }
+      else if (lane < d - 1 && rec_kept(c, keep_src, vidType(y))) atomicAdd(&c.cnt[y], 1u);
     }
   }
 }
 
 // GT threads per row, the row in shared memory (P = next power of two of d, padded with kVidMax)
-template <int GT, int MAXD, int CLS>
-__global__ void __launch_bounds__(256)
+template <int GT, int MAXD, int CLS, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_rows_group(RowCtx c) {
-  constexpr int kGroups = 256 / GT;
+  constexpr int kGroups = THREADS / GT;
   __shared__ uint32_t smem[kGroups * MAXD];
   const int tid = threadIdx.x % GT, grp = threadIdx.x / GT;
   uint32_t *s = smem + grp * MAXD;
@@ -180,7 +193,8 @@ k_rows_group(RowCtx c) {
       const uint32_t x = s[t];                        // s[d..P) holds kVidMax: exactly the padding value
       dst[t] = vidType(x);
       if (t < d && vidType(x) <= i) atomicOr(c.bad, 1);
-      if (t < d - 1 && rec_kept(c, keep_src, vidType(x))) atomicAdd(&c.cnt[x], 1u);
+      if (c.derived_cnt) { if (t == d - 1 && rec_kept(c, keep_src, vidType(x))) atomicSub(&c.cnt[x], 1u); }
+      else if (t < d - 1 && rec_kept(c, keep_src, vidType(x))) atomicAdd(&c.cnt[x], 1u);
     }
     if (GT == 32) __syncwarp(); else __syncthreads();
   }
@@ -189,9 +203,9 @@ k_rows_group(RowCtx c) {
 // rows beyond kBigMax: gather + pad now, sort with one segmented radix sort, count afterwards
 __global__ void __launch_bounds__(256)
 k_rows_huge_gather(RowCtx c, eidType *seg_begin, eidType *seg_end) {
-  const int64_t n = int64_t(c.nlist[2]);
+  const int64_t n = int64_t(c.nlist[3]);
   for (int64_t q = blockIdx.x; q < n; q += gridDim.x) {
-    const vidType i = c.lists[2 * c.cap + q];
+    const vidType i = c.lists[3 * c.cap + q];
     const uint2 vi = c.vinfo[i];
     const int d = int(vi.y), padded = (d + 3) & ~3;
     const vidType *row = c.colidx + c.rowptr[c.orig_of[i]];
@@ -202,9 +216,9 @@ k_rows_huge_gather(RowCtx c, eidType *seg_begin, eidType *seg_end) {
 }
 __global__ void __launch_bounds__(256)
 k_rows_huge_finish(RowCtx c, const vidType *sorted) {
-  const int64_t n = int64_t(c.nlist[2]);
+  const int64_t n = int64_t(c.nlist[3]);
   for (int64_t q = blockIdx.x; q < n; q += gridDim.x) {
-    const vidType i = c.lists[2 * c.cap + q];
+    const vidType i = c.lists[3 * c.cap + q];
     const uint2 vi = c.vinfo[i];
     const int d = int(vi.y);
     const vidType v = c.orig_of[i];
@@ -214,7 +228,8 @@ k_rows_huge_finish(RowCtx c, const vidType *sorted) {
       const vidType x = sorted[base + t];
       c.acol[base + t] = x;
       if (x <= i) atomicOr(c.bad, 1);
-      if (t < d - 1 && rec_kept(c, keep_src, x)) atomicAdd(&c.cnt[x], 1u);
+      if (c.derived_cnt) { if (t == d - 1 && rec_kept(c, keep_src, x)) atomicSub(&c.cnt[x], 1u); }
+      else if (t < d - 1 && rec_kept(c, keep_src, x)) atomicAdd(&c.cnt[x], 1u);
     }
   }
 }
@@ -313,7 +328,7 @@ int ensure_ranked(gm_graph *g) {
     GM_CUDA(dmalloc(g, &g->rk_vinfo, sizeof(uint2) * size_t(nv)));
     GM_CUDA(dmalloc(g, &g->rk_acol, sizeof(vidType) * size_t(acol_len + 8)));   // + slack: the TMA pipeline reads whole 16-byte units (tc.algo=merge)
     GM_CUDA(dmalloc(g, &cnt, sizeof(unsigned) * nv1));
-    GM_CUDA(dmalloc(g, &lists, sizeof(vidType) * size_t(cap) * 3));
+    GM_CUDA(dmalloc(g, &lists, sizeof(vidType) * size_t(cap) * 4));
     GM_CUDA(dmalloc(g, &g->rk_prow, sizeof(eidType) * nv1));
     GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * nv1, g->stream));
     k_ranked_vinfo<<<nblk(nv), 256, 0, g->stream>>>(nv, g->rk_nrow, units, g->rk_vinfo);
@@ -324,15 +339,18 @@ int ensure_ranked(gm_graph *g) {
     c.by_dest = options().tc_shard == "dest" || g->force_dest_shard;
     c.full_range = g->src_begin == 0 && g->src_end == nv;
     c.bad = bad; c.lists = lists; c.nlist = nlist; c.cap = cap;
+    c.derived_cnt = c.full_range || c.by_dest;              // the shard filter depends on the destination only
+    if (c.derived_cnt) k_cnt_from_indeg<<<nblk(nv), 256, 0, g->stream>>>(c, indeg);
     const int wide = g->num_sms * 8;
     k_rows_small<<<unsigned(std::min<int64_t>(nblk((int64_t(nv) + kRowsInFlight - 1) / kRowsInFlight * 32), int64_t(wide) * 4)), 256, 0, g->stream>>>(c);
-    k_rows_group<32, kMidMax, 0><<<wide, 256, 0, g->stream>>>(c);
-    k_rows_group<256, kBigMax, 1><<<wide, 256, 0, g->stream>>>(c);
+    k_rows_group<32, kMidMax, 0, 256><<<wide, 256, 0, g->stream>>>(c);
+    k_rows_group<32, kMid2Max, 1, 128><<<wide, 128, 0, g->stream>>>(c);
+    k_rows_group<256, kBigMax, 2, 256><<<wide, 256, 0, g->stream>>>(c);
     unsigned h_nlist[4] = {0, 0, 0, 0};
     GM_CUDA(cudaMemcpyAsync(h_nlist, nlist, sizeof h_nlist, cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
-    if (h_nlist[2] > 0) {
-      const int nh = int(h_nlist[2]);
+    if (h_nlist[3] > 0) {
+      const int nh = int(h_nlist[3]);
       GM_CUDA(dmalloc(g, &seg, sizeof(eidType) * size_t(nh) * 2));
       GM_CUDA(dmalloc(g, &huge_tmp, sizeof(vidType) * size_t(acol_len)));
       k_rows_huge_gather<<<std::min(nh, wide), 256, 0, g->stream>>>(c, seg, seg + nh);

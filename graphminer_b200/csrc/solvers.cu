@@ -53,6 +53,7 @@ int gm_graph_prepare(gm_graph_t *g, const char *what) {
   if (w == "tc" || w == "all") GM_TRY(prepare_tc(g));
   if (w == "clique" || w == "all") { GM_TRY(ensure_coo(g, 0)); if (options().clique_algo != "list") GM_TRY(prepare_kclique_bitmap(g)); }
   if (w == "sgl:rectangle" && options().sgl_algo != "list") { bool ok = false; GM_TRY(prepare_rectangle_fast(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
+  else if (w == "sgl:house" && options().sgl_algo != "list") { bool ok = false; GM_TRY(prepare_house_fast(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
   else if (w == "sgl:diamond" && options().sgl_algo != "list") { bool ok = false; GM_TRY(prepare_diamond_support(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
   else if (w.rfind("sgl", 0) == 0 || w == "all") GM_TRY(ensure_coo(g, 1));
   if (w == "motif:formula4" && options().motif_algo != "list") { bool ok = false; GM_TRY(prepare_motif4_fast(g, &ok)); if (!ok) GM_TRY(ensure_coo(g, 1)); }
@@ -80,15 +81,17 @@ int gm_sgl(gm_graph_t *g, const char *pattern, uint64_t *total) {
   if (!g || !total) { set_error("gm_sgl: null argument"); return GM_EINVAL; }
   int pid = pattern_id(pattern);
   if (pid < 0) { set_error("sgl: pattern '%s' not supported (diamond, rectangle, house, pentagon)", pattern ? pattern : "(null)"); return GM_EUNSUPPORTED; }
-  bool support = false, cycles = false;
+  bool support = false, cycles = false, house = false;
   if (pid == 0 && options().sgl_algo != "list") GM_TRY(prepare_diamond_support(g, &support));
   if (pid == 1 && options().sgl_algo != "list") GM_TRY(prepare_rectangle_fast(g, &cycles));
-  if (!support && !cycles) GM_TRY(ensure_coo(g, 1));
+  if (pid == 2 && options().sgl_algo != "list") GM_TRY(prepare_house_fast(g, &house));
+  if (!support && !cycles && !house) GM_TRY(ensure_coo(g, 1));
   int launches = 0;
   g->last_alg_bytes = 0; g->last_alg_kind = pid == 0 ? 3 : 0;
   GM_TRY(begin_timed(g));
   if (support) GM_TRY(run_diamond_support(g, &launches));
   else if (cycles) GM_TRY(run_rectangle_fast(g, &launches));
+  else if (house) GM_TRY(run_house_fast(g, &launches));
   else GM_TRY(run_sgl(g, pid, &launches));
   return end_timed(g, launches, 1, total);
 }

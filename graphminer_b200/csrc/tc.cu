@@ -129,6 +129,31 @@ __device__ __forceinline__ uint32_t stream_partners_simple(const RowTable &tab, 
   return c;
 }
 
+// Mixed form (tc.short = T > 0): of the 32 records a warp holds, those longer than T are streamed warp-wide as
+// above, the others are walked by their OWN lane, four elements per round -- a suffix of a handful of elements
+// costs a whole warp ~75 instructions in the warp-wide loop (44 % of the records of an R-MAT DAG are at most 32
+// elements long and carry 7 % of the elements), here all short records of the group share the rounds.
+__device__ __forceinline__ uint32_t stream_partners_mixed(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane, int short_max) {
+  uint32_t c = 0;
+  const bool is_short = lane < np && int(pv.y) <= short_max;
+  for (unsigned m = __ballot_sync(kFullMask, lane < np && !is_short); m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    const uint32_t off = __shfl_sync(kFullMask, pv.x, j);
+    const int len = int(__shfl_sync(kFullMask, pv.y, j));
+    const vidType *p = acol + off + lane;
+    for (int rem = len; rem > 0; rem -= 128, p += 128)
+      c += probe_block(tab, s1, ldg_or_pad(p, rem > lane), ldg_or_pad(p + 32, rem > lane + 32),
+                       ldg_or_pad(p + 64, rem > lane + 64), ldg_or_pad(p + 96, rem > lane + 96), rem);
+  }
+  const int mylen = is_short ? int(pv.y) : 0;
+  const int maxlen = __reduce_max_sync(kFullMask, mylen);
+  const vidType *q = acol + pv.x;
+  for (int e = 0; e < maxlen; e += 4)
+    c += probe_block(tab, s1, ldg_or_pad(q + e, mylen > e), ldg_or_pad(q + e + 1, mylen > e + 1),
+                     ldg_or_pad(q + e + 2, mylen > e + 2), ldg_or_pad(q + e + 3, mylen > e + 3), maxlen - e > 2 ? 128 : 64);
+  return c;
+}
+
 // Fallback when the root row does not fit the table: search it where it lies (global / L2).
 __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, const vidType *list, int len, int lane) {
   uint32_t c = 0;
@@ -144,7 +169,7 @@ template <int GT, int MAXB1, int CAP, int MODE, bool PIPE>
 __global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
 tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
                const uint2 *__restrict__ prec,
-               const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
+               const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int short_max) {
   using Cfg = GroupCfg<GT>;
   extern __shared__ uint32_t smem[];
   __shared__ int64_t s_next;
@@ -201,7 +226,9 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
         if (fits) {
           // ranked rows: pv = {element offset, length} of the suffix; whole aligned rows: offsets in 16-byte units
           const uint2 ev = MODE == 2 ? pv : make_uint2(pv.x << 2, pv.y);
-          c += PIPE ? stream_partners(tab, s1, g.d_acol, ev, np, lane) : stream_partners_simple(tab, s1, g.d_acol, ev, np, lane);
+          c += PIPE ? stream_partners(tab, s1, g.d_acol, ev, np, lane)
+                    : short_max > 0 ? stream_partners_mixed(tab, s1, g.d_acol, ev, np, lane, short_max)
+                                    : stream_partners_simple(tab, s1, g.d_acol, ev, np, lane);
         } else {
           for (int j = 0; j < np; j++) {
             uint32_t off = __shfl_sync(kFullMask, pv.x, j);
@@ -321,7 +348,7 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
   const eidType *prow = g->d_rowptr; const vidType *pcol = g->d_colidx; const uint2 *prec = nullptr;
   if (MODE == 1) { prow = g->d_rrowptr; pcol = g->d_rcolidx; }
   if (MODE == 2) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; prow = g->rk_prow; pcol = nullptr; prec = g->rk_prec; }
-  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(view, prow, pcol, prec, il.d_items, il.n, g->d_ticket + cls, g->d_counts);
+  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(view, prow, pcol, prec, il.d_items, il.n, g->d_ticket + cls, g->d_counts, options().tc_short);
   (*launches)++;
   return GM_OK;
 }

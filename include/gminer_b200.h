@@ -65,7 +65,8 @@ int gm_device_init(int device);
  *       prefetch in the TC stream loop; measured slower, off by default), "tc.gt2" = 256|512, "sup.gt2" =
  *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
  *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers), "c4.hash" = -1|0|1
- *       (cluster tier on dense |V|-sized arrays or per-root hash tables; auto by |V|).
+ *       (cluster tier on dense |V|-sized arrays or per-root hash tables; auto by |V|), "c4.persist" = 0|1 (pin the
+ *       dense arrays in the L2 with a persisting access-policy window; measured: no effect, off).
  *       Unknown key or out-of-range value -> GM_EINVAL.  Options are process-global: set them before the
  *       solver calls, not concurrently with them. */
 int gm_set_option(const char *key, const char *value);
@@ -204,7 +205,13 @@ int gm_motif_host(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int6
  * (device int32 array): a_i = pool[a_off[i] .. a_off[i]+a_len[i]).  `bound` / `anc` arrays may be
  * NULL when the op does not use them.  out[i] (device uint64) receives the count; for the
  * materialising ops (GM_OP_*_SET) d_out_pool/out_off receive the elements as well.
- * algo: GM_ALGO_AUTO or one specific variant (each variant is what gets an ncu capture). */
+ * algo: GM_ALGO_AUTO or one specific variant (each variant is what gets an ncu capture).  The counting ops
+ * (GM_OP_INTERSECT_NUM .. GM_OP_DIFFERENCE_NUM_BOUND) run on every variant; the materialising ops and
+ * GM_OP_COUNT_SMALLER take GM_ALGO_AUTO / GM_ALGO_BSEARCH (operator API).
+ * Pool contract of the TMA-staged variants (AUTO on an aligned pool, MERGE, GALLOP): lists are bulk-copied in whole
+ * 16-byte units, so up to 12 bytes before and after every list are READ (never interpreted): d_pool must be
+ * 16-byte aligned (GM_ALGO_MERGE returns GM_EINVAL otherwise; AUTO and GALLOP fall back to the operator API) and
+ * must stay readable for 16 bytes past its last list -- pad the allocation.  At most 2^31 - 1 pairs per call. */
 enum {
   GM_OP_INTERSECT_NUM = 0,        /* |a ∩ b|                       set_intersect.cuh:352-357, VertexSet.h:65-76 */
   GM_OP_INTERSECT_NUM_BOUND = 1,  /* |{x∈a∩b : x<bound}|           set_intersect.cuh:428-433, VertexSet.h:110-122 */

@@ -39,7 +39,7 @@ def counts(out, kind):
         m = re.findall(r"total_num_triangles = (\d+)", out)
     elif kind == "clique4":
         m = re.findall(r"num_4-cliques = (\d+)", out)
-    elif kind == "diamond":
+    elif kind in ("diamond", "house", "rectangle"):
         m = re.findall(r"total_num = (\d+)", out)
     else:
         m = re.findall(r"pattern \d+: (\d+)", out)
@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--clique-scale", type=int, default=21)
     ap.add_argument("--lj-div", type=int, default=1)
     ap.add_argument("--fr-div", type=int, default=64)
+    ap.add_argument("--house-div", type=int, default=8, help="LiveJournal shape divisor for house / rectangle (the reference GPU kernels are slow there)")
     a = ap.parse_args()
     dev = "cuda:0"
     jobs = {
@@ -62,6 +63,10 @@ def main():
         "clique4": dict(graph=lambda: rmat_graph(a.clique_scale, device=dev), name=f"rmat{a.clique_scale}", ref=["clique_gpu_base"], ours=["clique_gpu_base"], args=["4"]),
         "diamond": dict(graph=lambda: shaped_graph(4_847_571 // a.lj_div, 68_993_773 // a.lj_div, 0x5EED004C, device=dev),
                         name=f"lj_div{a.lj_div}", ref=["sgl_gpu_count"], ours=["sgl_gpu_base"], args=["diamond"]),
+        "house": dict(graph=lambda: shaped_graph(4_847_571 // a.house_div, 68_993_773 // a.house_div, 0x5EED004C, device=dev),
+                      name=f"lj_div{a.house_div}", ref=["sgl_gpu_base"], ours=["sgl_gpu_base"], args=["house"]),
+        "rectangle": dict(graph=lambda: shaped_graph(4_847_571 // a.house_div, 68_993_773 // a.house_div, 0x5EED004C, device=dev),
+                          name=f"lj_div{a.house_div}", ref=["sgl_gpu_base"], ours=["sgl_gpu_base"], args=["rectangle"]),
         "motif4": dict(graph=lambda: shaped_graph(65_608_366 // a.fr_div, 1_806_067_135 // a.fr_div, 0x5EED00F5, probs=(0.45, 0.22, 0.22, 0.11), device=dev),
                        name=f"friendster_div{a.fr_div}", ref=["motif_gpu_formula"], ours=["motif_gpu_formula"], args=["4"]),
     }
@@ -82,7 +87,7 @@ def main():
             f = g.tc if kind == "tc" else (lambda: g.kclique(4))
         else:
             g = capi.DeviceGraph(rp_h, ci_h, md)
-            f = (lambda: g.sgl("diamond")) if kind == "diamond" else (lambda: g.motif(4, formula=True))
+            f = (lambda k=kind: g.sgl(k)) if kind in ("diamond", "house", "rectangle") else (lambda: g.motif(4, formula=True))
         f(); want = f(); ours_kernel_ms = g.last_stats()[0]
         g.close(); del g
         torch.cuda.empty_cache()

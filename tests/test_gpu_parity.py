@@ -32,6 +32,9 @@ def _reset_options():
     capi.set_option("c4.mid_max", -1)
     capi.set_option("c4.cta_max", -1)
     capi.set_option("c4.hash", -1)
+    capi.set_option("c4.persist", 1)
+    capi.set_option("tc.short", 0)
+    capi.set_option("tc.pipe", 0)
 
 
 def _graph(name):
@@ -663,3 +666,62 @@ def test_motif4_partitioned_support_exchange():
     finally:
         for g in gs:
             g.close()
+
+
+@pytest.mark.parametrize("short_max", [1, 8, 32, 1000])
+@pytest.mark.parametrize("pipe", [0, 1])
+def test_tc_stream_loop_variants(short_max, pipe):
+    """tc.short (suffixes walked by one lane each) and tc.pipe (cross-partner prefetch) are schedules of the same
+    count: every golden graph, the ranked and the unranked table kernels, and the support / clique kernels that
+    share the partner records stay exact"""
+    capi.set_option("tc.short", short_max)
+    capi.set_option("tc.pipe", pipe)
+    for name in ("rmat8", "rmat12", "rmat14", "shaped3000"):
+        rp, ci = _graph(name)
+        orp, oci, md = _dag(rp, ci)
+        for algo in ("rank", "hash", "hash_rev"):
+            capi.set_option("tc.algo", algo)
+            with capi.DeviceGraph(orp, oci, md) as g:
+                assert g.tc() == GOLD[name]["tc"], (name, algo)
+    rp, ci, _ = _complete_dag(300)
+    capi.set_option("tc.algo", "rank")
+    with capi.DeviceGraph(rp, ci, 299) as g:
+        assert g.tc() == 300 * 299 * 298 // 6
+
+
+def test_c4_persisting_window_is_only_a_hint():
+    for persist in (0, 1):
+        capi.set_option("c4.persist", persist)
+        capi.set_option("c4.small_max", 0); capi.set_option("c4.cta_max", 0)
+        rp, ci = _graph("rmat12")
+        with capi.DeviceGraph(rp, ci, 0) as g:
+            assert g.motif(4, formula=True) == GOLD["rmat12"]["motif4_formula"]
+
+
+@pytest.mark.parametrize("hash_tier", [0, 1])
+@pytest.mark.parametrize("small_max,cta_max,mid_max", [(-1, -1, -1), (0, -1, -1), (0, 0, -1), (0, 0, 0), (16, 100, 300)])
+def test_house_on_the_dag_machinery(small_max, cta_max, mid_max, hash_tier, citeseer, mico):
+    """house = sum_e [t(e) sq(e) - 2 t(e)^2 + 2 t(e)]: supports + per-edge 4-cycle counts attributed by every tier
+    of the wedge-pair kernel (cycle4.cu ATTR) against the README counts, the reference OMP goldens and the
+    operator-API kernel"""
+    capi.set_option("c4.small_max", small_max); capi.set_option("c4.cta_max", cta_max); capi.set_option("c4.mid_max", mid_max)
+    capi.set_option("c4.hash", hash_tier)
+    cases = [(citeseer[0], citeseer[1], KAT["citeseer"]["house"])]
+    if small_max == -1:
+        cases.append((mico[0], mico[1], KAT["mico"]["house"]))
+    for name in ("rmat8", "rmat10", "shaped3000"):
+        rp, ci = _graph(name)
+        cases.append((rp, ci, GOLD[name]["house"] if "house" in GOLD[name] else oracle.sgl(rp, ci, "house")))
+    for rp, ci, want in cases:
+        with capi.DeviceGraph(rp, ci, 0) as g:
+            assert g.sgl("house") == want
+            assert g.sgl("house") == want                      # cached structures, cleared tables
+            assert g.sgl("rectangle") == oracle.sgl(rp, ci, "rectangle") if len(rp) < 5000 else True
+    capi.set_option("sgl.algo", "list")
+    rp, ci = _graph("rmat10")
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        want = oracle.sgl(rp, ci, "house")
+        assert g.sgl("house") == want
+        g.set_source_range(10, 500)                              # a shard keeps the operator-API kernel
+        capi.set_option("sgl.algo", "auto")
+        assert g.sgl("house") == oracle.sgl(rp, ci, "house", (10, 500))
