@@ -30,7 +30,7 @@ SYMBOLS = [
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
     "gm_host_alloc", "gm_host_free", "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
     "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_motif_support_begin", "gm_motif_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
-    "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info",
+    "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info", "gm_graph_device_view",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
     "gm_motif_formula_finish", "gm_last_stats", "gm_last_alg_bytes",
     "gm_tc_host", "gm_kclique_host", "gm_sgl_host", "gm_motif_host",

@@ -57,6 +57,18 @@ __global__ void k_members(GraphGPU g, const vidType *anc, int nanc, vidType boun
   atomicAdd(&out[4], a); atomicAdd(&out[5], b);
 }
 
+// warp 0: the materialising except forms, the bounded ancestor-list count and the 3-way intersection
+__global__ void k_except_forms(GraphGPU g, vidType anc, vidType bound, const vidType *ancs, int nanc, vidType *o1, vidType *o2, vidType *o3, int *sizes) {
+  if (threadIdx.x >= 32) return;
+  const vidType *a = g.N(0), *b = g.N(1), *c = g.N(2);
+  const vidType na = g.get_degree(0), nb = g.get_degree(1), nc = g.get_degree(2);
+  const int n1 = intersect_except(a, na, b, nb, anc, o1);
+  const int n2 = intersect_bound_except(a, na, b, nb, bound, anc, o2);
+  unsigned long long n3 = warp_reduce((unsigned long long)intersect_num(a, na, b, nb, bound, ancs, nanc));
+  const int n4 = intersect(a, na, b, nb, c, nc, o3);
+  if ((threadIdx.x & 31) == 0) { sizes[0] = n1; sizes[1] = n2; sizes[2] = int(n3); sizes[3] = n4; }
+}
+
 static std::vector<vidType> sorted_unique(std::mt19937 &rng, int n, int range) {
   std::vector<vidType> v(n);
   for (auto &x : v) x = vidType(rng() % range);
@@ -144,6 +156,29 @@ int main() {
       for (unsigned long long i = 0; i < m; i++) if (scr[i] != a[i]) { printf("list_smaller wrote %d at %llu, want %d\n", scr[i], i, a[i]); return 1; }
     }
     CK(cudaFree((void *)g.d_rowptr)); CK(cudaFree((void *)g.d_colidx)); CK(cudaFree(danc)); CK(cudaFree(dscr)); CK(cudaFree(dout));
+  }
+  for (auto &pr : pairs) {
+    std::vector<vidType> a = sorted_unique(rng, pr[0], 9000), b = sorted_unique(rng, pr[1], 9000), c = sorted_unique(rng, 4000, 9000);
+    std::vector<vidType> ab; std::set_intersection(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(ab));
+    std::vector<vidType> abc; std::set_intersection(ab.begin(), ab.end(), c.begin(), c.end(), std::back_inserter(abc));
+    const vidType anc = ab.empty() ? 3 : ab[ab.size() / 3], bound = ab.empty() ? 100 : ab[ab.size() / 2] + 1;
+    std::vector<vidType> ancs = {anc, ab.empty() ? 5 : ab[0], -3};
+    std::vector<vidType> w1, w2; int w3 = 0;
+    for (vidType x : ab) { if (x != anc) w1.push_back(x); if (x != anc && x < bound) w2.push_back(x); if (x < bound && std::find(ancs.begin(), ancs.end(), x) == ancs.end()) w3++; }
+    std::vector<eidType> rp = {0, eidType(a.size()), eidType(a.size() + b.size()), eidType(a.size() + b.size() + c.size())};
+    std::vector<vidType> ci = a; ci.insert(ci.end(), b.begin(), b.end()); ci.insert(ci.end(), c.begin(), c.end());
+    GraphGPU g{}; g.num_vertices = 3; g.num_edges = eidType(ci.size()); g.d_rowptr = upload(rp); g.d_colidx = upload(ci);
+    const size_t cap = std::max<size_t>(std::min(a.size(), b.size()), 1);
+    vidType *o1, *o2, *o3, *dancs = upload(ancs); int *dsz;
+    CK(cudaMalloc(&o1, cap * 4)); CK(cudaMalloc(&o2, cap * 4)); CK(cudaMalloc(&o3, cap * 4)); CK(cudaMalloc(&dsz, 16));
+    k_except_forms<<<1, 64>>>(g, anc, bound, dancs, int(ancs.size()), o1, o2, o3, dsz);
+    int sz[4]; CK(cudaMemcpy(sz, dsz, 16, cudaMemcpyDeviceToHost));
+    auto fetch = [&](vidType *d, int n) { std::vector<vidType> h(std::max(n, 0)); if (n > 0) CK(cudaMemcpy(h.data(), d, size_t(n) * 4, cudaMemcpyDeviceToHost)); return h; };
+    if (fetch(o1, sz[0]) != w1) { printf("intersect_except |a|=%zu |b|=%zu: %d elements, want %zu\n", a.size(), b.size(), sz[0], w1.size()); return 1; }
+    if (fetch(o2, sz[1]) != w2) { printf("intersect_bound_except |a|=%zu |b|=%zu: %d elements, want %zu\n", a.size(), b.size(), sz[1], w2.size()); return 1; }
+    if (sz[2] != w3) { printf("intersect_num(bound, ancestors[]) got %d want %d\n", sz[2], w3); return 1; }
+    if (fetch(o3, sz[3]) != abc) { printf("intersect(a,b,c) |a|=%zu |b|=%zu: %d elements, want %zu\n", a.size(), b.size(), sz[3], abc.size()); return 1; }
+    CK(cudaFree((void *)g.d_rowptr)); CK(cudaFree((void *)g.d_colidx)); CK(cudaFree(o1)); CK(cudaFree(o2)); CK(cudaFree(o3)); CK(cudaFree(dancs)); CK(cudaFree(dsz));
   }
   printf("gm_ops_selftest ok\n");
   return 0;

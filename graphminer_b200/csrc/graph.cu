@@ -775,6 +775,19 @@ int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, 
   return GM_OK;
 }
 
+int gm_graph_device_view(gm_graph_t *g, int sym_break, void *view_out, size_t view_size, void **stream_out,
+                         int *num_sms, int32_t *max_degree) {
+  if (!g || !view_out || (sym_break != 0 && sym_break != 1)) { set_error("gm_graph_device_view: bad arguments"); return GM_EINVAL; }
+  if (view_size != sizeof(GraphGPU)) { set_error("gm_graph_device_view: caller was built against another gm/graph_gpu.cuh (%zu != %zu bytes)", view_size, sizeof(GraphGPU)); return GM_EINVAL; }
+  GM_TRY(ensure_coo(g, sym_break));
+  GraphGPU v = g->view(sym_break);
+  memcpy(view_out, &v, sizeof v);
+  if (stream_out) *stream_out = g->stream;
+  if (num_sms) *num_sms = g->num_sms;
+  if (max_degree) *max_degree = g->max_degree;
+  return GM_OK;
+}
+
 int gm_last_stats(gm_graph_t *g, float *kernel_ms, int *launches) {
   if (!g) { set_error("null graph"); return GM_EINVAL; }
   if (g->stats_pending) {

@@ -280,6 +280,56 @@ __device__ __forceinline__ T intersect(const T *a, T size_a, const T *b, T size_
   return detail::probe_set<true>(keys, nk, idx, upper_bound, detail::NoFilter(), c);
 }
 
+// materialising forms with excluded ancestors (VertexSet::intersect_except / intersect_bound_except,
+// VertexSet.h:124-148; the reference has no GPU counterpart) and with a bound plus an ancestor LIST
+// (intersect_ns_bound_except, VertexSet.h:207-222, as a count)
+template <typename T = vidType>
+__device__ __forceinline__ T intersect_except(const T *a, T size_a, const T *b, T size_b, T ancestor, T *c) {
+  if (size_a == 0 || size_b == 0) return 0;
+  const T *keys = a, *srch = b; T nk = size_a, ns = size_b;
+  if (size_a > size_b) { keys = b; srch = a; nk = size_b; ns = size_a; }
+  WarpIndex<T> idx; idx.build(srch, ns);
+  return detail::probe_set<true>(keys, nk, idx, (T)kVidMax, detail::Except1{ancestor}, c);
+}
+template <typename T = vidType>
+__device__ __forceinline__ T intersect_bound_except(const T *a, T size_a, const T *b, T size_b, T upper_bound, T ancestor, T *c) {
+  if (size_a == 0 || size_b == 0) return 0;
+  const T *keys = a, *srch = b; T nk = size_a, ns = size_b;
+  if (size_a > size_b) { keys = b; srch = a; nk = size_b; ns = size_a; }
+  WarpIndex<T> idx; idx.build(srch, ns);
+  return detail::probe_set<true>(keys, nk, idx, upper_bound, detail::Except1{ancestor}, c);
+}
+template <typename T = vidType>
+__device__ __forceinline__ T intersect_num(const T *a, T size_a, const T *b, T size_b, T upper_bound, const T *ancestors, int n) {
+  if (size_a == 0 || size_b == 0) return 0;
+  const T *keys = a, *srch = b; T nk = size_a, ns = size_b;
+  if (size_a > size_b) { keys = b; srch = a; nk = size_b; ns = size_a; }
+  WarpIndex<T> idx; idx.build(srch, ns);
+  return detail::probe_num<true>(keys, nk, idx, upper_bound, detail::ExceptN{ancestors, n});
+}
+// a ∩ b ∩ c materialised (intersection(a,b,c), VertexSet.h:333-342): keys of the shortest list, both others searched
+template <typename T = vidType>
+__device__ __forceinline__ T intersect(const T *a, T size_a, const T *b, T size_b, const T *c3, T size_c, T *out) {
+  if (size_a == 0 || size_b == 0 || size_c == 0) return 0;
+  const T *k = a, *s1 = b, *s2 = c3; T nk = size_a, n1 = size_b, n2 = size_c;
+  if (n1 < nk) { const T *t = k; k = s1; s1 = t; const T tn = nk; nk = n1; n1 = tn; }
+  if (n2 < nk) { const T *t = k; k = s2; s2 = t; const T tn = nk; nk = n2; n2 = tn; }
+  WarpIndex<T> i1, i2; i1.build(s1, n1); i2.build(s2, n2);
+  T total = 0;
+  const int ln = lane_id();
+  for (T base = 0; base < nk; base += 32) {
+    const T i = base + ln;
+    const T key = (i < nk) ? k[i] : (T)kVidMax;
+    const bool f1 = i1.contains(key), f2 = i2.contains(key);       // warp-collective: every lane calls both
+    const bool sel = i < nk && f1 && f2;
+    const unsigned m = __ballot_sync(kFullMask, sel);
+    if (sel) out[total + __popc(m & ((1u << ln) - 1))] = key;
+    total += __popc(m);
+  }
+  __syncwarp();
+  return total;
+}
+
 // ---- difference (set_difference.cuh:20-201) ------------------------------------------------
 // Every key of `a` is searched in `b` (no swap).  `b_vid` is VertexSet::difference's silent
 // `other.vid` exclusion (VertexSet.cc:29,37); pass -1 (the default) for the reference GPU behaviour.

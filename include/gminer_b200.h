@@ -138,6 +138,13 @@ int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end);
  * "motif:formula4" (DAG, supports, 4-cycle tiers of the fast formula path), or "all".  Solvers call it lazily. */
 int gm_graph_prepare(gm_graph_t *g, const char *what);
 int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, int *device);
+/* For kernels written against the header-only operator API (a GraphMiner kernel author's own, or one emitted by
+ * graphminer_b200/codegen.py): the device view of the graph -- a gm::GraphGPU (include/gm/graph_gpu.cuh) copied into
+ * view_out, with the COO task list of Graph::init_edgelist(sym_break) built (graph_gpu.h:124-178) -- plus the
+ * stream the handle launches on, the SM count and the true maximum degree (per-warp frontier sizing,
+ * clique/gpu_base.cu:31,47-50).  view_size = sizeof(gm::GraphGPU) guards against a stale header. */
+int gm_graph_device_view(gm_graph_t *g, int sym_break, void *view_out, size_t view_size, void **stream_out,
+                         int *num_sms, int32_t *max_degree);
 
 /* ---- solvers on a device-resident graph (what *_gpu_base time: kernel only) ------------------ */
 /* TCSolver, src/triangle/gpu_base.cu:25-74.  g must be the (degree,id)-oriented DAG. */
