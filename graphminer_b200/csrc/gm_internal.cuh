@@ -48,6 +48,7 @@ struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
   int tc_short = 16;               // TC: partner suffixes of at most this many elements are walked by one lane each (0: all warp-wide)
+  int tc_flat = 1;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (0: a loop per record, 2: flat with 40 registers / 1536 threads per SM)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)

@@ -656,6 +656,9 @@ int gm_set_option(const char *key, const char *value) {
     char *end = nullptr; long t = strtol(value, &end, 10);
     if (end == value || *end || t < 0 || t > 1024) { set_error("tc.short: suffix length in [0, 1024] (0 = off), got '%s'", value); return GM_EINVAL; }
     options().tc_short = int(t);
+  } else if (k == "tc.flat") {
+    if (v != "0" && v != "1" && v != "2" && v != "3") { set_error("tc.flat: 0 .. 3"); return GM_EINVAL; }
+    options().tc_flat = atoi(value);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";

@@ -25,6 +25,8 @@ struct GroupCfg {
   // resident CTAs the register allocation must allow: 1536 threads per SM for the two main classes (the
   // prefetching stream loop holds two blocks of elements in registers: ~42 registers per thread)
   static constexpr int kMinCtas = GT == 256 ? 8 : GT == 512 ? 4 : 1;
+  // tc.flat=3: 1536 threads per SM (40 registers): room for the prefetched window
+  static constexpr int kMinCtasRelaxed = GT == 256 ? 6 : GT == 512 ? 3 : 1;
 };
 
 template <int GT>
@@ -154,6 +156,130 @@ __device__ __forceinline__ uint32_t stream_partners_mixed(const RowTable &tab, u
   return c;
 }
 
+// Flat form (tc.flat = 1, ranked graph only): the suffixes of the 32 records a warp holds are laid end to end
+// as ONE sequence of 16-byte units and the warp walks that sequence 32 units (128 elements) at a time, one
+// LDG.128 and four probes per lane, whatever records the window happens to cover.  The per-record loop above
+// pays ~45 instructions of set-up per record and rounds every suffix up to 64 or 128 elements -- at a median
+// suffix of ~40 elements more than half of the issue slots (the kernel's limiter) went there.
+//   * a suffix starts at any element of its row: it is widened to whole units.  The elements added in front
+//     are members of row a that are <= b, and the table holds N+(b), all > b: guaranteed misses, like the
+//     kVidMax padding behind the row's last element;
+//   * lane j owns record j: nu_j units from unit u0_j; pos_j = exclusive prefix sum of nu.  Slot s of the
+//     sequence belongs to the last record with pos_j <= s (no record is empty: a ranked partner record has at
+//     least one element).  Per window the records that START inside it set one bit each (REDUX.OR), a slot's
+//     record = records started before the window + head bits at or below the slot - 1: no search, no shared
+//     memory, no divergence.
+__device__ __forceinline__ uint4 ldg4_or_pad(const uint4 *p, bool live) {
+  uint4 v = make_uint4(uint32_t(kVidMax), uint32_t(kVidMax), uint32_t(kVidMax), uint32_t(kVidMax));
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"(int(live)));
+  return v;
+}
+
+// probes of one window of the flat form: 4 elements per lane, then ONE unconditional level-2 probe of the
+// lane's remembered key (px stays kVidMax, which no table stores, when the lane met no flagged slot): the
+// branch-and-diverge resolution of probe_block costs ~26 instructions per window, taken on 97 % of them.
+// Left to a slow path (the lane recounts its four elements with the full three-level lookup): two flagged
+// slots in one lane (0.4 % of the lanes) or a level-2 slot that points on to the stash.
+__device__ __forceinline__ uint32_t probe_window(const RowTable &tab, uint32_t s1, uint32_t s2, uint4 x) {
+  uint32_t c = 0, px = uint32_t(kVidMax), np = 0;
+  probe_l1(tab, s1, x.x, c, px, np);
+  probe_l1(tab, s1, x.y, c, px, np);
+  probe_l1(tab, s1, x.z, c, px, np);
+  probe_l1(tab, s1, x.w, c, px, np);
+  const uint32_t t = RowTable::lds(s2 + (((px * kHashK2) >> tab.sh2) << 2));
+  const bool miss2 = ((t ^ px) & kKeyMask) != 0;
+  c += miss2 ? 0u : 1u;
+  const bool rare = np > 1 || (np == 1 && miss2 && int32_t(t) < 0);
+  if (__any_sync(kFullMask, rare)) {
+    if (rare) c = uint32_t(tab.contains(x.x)) + uint32_t(tab.contains(x.y)) + uint32_t(tab.contains(x.z)) + uint32_t(tab.contains(x.w));
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // PTX shl: shift amounts above 31 give 0
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t stream_partners_flat(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane) {
+  const uint4 *units = reinterpret_cast<const uint4 *>(acol);
+  uint32_t s2 = uint32_t(__cvta_generic_to_shared(tab.t2));
+  const uint32_t nu = lane < np ? ((pv.x & 3u) + pv.y + 3u) >> 2 : 0u;
+  uint32_t inc = nu;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const uint32_t pos = inc - nu;                                   // lanes beyond np: pos = total (a head bit they set
+  const uint32_t total = __shfl_sync(kFullMask, inc, 31);         // in the last window only reaches dead slots)
+  const uint32_t delta = (pv.x >> 2) - pos;                        // unit of slot s of this record = delta + s
+  uint32_t le_mask = 0xffffffffu >> (31 - lane);
+  // loop invariants nvcc would otherwise re-derive in every window (S2R tid, the shared window base through
+  // S2UR/ULEA, the pointer from the constant bank: 13 of ~90 instructions): made opaque so they stay in registers
+  uint32_t ln = uint32_t(lane);
+  asm volatile("" : "+r"(ln));
+  asm volatile("" : "+r"(le_mask));
+  asm volatile("" : "+r"(s1));
+  asm volatile("" : "+r"(s2));
+  asm volatile("" : "+l"(units));
+  uint32_t started = 0;                                            // records whose first slot lies before the window
+  uint32_t c = 0;
+  for (uint32_t w = 0; w < total; w += 32) {
+    const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(1u, pos - w));
+    const int j = int(started + __popc(heads & le_mask)) - 1;
+    started += __popc(heads);
+    const uint32_t s = w + ln;
+    const uint32_t u = __shfl_sync(kFullMask, delta, j) + s;
+    c += probe_window(tab, s1, s2, ldg4_or_pad(units + u, s < total));
+  }
+  return c;
+}
+
+// The flat form with the loads of window w+1 issued before window w is probed (tc.flat = 2 | 3): the chain
+// REDUX -> SHFL -> LDG -> LDS -> LDS of one window is ~10 dependent steps, one of them a trip to L2 or HBM.
+__device__ __forceinline__ uint32_t stream_partners_flat_pipe(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane) {
+  const uint4 *units = reinterpret_cast<const uint4 *>(acol);
+  uint32_t s2 = uint32_t(__cvta_generic_to_shared(tab.t2));
+  const uint32_t nu = lane < np ? ((pv.x & 3u) + pv.y + 3u) >> 2 : 0u;
+  uint32_t inc = nu;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const uint32_t pos = inc - nu;
+  const uint32_t total = __shfl_sync(kFullMask, inc, 31);
+  const uint32_t delta = (pv.x >> 2) - pos;
+  uint32_t le_mask = 0xffffffffu >> (31 - lane);
+  uint32_t ln = uint32_t(lane);
+  asm volatile("" : "+r"(ln));
+  asm volatile("" : "+r"(le_mask));
+  asm volatile("" : "+r"(s1));
+  asm volatile("" : "+r"(s2));
+  uint32_t started = 0, c = 0;
+  auto fetch = [&](uint32_t w) {
+    const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(1u, pos - w));
+    const int j = int(started + __popc(heads & le_mask)) - 1;
+    started += __popc(heads);
+    const uint32_t s = w + ln;
+    const uint32_t u = __shfl_sync(kFullMask, delta, j) + s;
+    return ldg4_or_pad(units + u, s < total);
+  };
+  if (total == 0) return 0;
+  uint4 y = fetch(0);
+  for (uint32_t w = 32; ; w += 32) {
+    const uint4 x = y;
+    const bool more = w < total;                                   // warp-uniform
+    if (more) y = fetch(w);
+    c += probe_window(tab, s1, s2, x);
+    if (!more) break;
+  }
+  return c;
+}
+
 // Fallback when the root row does not fit the table: search it where it lies (global / L2).
 __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, const vidType *list, int len, int lane) {
   uint32_t c = 0;
@@ -165,8 +291,10 @@ __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, c
 // MODE 1: partners = in-neighbours (prow/pcol = reverse adjacency)
 // MODE 2: RANKED graph (rank.cu): g's aligned view holds the rank-relabelled rows, partners are
 //         records {element offset of the row suffix to stream, its length} in prec
-template <int GT, int MAXB1, int CAP, int MODE, bool PIPE>
-__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
+// VAR 0: stream loop chosen at run time (flat / mixed / per record), 1: cross-partner prefetch (tc.pipe),
+// 2: flat with prefetch, 3: flat with prefetch and the relaxed register allocation
+template <int GT, int MAXB1, int CAP, int MODE, int VAR>
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, VAR == 3 ? GroupCfg<GT>::kMinCtasRelaxed : GroupCfg<GT>::kMinCtas)
 tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
                const uint2 *__restrict__ prec,
                const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int short_max) {
@@ -226,7 +354,9 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
         if (fits) {
           // ranked rows: pv = {element offset, length} of the suffix; whole aligned rows: offsets in 16-byte units
           const uint2 ev = MODE == 2 ? pv : make_uint2(pv.x << 2, pv.y);
-          c += PIPE ? stream_partners(tab, s1, g.d_acol, ev, np, lane)
+          c += VAR == 1 ? stream_partners(tab, s1, g.d_acol, ev, np, lane)
+                    : (MODE == 2 && VAR >= 2) ? stream_partners_flat_pipe(tab, s1, g.d_acol, ev, np, lane)
+                    : (MODE == 2 && short_max < 0) ? stream_partners_flat(tab, s1, g.d_acol, ev, np, lane)
                     : short_max > 0 ? stream_partners_mixed(tab, s1, g.d_acol, ev, np, lane, short_max)
                                     : stream_partners_simple(tab, s1, g.d_acol, ev, np, lane);
         } else {
@@ -335,7 +465,10 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
   const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
-  auto kern = options().tc_pipe ? tc_hash_kernel<GT, MAXB1, CAP, MODE, true> : tc_hash_kernel<GT, MAXB1, CAP, MODE, false>;
+  auto kern = options().tc_pipe ? tc_hash_kernel<GT, MAXB1, CAP, MODE, 1>
+              : (MODE == 2 && options().tc_flat == 2) ? tc_hash_kernel<GT, MAXB1, CAP, MODE, MODE == 2 ? 2 : 0>
+              : (MODE == 2 && options().tc_flat == 3) ? tc_hash_kernel<GT, MAXB1, CAP, MODE, MODE == 2 ? 3 : 0>
+                                                      : tc_hash_kernel<GT, MAXB1, CAP, MODE, 0>;
   size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
   GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int occ = 0;
@@ -348,7 +481,8 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
   const eidType *prow = g->d_rowptr; const vidType *pcol = g->d_colidx; const uint2 *prec = nullptr;
   if (MODE == 1) { prow = g->d_rrowptr; pcol = g->d_rcolidx; }
   if (MODE == 2) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; prow = g->rk_prow; pcol = nullptr; prec = g->rk_prec; }
-  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(view, prow, pcol, prec, il.d_items, il.n, g->d_ticket + cls, g->d_counts, options().tc_short);
+  kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(view, prow, pcol, prec, il.d_items, il.n, g->d_ticket + cls, g->d_counts,
+                                                 (MODE == 2 && options().tc_flat) ? -1 : options().tc_short);
   (*launches)++;
   return GM_OK;
 }
