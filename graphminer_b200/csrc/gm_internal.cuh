@@ -33,6 +33,10 @@ void set_error(const char *fmt, ...);
 constexpr int kNumSMsB200 = 148;
 
 // One unit of vertex-centric work: root vertex + a slice of its partner list.
+// hybrid rows (rank.cu / tc.cu): the top kHubRanks ranks are kept as 16-rank bitmap blocks, keys below as 4 * rank + 1
+constexpr int kHubRanks = 65536;
+constexpr uint32_t kHyPad = 0x7ffffffdu;   // key padding: 1 mod 4 like every key, above all of them
+
 struct WorkItem {
   vidType root;
   vidType pbegin;   // first partner (index into the root's partner row)
@@ -48,7 +52,7 @@ struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
   int tc_short = 16;               // TC: partner suffixes of at most this many elements are walked by one lane each (0: all warp-wide)
-  int tc_flat = 1;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (0: a loop per record, 2: flat with 40 registers / 1536 threads per SM)
+  int tc_flat = 5;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (0: a loop per record, 2: flat with 40 registers / 1536 threads per SM)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)
@@ -111,6 +115,11 @@ struct gm_graph {
   gm::eidType *rk_prow = nullptr;      // per new root: offsets into rk_prec (nv+1)
   uint2 *rk_prec = nullptr;            // partner records {element offset of the suffix, length}
   gm::vidType *rk_orig = nullptr;      // new id -> original id
+  uint32_t *rk_acol4 = nullptr;        // the ranked rows as 4 * rank, padded with 0x7ffffffc (tc.flat=4, tc.cu)
+  // hybrid rows of the ranked graph (rank.cu: ensure_hybrid; tc.flat=5)
+  bool hy_ready = false, hy_valid = false;
+  uint4 *hy_vinfo = nullptr; uint32_t *hy_data = nullptr; uint4 *hy_prec = nullptr;
+  uint32_t hy_units = 0; gm::vidType hy_hb = 0;
   int64_t rk_acol_len = 0;             // elements of rk_acol (aligned, padded)
   // tc.algo=merge: every kept partner record as one (row suffix, root row) pair of gm_intersect_batch
   int64_t *mg_aoff = nullptr, *mg_boff = nullptr; int32_t *mg_alen = nullptr, *mg_blen = nullptr;
@@ -183,6 +192,7 @@ int ensure_coo(gm_graph *g, int sym_break);
 int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
+int ensure_hybrid(gm_graph *g);
 int ensure_dag_child(gm_graph *g);
 int prepare_diamond_support(gm_graph *g, bool *ok, bool partial = false);
 int run_diamond_support(gm_graph *g, int *launches);

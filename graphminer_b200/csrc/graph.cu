@@ -363,6 +363,9 @@ static void free_aux(gm_graph *g) {
     g->items_ready[s] = false;
   }
   dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec); dfree(g, g->rk_orig);
+  dfree(g, g->rk_acol4); g->rk_acol4 = nullptr;
+  dfree(g, g->hy_vinfo); dfree(g, g->hy_data); dfree(g, g->hy_prec);
+  g->hy_vinfo = nullptr; g->hy_data = nullptr; g->hy_prec = nullptr; g->hy_ready = g->hy_valid = false;
   g->rk_orig = nullptr; g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   g->rk_ready = g->rk_valid = false;
   dfree(g, g->mg_aoff); dfree(g, g->mg_boff); dfree(g, g->mg_alen); dfree(g, g->mg_blen); dfree(g, g->mg_out);
@@ -657,7 +660,7 @@ int gm_set_option(const char *key, const char *value) {
     if (end == value || *end || t < 0 || t > 1024) { set_error("tc.short: suffix length in [0, 1024] (0 = off), got '%s'", value); return GM_EINVAL; }
     options().tc_short = int(t);
   } else if (k == "tc.flat") {
-    if (v != "0" && v != "1" && v != "2" && v != "3") { set_error("tc.flat: 0 .. 3"); return GM_EINVAL; }
+    if (v != "0" && v != "1" && v != "2" && v != "3" && v != "4" && v != "5") { set_error("tc.flat: 0 .. 5"); return GM_EINVAL; }
     options().tc_flat = atoi(value);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }

@@ -253,6 +253,102 @@ k_partner_fill(RowCtx c, const eidType *prow, unsigned *cursor, uint2 *prec) {
   }
 }
 
+// ---- hybrid rows: hub bitmaps + hashed tail (tc.flat=5, tc.cu: tc_hybrid_kernel) -----------------------------
+// On a power-law graph almost every streamed element is a hub: with the rows sorted by rank, 76 % of the
+// elements the TC kernel streams on R-MAT scale 22 lie among the 4,096 highest ranks, 99.4 % among the 65,536
+// highest (profiles/README).  The hub part of a row is therefore stored as a sparse BITMAP over the top
+// kHubRanks ranks -- 4-byte entries {2 * (index of a 16-rank block) : 16, member mask : 16}, sorted by block -- and
+// the part below as plain keys (4 * rank + 1).  A root keeps the hub part of ITS row as a dense bitmap in shared
+// memory (8 KB), so that
+//     |suffix_a(b) ∩ N+(b)|  =  table hits of the non-hub suffix  +  sum over a's entries popc(mask & bitmap_b[block])
+// (every member of N+(b) ranks above b, so the entries of a need no cut at b: blocks below b's are zero in b's
+// bitmap).  One entry stands for 2.5 elements on average, its lookup walks the bitmap monotonically (sorted
+// entries in consecutive lanes: hardly a bank conflict, where a hashed probe took 3.4 wavefronts), and the
+// element that was one LDS + 8 instructions becomes 0.4 LDS.U16 + ~2 instructions.
+// Layout of hy_data (16-byte units): per ranked row [non-hub keys, padded to a unit with kPad4][entries, padded
+// with 0]; two trailing units: one of kPad4, one of zeros (what the dead lanes of a window read).
+// hy_vinfo[v] = {unit of the keys, number of keys, unit of the entries, number of entries};
+// hy_prec = per partner record {element offset of the key suffix, its length, element offset of the entries
+// from b's block on (all of them for a non-hub b), their number}, indexed by rk_prow like rk_prec.
+struct HyCtx {
+  vidType nv, hb;
+  const uint2 *vinfo; const vidType *acol;           // ranked plain rows
+  uint4 *hv; uint32_t *data;
+};
+
+// 8 lanes per row walk its sorted elements 8 at a time.  head = first element of a 16-rank hub block; the entry
+// index of a hub element = heads up to and including it - 1.  F(i, x, is_hub, entry) is called for every element.
+template <typename F>
+__device__ __forceinline__ void hy_walk_row(const HyCtx &c, vidType a, bool valid, int sub, int lane, unsigned &n_keys, unsigned &n_entries, F f) {
+  const uint2 vi = valid ? c.vinfo[a] : make_uint2(0, 0);
+  const int d = int(vi.y);
+  const vidType *row = c.acol + (size_t(vi.x) << 2);
+  const int gshift = lane & ~7;
+  const int dmax = __reduce_max_sync(kFullMask, d);
+  unsigned heads_before = 0, keys = 0;
+  int carry_blk = -3;
+  for (int i0 = 0; i0 < dmax; i0 += 8) {
+    const int i = i0 + sub;
+    const bool active = i < d;
+    const vidType x = active ? row[i] : 0;
+    const bool is_hub = active && x >= c.hb;
+    const int blk = is_hub ? int(x - c.hb) >> 4 : -2;
+    int prev = __shfl_up_sync(kFullMask, blk, 1);
+    if (sub == 0) prev = carry_blk;
+    const bool head = is_hub && blk != prev;
+    const unsigned gh = (__ballot_sync(kFullMask, head) >> gshift) & 0xffu;
+    const unsigned gk = (__ballot_sync(kFullMask, active && !is_hub) >> gshift) & 0xffu;
+    const unsigned entry = heads_before + __popc(gh & ((2u << sub) - 1u)) - 1u;
+    if (active) f(i, x, is_hub, entry, blk);
+    heads_before += __popc(gh); keys += __popc(gk);
+    carry_blk = __shfl_sync(kFullMask, blk, gshift + 7);
+  }
+  n_keys = keys; n_entries = heads_before;
+}
+
+__global__ void __launch_bounds__(256)
+k_hy_count(HyCtx c, uint32_t *units) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType a = vidType(t >> 3); const int sub = int(t & 7), lane = threadIdx.x & 31;
+  const bool valid = a < c.nv;
+  unsigned nk = 0, ne = 0;
+  hy_walk_row(c, a, valid, sub, lane, nk, ne, [](int, vidType, bool, unsigned, int) {});
+  if (valid && sub == 0) { c.hv[a] = make_uint4(0, nk, 0, ne); units[a] = ((nk + 3u) >> 2) + ((ne + 3u) >> 2); }
+}
+__global__ void k_hy_offsets(vidType nv, const uint32_t *off_units, uint4 *hv) {
+  const vidType v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  uint4 h = hv[v];
+  h.x = off_units[v]; h.z = h.x + ((h.y + 3u) >> 2);
+  hv[v] = h;
+}
+__global__ void __launch_bounds__(256)
+k_hy_fill(HyCtx c, RowCtx rc, const eidType *prow, unsigned *cursor, uint4 *prec) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType a = vidType(t >> 3); const int sub = int(t & 7), lane = threadIdx.x & 31;
+  const bool valid = a < c.nv;
+  const uint4 h = valid ? c.hv[a] : make_uint4(0, 0, 0, 0);
+  const uint32_t base_k = h.x << 2, base_e = h.z << 2;
+  const int d = valid ? int(c.vinfo[a].y) : 0;
+  bool keep_src = false;
+  if (valid) { const vidType v = rc.orig_of[a]; keep_src = v >= rc.src_begin && v < rc.src_end; }
+  unsigned nk = 0, ne = 0;
+  hy_walk_row(c, a, valid, sub, lane, nk, ne, [&](int i, vidType x, bool is_hub, unsigned entry, int blk) {
+    if (is_hub) atomicOr(&c.data[base_e + entry], (uint32_t(blk) << 17) | (1u << (uint32_t(x - c.hb) & 15u)));
+    else c.data[base_k + i] = (uint32_t(x) << 2) | 1u;
+    if (i + 1 < d && rec_kept(rc, keep_src, x)) {
+      const unsigned p = atomicAdd(&cursor[x], 1u);
+      prec[prow[x] + eidType(p)] = is_hub ? make_uint4(0u, 0u, base_e + entry, h.w - entry)
+                                          : make_uint4(base_k + uint32_t(i) + 1u, h.y - uint32_t(i) - 1u, base_e, h.w);
+    }
+  });
+  if (valid) for (uint32_t i = h.y + sub; i < ((h.y + 3u) & ~3u); i += 8) c.data[base_k + i] = kHyPad;
+}
+__global__ void k_hy_tail(uint32_t *data, uint32_t total_units) {
+  const int i = threadIdx.x;
+  if (i < 8) data[(size_t(total_units) << 2) + i] = i < 4 ? kHyPad : 0u;
+}
+
 template <typename T>
 static int scan_inplace(gm_graph *g, T *d, int64_t n) {   // n+1 slots
   size_t tmp = 0;
@@ -386,6 +482,52 @@ int ensure_ranked(gm_graph *g) {
     g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   }
   g->rk_ready = true;
+  return GM_OK;
+}
+
+// builds the hybrid rows and their partner records on top of the ranked graph (same record counts: rk_prow)
+int ensure_hybrid(gm_graph *g) {
+  if (g->hy_ready) return GM_OK;
+  GM_TRY(ensure_ranked(g));
+  g->hy_ready = true; g->hy_valid = false;
+  const vidType nv = g->nv;
+  if (!g->rk_valid || uint64_t(nv) >= (1ull << 29)) return GM_OK;          // keys are 4 * rank + 1 below 2^31
+  GM_CUDA(cudaSetDevice(g->device));
+  HyCtx c; c.nv = nv; c.hb = nv > vidType(kHubRanks) ? nv - vidType(kHubRanks) : 0;
+  c.vinfo = g->rk_vinfo; c.acol = g->rk_acol;
+  uint32_t *units = nullptr; unsigned *cursor = nullptr;
+  GM_CUDA(dmalloc(g, &g->hy_vinfo, sizeof(uint4) * size_t(nv)));
+  GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * (size_t(nv) + 1)));
+  GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned) * (size_t(nv) + 1)));
+  c.hv = g->hy_vinfo; c.data = nullptr;
+  int rc = [&]() -> int {
+    GM_CUDA(cudaMemsetAsync(units + nv, 0, sizeof(uint32_t), g->stream));
+    GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * (size_t(nv) + 1), g->stream));
+    k_hy_count<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, units);
+    GM_TRY(scan_inplace(g, units, nv));
+    uint32_t total_units = 0;
+    GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    k_hy_offsets<<<nblk(nv), 256, 0, g->stream>>>(nv, units, g->hy_vinfo);
+    const size_t words = (size_t(total_units) + 2) << 2;
+    GM_CUDA(dmalloc(g, &g->hy_data, sizeof(uint32_t) * words));
+    GM_CUDA(cudaMemsetAsync(g->hy_data, 0, sizeof(uint32_t) * words, g->stream));      // entries are OR-ed in; padding entries stay 0
+    GM_CUDA(dmalloc(g, &g->hy_prec, sizeof(uint4) * size_t(g->ne > 0 ? g->ne : 1)));
+    c.data = g->hy_data;
+    RowCtx r{};
+    r.nv = nv; r.orig_of = g->rk_orig; r.src_begin = g->src_begin; r.src_end = g->src_end;
+    r.by_dest = options().tc_shard == "dest" || g->force_dest_shard;
+    r.full_range = g->src_begin == 0 && g->src_end == nv;
+    k_hy_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, r, g->rk_prow, cursor, g->hy_prec);
+    k_hy_tail<<<1, 32, 0, g->stream>>>(g->hy_data, total_units);
+    GM_CUDA(cudaGetLastError());
+    g->hy_units = total_units; g->hy_hb = c.hb;
+    return GM_OK;
+  }();
+  dfree(g, units); dfree(g, cursor);
+  if (rc != GM_OK) return rc;
+  g->hy_valid = true;
+  trace_phase(g->stream, "rank: hybrid rows (hub bitmaps + keys)");
   return GM_OK;
 }
 

@@ -376,6 +376,330 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
 }
 
 // ------------------------------------------------------------------------------------------
+// tc.flat = 4: the ranked kernel on keys stored as 4 * rank + 1 (g->rk_acol4, built once by k_scale_keys).
+//
+// After the flat form the stream loop was 84 instructions per window of 128 elements, IPC 3.2 of 4
+// (profiles/r02p_tc_s22_flat1.summary.txt): 36 in the four probes, 14 in the level-2 probe and its checks.
+// With every key = 1 mod 4 and below 2^31:
+//   * the level-1 slot's BYTE offset is one LOP3 (key & mask4; the low bits of a rank are as good as a
+//     multiplicative hash: hub ranks are consecutive, the others arbitrary) and the table base rides in the
+//     LDS address -- IMAD + SHF + LEA before;
+//   * the two low bits count flagged slots: one predicated add (r += key) remembers the key AND counts it,
+//     where the flat form spent SEL + IADD; r & 3 == 1 afterwards means "exactly one, and r is its key".
+// Rows are padded with kPad4 (1 mod 4, above every key), and dead slots of a batch's last window read a unit
+// of padding behind the array instead of presetting four registers.
+constexpr uint32_t kPad4 = kHyPad;
+
+struct ScaledTable {
+  uint32_t *t1, *t2, *stash;
+  int *nstash;
+  uint32_t mask4;    // (S1 - 1) << 2
+  int sh2, stash_cap;
+
+  __device__ __forceinline__ void configure(uint32_t *base, int b1, int cap) {
+    const int b2 = max(b1 - 2, 3);
+    t1 = base; t2 = base + (1 << b1); stash = t2 + (1 << b2);
+    nstash = reinterpret_cast<int *>(stash + cap);
+    mask4 = ((1u << b1) - 1u) << 2; sh2 = 32 - b2; stash_cap = cap;
+  }
+  __device__ __forceinline__ uint32_t &slot1(uint32_t x) const { return t1[(x & mask4) >> 2]; }
+  __device__ __forceinline__ uint32_t &slot2(uint32_t x) const { return t2[(x * kHashK2) >> sh2]; }
+  // same protocol as RowTable::build: store, re-read, losers move one level down, flags mark the way
+  template <typename SYNC>
+  __device__ __forceinline__ void build(const uint32_t *row, int d, int tid, int nthr, SYNC sync) {
+    const int n = int(mask4 >> 2) + 1 + (1 << (32 - sh2));
+    for (int i = tid; i < n; i += nthr) t1[i] = kSlotEmpty;
+    if (tid == 0) *nstash = 0;
+    sync();
+    for (int i = tid; i < d; i += nthr) { const uint32_t x = __ldg(row + i); slot1(x) = x; }
+    sync();
+    for (int i = tid; i < d; i += nthr) {
+      const uint32_t x = __ldg(row + i), t = slot1(x);
+      if ((t & kKeyMask) != x) { slot1(x) = t | kSlotFlag; slot2(x) = x; }
+    }
+    sync();
+    for (int i = tid; i < d; i += nthr) {
+      const uint32_t x = __ldg(row + i);
+      if ((slot1(x) & kKeyMask) == x) continue;
+      const uint32_t t = slot2(x);
+      if ((t & kKeyMask) != x) {
+        slot2(x) = t | kSlotFlag;
+        const int p = atomicAdd(nstash, 1);
+        if (p < stash_cap) stash[p] = x;
+      }
+    }
+    sync();
+  }
+  __device__ __forceinline__ bool overflowed() const { return *nstash > stash_cap; }
+  __device__ __forceinline__ bool contains(uint32_t x) const {
+    uint32_t t = slot1(x);
+    if ((t & kKeyMask) == x) return true;
+    if (!(t & kSlotFlag)) return false;
+    t = slot2(x);
+    if ((t & kKeyMask) == x) return true;
+    if (!(t & kSlotFlag)) return false;
+    const int n = min(*nstash, stash_cap);
+    for (int i = 0; i < n; i++) if (stash[i] == x) return true;
+    return false;
+  }
+};
+
+__device__ __forceinline__ void probe_scaled(uint32_t s1, uint32_t mask4, uint32_t x, uint32_t &c, uint32_t &r) {
+  const uint32_t tw = RowTable::lds(s1 + (x & mask4));
+  asm("{\n\t.reg .pred pm, pf;\n\t.reg .b32 t;\n\t"
+      "xor.b32 t, %2, %3;\n\tand.b32 t, t, 0x7fffffff;\n\tsetp.ne.u32 pm, t, 0;\n\t"
+      "@!pm add.u32 %0, %0, 1;\n\t"
+      "setp.lt.and.s32 pf, %2, 0, pm;\n\t"
+      "@pf add.u32 %1, %1, %3;\n\t}"
+      : "+r"(c), "+r"(r) : "r"(tw), "r"(x));
+}
+
+__device__ __forceinline__ uint32_t probe_window_scaled(const ScaledTable &tab, uint32_t s1, uint32_t s2, uint4 x) {
+  uint32_t c = 0, r = 0;
+  probe_scaled(s1, tab.mask4, x.x, c, r);
+  probe_scaled(s1, tab.mask4, x.y, c, r);
+  probe_scaled(s1, tab.mask4, x.z, c, r);
+  probe_scaled(s1, tab.mask4, x.w, c, r);
+  const uint32_t t = RowTable::lds(s2 + (((r * kHashK2) >> tab.sh2) << 2));     // r = the key when r & 3 == 1; 0 (never stored) when no slot was flagged
+  const bool miss2 = ((t ^ r) & kKeyMask) != 0;
+  c += miss2 ? 0u : 1u;
+  const uint32_t k = r & 3u;
+  const bool rare = k == 1u ? (miss2 && int32_t(t) < 0) : r != 0u;   // several flagged slots in the lane, or on to the stash
+  if (__any_sync(kFullMask, rare)) {
+    if (rare) c = uint32_t(tab.contains(x.x)) + uint32_t(tab.contains(x.y)) + uint32_t(tab.contains(x.z)) + uint32_t(tab.contains(x.w));
+  }
+  return c;
+}
+
+// the window walk of the flat form over per-lane segments {first unit u0, nu units}: PROBE(uint4) -> count.
+// Every live lane must own at least one unit (an empty segment is given one unit of padding by its caller):
+// the slot -> record rule counts head bits, and two records starting on one slot would share theirs.
+template <typename PROBE>
+__device__ __forceinline__ uint32_t walk_windows(const uint4 *units, uint32_t pad_unit, uint32_t u0, uint32_t nu, int lane, PROBE probe) {
+  uint32_t inc = nu;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const uint32_t pos = inc - nu;
+  const uint32_t total = __shfl_sync(kFullMask, inc, 31);
+  const uint32_t delta = u0 - pos;
+  uint32_t le_mask = 0xffffffffu >> (31 - lane), ln = uint32_t(lane), one = 1u;
+  asm volatile("" : "+r"(ln));
+  asm volatile("" : "+r"(le_mask));
+  asm volatile("" : "+r"(one));
+  uint32_t started = 0, c = 0;
+  for (uint32_t w = 0; w < total; w += 32) {
+    const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(one, pos - w));
+    const int j = int(started + __popc(heads & le_mask)) - 1;
+    started += __popc(heads);
+    const uint32_t s = w + ln;
+    uint32_t u = __shfl_sync(kFullMask, delta, j) + s;
+    u = s < total ? u : pad_unit;
+    c += probe(__ldg(units + u));
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint32_t stream_partners_scaled(const ScaledTable &tab, uint32_t s1, uint32_t s2, const uint4 *units, uint32_t pad_unit,
+                                                           uint2 pv, int np, int lane) {
+  // {element offset, length} -> whole units; an empty suffix reads one unit of padding
+  const bool live = lane < np;
+  const uint32_t u0 = pv.y ? pv.x >> 2 : pad_unit;
+  const uint32_t nu = !live ? 0u : pv.y ? ((pv.x & 3u) + pv.y + 3u) >> 2 : 1u;
+  return walk_windows(units, pad_unit, u0, nu, lane, [&](uint4 x) { return probe_window_scaled(tab, s1, s2, x); });
+}
+
+template <int GT, int MAXB1, int CAP>
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
+tc_rank_kernel(const uint2 *__restrict__ vinfo, const uint32_t *__restrict__ acol4, uint32_t pad_unit,
+               const eidType *__restrict__ prow, const uint2 *__restrict__ prec,
+               const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
+  using Cfg = GroupCfg<GT>;
+  extern __shared__ uint32_t smem[];
+  __shared__ int64_t s_next;
+  constexpr int kWords = RowTable::words_for_bits(MAXB1, CAP);
+  constexpr int kBatch = GT == 32 ? 4 : 1;
+  constexpr int W = Cfg::kWarpsPerGroup;
+  const int lane = threadIdx.x & 31;
+  const int gtid = threadIdx.x % GT;
+  const int gwarp = gtid >> 5;
+  uint32_t *gbase = smem + (threadIdx.x / GT) * kWords;
+  const uint4 *units = reinterpret_cast<const uint4 *>(acol4);
+  AccType acc = 0;
+
+  while (true) {
+    int64_t first;
+    if (GT == 32) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(ticket, kBatch);
+      first = int64_t(__shfl_sync(kFullMask, t, 0));
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) s_next = int64_t(atomicAdd(ticket, kBatch));
+      __syncthreads();
+      first = s_next;
+    }
+    if (first >= nitems) break;
+    for (int b = 0; b < kBatch && first + b < nitems; b++) {
+      const WorkItem it = items[first + b];
+      const uint2 ri = vinfo[it.root];
+      const int d = int(ri.y);
+      const uint32_t *rrow = acol4 + (size_t(ri.x) << 2);
+      ScaledTable tab;
+      const int b1 = RowTable::bits_for(d);
+      bool fits = b1 <= MAXB1;
+      if (fits) {
+        tab.configure(gbase, b1, CAP);
+        if (GT == 32) __syncwarp();
+        tab.build(rrow, d, gtid, GT, [] { group_sync<GT>(); });
+        if (tab.overflowed()) fits = false;
+      }
+      const uint2 *R = prec + prow[it.root] + it.pbegin;
+      const uint32_t s1 = uint32_t(__cvta_generic_to_shared(gbase));
+      const uint32_t s2 = s1 + (4u << b1);
+      uint32_t c = 0;
+      const int mine = (it.pcount - gwarp + W - 1) / W;
+      for (int pb = 0; pb < mine; pb += 32) {
+        const int q = pb + lane;
+        uint2 pv = make_uint2(0, 0);
+        if (q < mine) pv = __ldg(R + q * W + gwarp);
+        const int np = min(32, mine - pb);
+        if (fits) {
+          c += stream_partners_scaled(tab, s1, s2, units, pad_unit, pv, np, lane);
+        } else {
+          for (int j = 0; j < np; j++) {
+            const uint32_t off = __shfl_sync(kFullMask, pv.x, j);
+            const int len = int(__shfl_sync(kFullMask, pv.y, j));
+            c += stream_bsearch(reinterpret_cast<const vidType *>(rrow), d, reinterpret_cast<const vidType *>(acol4) + off, len, lane);
+          }
+        }
+      }
+      acc += c;
+    }
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// tc.flat = 5: hybrid rows (rank.cu: ensure_hybrid).  Per root: the non-hub keys of its row in a ScaledTable, the
+// hub part as a dense bitmap (one 16-bit mask per 16-rank block, kHubRanks / 8 bytes of shared memory); per
+// partner record two flat passes: the key suffix against the table (only when the root has non-hub keys and is
+// no hub itself), the bitmap entries against the bitmap.
+constexpr int kBitmapWords = kHubRanks / 32;
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return uint32_t(v);
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"(uint16_t(v)));
+}
+
+// four entries {2 * block : 16, mask : 16} against the root's bitmap: the entry's high half IS the byte offset
+__device__ __forceinline__ uint32_t probe_window_hub(uint32_t sb, uint4 e) {
+  const uint32_t r0 = lds_u16(sb + (e.x >> 16)) & e.x, r1 = lds_u16(sb + (e.y >> 16)) & e.y;
+  const uint32_t r2 = lds_u16(sb + (e.z >> 16)) & e.z, r3 = lds_u16(sb + (e.w >> 16)) & e.w;
+  return __popc(__byte_perm(r0, r1, 0x5410)) + __popc(__byte_perm(r2, r3, 0x5410));
+}
+
+template <int GT, int MAXB1, int CAP>
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
+tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data, uint32_t pad_keys, uint32_t pad_zero, vidType hb,
+                 const eidType *__restrict__ prow, const uint4 *__restrict__ prec,
+                 const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
+  static_assert(GT >= 256, "one group per CTA");
+  using Cfg = GroupCfg<GT>;
+  extern __shared__ uint32_t smem[];
+  __shared__ int64_t s_next;
+  constexpr int kWords = RowTable::words_for_bits(MAXB1, CAP);
+  constexpr int W = Cfg::kWarpsPerGroup;
+  const int lane = threadIdx.x & 31, tid = threadIdx.x, gwarp = tid >> 5;
+  uint32_t *bitmap = smem + kWords;
+  const uint32_t s1 = uint32_t(__cvta_generic_to_shared(smem));
+  const uint32_t sb = uint32_t(__cvta_generic_to_shared(bitmap));
+  const uint4 *units = reinterpret_cast<const uint4 *>(data);
+  for (int i = tid; i < kBitmapWords; i += GT) bitmap[i] = 0u;
+  uint4 prev = make_uint4(0, 0, 0, 0);
+  AccType acc = 0;
+
+  while (true) {
+    __syncthreads();                                 // previous item fully done (also: the bitmap is zeroed)
+    {                                                // take the previous root's blocks out of the bitmap again
+      const uint32_t *pe = data + (size_t(prev.z) << 2);
+      for (uint32_t i = tid; i < prev.w; i += GT) sts_u16(sb + (__ldg(pe + i) >> 16), 0u);
+    }
+    if (tid == 0) s_next = int64_t(atomicAdd(ticket, 1));
+    __syncthreads();
+    const int64_t first = s_next;
+    if (first >= nitems) break;
+    const WorkItem it = items[first];
+    const uint4 h = hv[it.root];
+    prev = h;
+    const uint32_t *keys = data + (size_t(h.x) << 2), *ents = data + (size_t(h.z) << 2);
+    const int nk = int(h.y);
+    for (uint32_t i = tid; i < h.w; i += GT) { const uint32_t e = __ldg(ents + i); sts_u16(sb + (e >> 16), e & 0xffffu); }
+    const bool use_keys = nk > 0 && it.root < hb;    // a hub root has no key suffixes to meet, an empty table no hits
+    ScaledTable tab;
+    int b1 = 5;
+    bool fits = true;
+    if (use_keys) {
+      b1 = RowTable::bits_for(nk);
+      fits = b1 <= MAXB1;
+      if (fits) {
+        tab.configure(smem, b1, CAP);
+        tab.build(keys, nk, tid, GT, [] { __syncthreads(); });
+        if (tab.overflowed()) fits = false;
+      }
+    }
+    if (!use_keys || !fits) __syncthreads();         // the bitmap stores (the table build ends with a barrier)
+    const uint32_t s2 = s1 + (4u << b1);
+    const uint4 *R = prec + prow[it.root] + it.pbegin;
+    uint32_t c = 0;
+    const int mine = (it.pcount - gwarp + W - 1) / W;
+    for (int pb = 0; pb < mine; pb += 32) {
+      const int q = pb + lane;
+      const bool live = q < mine;
+      uint4 rec = make_uint4(0, 0, 0, 0);
+      if (live) rec = __ldg(R + q * W + gwarp);
+      if (use_keys) {
+        if (fits) {
+          const uint32_t u0 = rec.y ? rec.x >> 2 : pad_keys;
+          const uint32_t nu = !live ? 0u : rec.y ? ((rec.x & 3u) + rec.y + 3u) >> 2 : 1u;
+          c += walk_windows(units, pad_keys, u0, nu, lane, [&](uint4 x) { return probe_window_scaled(tab, s1, s2, x); });
+        } else {
+          const int np = min(32, mine - pb);
+          for (int j = 0; j < np; j++) {
+            const uint32_t off = __shfl_sync(kFullMask, rec.x, j);
+            const int len = int(__shfl_sync(kFullMask, rec.y, j));
+            c += stream_bsearch(reinterpret_cast<const vidType *>(keys), nk, reinterpret_cast<const vidType *>(data) + off, len, lane);
+          }
+        }
+      }
+      if (h.w) {
+        const uint32_t u0 = rec.w ? rec.z >> 2 : pad_zero;
+        const uint32_t nu = !live ? 0u : rec.w ? ((rec.z & 3u) + rec.w + 3u) >> 2 : 1u;
+        c += walk_windows(units, pad_zero, u0, nu, lane, [&](uint4 e) { return probe_window_hub(sb, e); });
+      }
+    }
+    acc += c;
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+__global__ void __launch_bounds__(256)
+k_scale_keys(int64_t n, int64_t n_alloc, const vidType *__restrict__ in, uint32_t *__restrict__ out) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_alloc; i += int64_t(gridDim.x) * blockDim.x) {
+    const vidType v = i < n ? in[i] : kVidMax;
+    out[i] = v == kVidMax ? kPad4 : (uint32_t(v) << 2) | 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // warp per COO edge, operator API (the reference's schedule: bs_warp_edge.cuh:9-15)
 __global__ void __launch_bounds__(256)
 tc_warp_edge_bs(GraphGPU g, AccType *total) {
@@ -465,6 +789,33 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
   const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
+  if (MODE == 2 && GT >= 256 && options().tc_flat == 5 && !options().tc_pipe && g->hy_valid) {
+    auto kern = tc_hybrid_kernel<(GT >= 256 ? GT : 256), MAXB1, CAP>;
+    const size_t smem = sizeof(uint32_t) * (size_t(RowTable::words_for_bits(MAXB1, CAP)) + kBitmapWords);
+    GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 0;
+    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::kCtaThreads, smem));
+    if (occ < 1) { set_error("tc_hybrid_kernel<%d,%d> does not fit on an SM (smem %zu)", GT, MAXB1, smem); return GM_ECUDA; }
+    const int grid = int(std::min<int64_t>(il.n, int64_t(occ) * g->num_sms));
+    kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(g->hy_vinfo, g->hy_data, g->hy_units, g->hy_units + 1, g->hy_hb, g->rk_prow, g->hy_prec,
+                                                   il.d_items, il.n, g->d_ticket + cls, g->d_counts);
+    (*launches)++;
+    return GM_OK;
+  }
+  if (MODE == 2 && options().tc_flat == 4 && !options().tc_pipe && g->rk_acol4) {
+    auto kern = tc_rank_kernel<GT, MAXB1, CAP>;
+    const size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
+    GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 0;
+    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::kCtaThreads, smem));
+    if (occ < 1) { set_error("tc_rank_kernel<%d,%d> does not fit on an SM (smem %zu)", GT, MAXB1, smem); return GM_ECUDA; }
+    const int64_t per_cta = int64_t(Cfg::kGroupsPerCta) * (GT == 32 ? 4 : 1);
+    const int grid = int(std::min<int64_t>((il.n + per_cta - 1) / per_cta, int64_t(occ) * g->num_sms));
+    kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(g->rk_vinfo, g->rk_acol4, uint32_t(g->rk_acol_len >> 2), g->rk_prow, g->rk_prec,
+                                                   il.d_items, il.n, g->d_ticket + cls, g->d_counts);
+    (*launches)++;
+    return GM_OK;
+  }
   auto kern = options().tc_pipe ? tc_hash_kernel<GT, MAXB1, CAP, MODE, 1>
               : (MODE == 2 && options().tc_flat == 2) ? tc_hash_kernel<GT, MAXB1, CAP, MODE, MODE == 2 ? 2 : 0>
               : (MODE == 2 && options().tc_flat == 3) ? tc_hash_kernel<GT, MAXB1, CAP, MODE, MODE == 2 ? 3 : 0>
@@ -530,7 +881,19 @@ int prepare_tc(gm_graph *g) {
   std::string algo;
   GM_TRY(resolve_tc_algo(g, &algo));
   if (algo == "bs") return ensure_coo(g, 0);
-  if (algo == "rank") return ensure_items(g, 3);
+  if (algo == "rank") {
+    GM_TRY(ensure_items(g, 3));
+    // keys as 4 * rank for tc_rank_kernel (tc.flat=4); needs 4 * nv below the padding value
+    if (options().tc_flat == 5) GM_TRY(ensure_hybrid(g));
+    if (options().tc_flat == 4 && !g->rk_acol4 && g->rk_valid && uint64_t(g->nv) < (uint64_t(kPad4) >> 2)) {
+      const int64_t n_alloc = g->rk_acol_len + 8;                     // + two units of padding: the dead slots of a last window read them
+      GM_CUDA(dmalloc(g, &g->rk_acol4, sizeof(uint32_t) * size_t(n_alloc)));
+      k_scale_keys<<<g->num_sms * 8, 256, 0, g->stream>>>(g->rk_acol_len, n_alloc, g->rk_acol, g->rk_acol4);
+      GM_CUDA(cudaGetLastError());
+      trace_phase(g->stream, "tc: scaled keys");
+    }
+    return GM_OK;
+  }
   if (algo == "merge") return prepare_tc_merge(g);
   GM_TRY(ensure_aligned(g));
   return ensure_items(g, algo == "hash" ? 0 : 1);
