@@ -581,20 +581,25 @@ def run_ours(args):
         prof = ncu_profile(wl.name) if n == 1 else None
         traffic = prof.get("dram_bytes_per_step") if prof else None
         dram_gbs = traffic / (kms / 1e3) / 1e9 if traffic else None
-        kernel = {"tc": "tc_hash_kernel<MODE=2 ranked>", "clique4": "kclique_bitmap_kernel",
+        kernel = {"tc": "tc_hybrid_kernel (hub bitmaps + hashed tail; roots of <= 32 neighbours: tc_hash_kernel<MODE=2 ranked>)", "clique4": "kclique_bitmap_kernel",
                   "diamond": "tc_support_kernel + k_diamond_sum", "motif4": "tc_support_kernel + c4_{small,cta,cluster,heavy}_kernel + kclique_bitmap_kernel"}[wl.kind]
         roofline = {
             # PHYSICAL HBM fraction: DRAM bytes the pass moves (ncu, per step) / device time / measured copy peak.
             # The solvers keep their working set in shared memory and the 126 MB L2, so this is far below 1 by
-            # design; what limits them is instruction issue (`issue`), and the single-pass HBM roofline of the
+            # design; what limits them is `limiter` (instruction issue or the L1 data pipe), and the single-pass HBM roofline of the
             # intersection kernels themselves is `stream_roofline`.
             "bound": "hbm", "achieved": dram_gbs, "peak": peak, "unit": "GB/s",
             "frac": (dram_gbs / peak) if dram_gbs else None, "traffic": traffic,
             "peak_source": peak_src, "kernel": kernel + " (all size classes of one pass, run concurrently)",
             "kernel_ms_per_step": kms,
-            "limiter": "issue" if prof and prof.get("ipc") else None,
+            # what bounds the pass: the larger of the issue fraction (IPC of 4) and the L1/shared-memory data pipe
+            # (LSU wavefronts of peak: LDS bank replays + LDG data + SHFL), both from the same launch list
+            "limiter": (None if not (prof and prof.get("ipc")) else
+                        "l1_data_pipe" if (prof.get("l1_pipe") or 0.0) > prof.get("ipc") / 4.0 else "issue"),
             "issue": ({"warp_insts_per_step": prof.get("warp_insts_per_step"), "ipc": prof.get("ipc"), "ipc_peak": 4.0,
                        "frac": prof.get("ipc") / 4.0} if prof and prof.get("ipc") else None),
+            "l1_data_pipe": ({"frac": prof.get("l1_pipe"), "metric": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"}
+                             if prof and prof.get("l1_pipe") else None),
             "alg_bytes_per_step": alg_bytes,
             "alg_gbs": (alg_bytes / (kms / 1e3) / 1e9) if alg_bytes else None,
             "source": (prof.get("source") if prof else None),

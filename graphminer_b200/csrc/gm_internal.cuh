@@ -53,6 +53,7 @@ struct Options {
   std::string clique_algo = "auto";
   int tc_short = 16;               // TC: partner suffixes of at most this many elements are walked by one lane each (0: all warp-wide)
   int tc_flat = 5;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (0: a loop per record, 2: flat with 40 registers / 1536 threads per SM)
+  int tc_hub = kHubRanks;          // hybrid rows: ranks kept as bitmap blocks (a multiple of 16, at most kHubRanks; smaller values are a test hook)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)
@@ -118,7 +119,9 @@ struct gm_graph {
   uint32_t *rk_acol4 = nullptr;        // the ranked rows as 4 * rank, padded with 0x7ffffffc (tc.flat=4, tc.cu)
   // hybrid rows of the ranked graph (rank.cu: ensure_hybrid; tc.flat=5)
   bool hy_ready = false, hy_valid = false;
-  uint4 *hy_vinfo = nullptr; uint32_t *hy_data = nullptr; uint4 *hy_prec = nullptr;
+  uint4 *hy_vinfo = nullptr; uint32_t *hy_data = nullptr; uint2 *hy_prec = nullptr;
+  bool want_hybrid = false;            // set by prepare_tc before the ranked graph is built: ensure_hybrid will write the partner records
+  bool rk_prec_full = false;           // rk_prec holds the records of every root (else: of the roots with <= 32 neighbours only)
   uint32_t hy_units = 0; gm::vidType hy_hb = 0;
   int64_t rk_acol_len = 0;             // elements of rk_acol (aligned, padded)
   // tc.algo=merge: every kept partner record as one (row suffix, root row) pair of gm_intersect_batch
@@ -193,6 +196,7 @@ int ensure_reverse(gm_graph *g);
 int ensure_items(gm_graph *g, int mode);
 int ensure_ranked(gm_graph *g);
 int ensure_hybrid(gm_graph *g);
+int ensure_full_prec(gm_graph *g);
 int ensure_dag_child(gm_graph *g);
 int prepare_diamond_support(gm_graph *g, bool *ok, bool partial = false);
 int run_diamond_support(gm_graph *g, int *launches);

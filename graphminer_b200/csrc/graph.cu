@@ -365,7 +365,7 @@ static void free_aux(gm_graph *g) {
   dfree(g, g->rk_vinfo); dfree(g, g->rk_acol); dfree(g, g->rk_nrow); dfree(g, g->rk_prow); dfree(g, g->rk_prec); dfree(g, g->rk_orig);
   dfree(g, g->rk_acol4); g->rk_acol4 = nullptr;
   dfree(g, g->hy_vinfo); dfree(g, g->hy_data); dfree(g, g->hy_prec);
-  g->hy_vinfo = nullptr; g->hy_data = nullptr; g->hy_prec = nullptr; g->hy_ready = g->hy_valid = false;
+  g->hy_vinfo = nullptr; g->hy_data = nullptr; g->hy_prec = nullptr; g->hy_ready = g->hy_valid = false; g->rk_prec_full = false;
   g->rk_orig = nullptr; g->rk_vinfo = nullptr; g->rk_acol = nullptr; g->rk_nrow = nullptr; g->rk_prow = nullptr; g->rk_prec = nullptr;
   g->rk_ready = g->rk_valid = false;
   dfree(g, g->mg_aoff); dfree(g, g->mg_boff); dfree(g, g->mg_alen); dfree(g, g->mg_blen); dfree(g, g->mg_out);
@@ -662,6 +662,10 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "tc.flat") {
     if (v != "0" && v != "1" && v != "2" && v != "3" && v != "4" && v != "5") { set_error("tc.flat: 0 .. 5"); return GM_EINVAL; }
     options().tc_flat = atoi(value);
+  } else if (k == "tc.hub") {
+    char *end = nullptr; long t = strtol(value, &end, 10);
+    if (end == value || *end || t < 16 || t > kHubRanks || (t & 15)) { set_error("tc.hub: a multiple of 16 in [16, %d], got '%s'", kHubRanks, value); return GM_EINVAL; }
+    options().tc_hub = int(t);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";
@@ -734,6 +738,7 @@ int gm_graph_free(gm_graph_t *g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->res_stream && g->res_stream != g->stream) cudaStreamSynchronize(g->res_stream);
   for (int i = 0; i < 3; i++) if (g->side[i]) cudaStreamSynchronize(g->side[i]);
+  trace_phase(g->res_stream ? g->res_stream : g->stream, "handle free");
   release_res(g);
   cudaGetLastError();
   delete g;

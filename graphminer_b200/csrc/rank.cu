@@ -265,24 +265,27 @@ k_partner_fill(RowCtx c, const eidType *prow, unsigned *cursor, uint2 *prec) {
 // bitmap).  One entry stands for 2.5 elements on average, its lookup walks the bitmap monotonically (sorted
 // entries in consecutive lanes: hardly a bank conflict, where a hashed probe took 3.4 wavefronts), and the
 // element that was one LDS + 8 instructions becomes 0.4 LDS.U16 + ~2 instructions.
-// Layout of hy_data (16-byte units): per ranked row [non-hub keys, padded to a unit with kPad4][entries, padded
-// with 0]; two trailing units: one of kPad4, one of zeros (what the dead lanes of a window read).
-// hy_vinfo[v] = {unit of the keys, number of keys, unit of the entries, number of entries};
-// hy_prec = per partner record {element offset of the key suffix, its length, element offset of the entries
-// from b's block on (all of them for a non-hub b), their number}, indexed by rk_prow like rk_prec.
+// Layout of hy_data (16-byte units): ranked row a owns the units [vinfo[a].x + a, ... + ceil(d/4) + 1) -- its
+// plain slot plus one, known without a counting pass: [non-hub keys, padded to a unit with kHyPad][entries,
+// padded with 0]; two trailing units: one of kHyPad, one of zeros (what the dead lanes of a window read).
+// hy_vinfo[v] = {unit of the keys, number of keys, unit of the entries, number of entries}.
+// hy_prec, indexed by rk_prow like rk_prec, 8 bytes per partner record of a -> b:
+//   b below the hub range: {element offset of the key suffix, its length << 13 | number of entries of a}
+//                          (a's entries start on the unit behind its last key: no separate offset);
+//   b a hub:               {element offset of a's entries from b's block on, their number}.
+// The same pass writes the PLAIN records (rk_prec) of the roots with at most 32 neighbours -- the one size class
+// that keeps the plain kernel -- so k_partner_fill is skipped when the hybrid form is built (rk_prec_full = false).
 struct HyCtx {
   vidType nv, hb;
   const uint2 *vinfo; const vidType *acol;           // ranked plain rows
   uint4 *hv; uint32_t *data;
+  uint2 *prec_plain;                                 // rk_prec (records of small roots only), may be null
 };
 
 // 8 lanes per row walk its sorted elements 8 at a time.  head = first element of a 16-rank hub block; the entry
-// index of a hub element = heads up to and including it - 1.  F(i, x, is_hub, entry) is called for every element.
+// index of a hub element = heads up to and including it - 1.  F(i, x, is_hub, entry, block) is called per element.
 template <typename F>
-__device__ __forceinline__ void hy_walk_row(const HyCtx &c, vidType a, bool valid, int sub, int lane, unsigned &n_keys, unsigned &n_entries, F f) {
-  const uint2 vi = valid ? c.vinfo[a] : make_uint2(0, 0);
-  const int d = int(vi.y);
-  const vidType *row = c.acol + (size_t(vi.x) << 2);
+__device__ __forceinline__ void hy_walk_row(const HyCtx &c, const vidType *row, int d, int sub, int lane, unsigned &n_keys, unsigned &n_entries, F f) {
   const int gshift = lane & ~7;
   const int dmax = __reduce_max_sync(kFullMask, d);
   unsigned heads_before = 0, keys = 0;
@@ -307,42 +310,34 @@ __device__ __forceinline__ void hy_walk_row(const HyCtx &c, vidType a, bool vali
 }
 
 __global__ void __launch_bounds__(256)
-k_hy_count(HyCtx c, uint32_t *units) {
+k_hy_fill(HyCtx c, RowCtx rc, const eidType *prow, unsigned *cursor, uint2 *prec) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const vidType a = vidType(t >> 3); const int sub = int(t & 7), lane = threadIdx.x & 31;
   const bool valid = a < c.nv;
+  const uint2 vi = valid ? c.vinfo[a] : make_uint2(0, 0);
+  const int d = int(vi.y);
+  const vidType *row = c.acol + (size_t(vi.x) << 2);
+  // pass 1 (counts): where the entries start and how many there are
   unsigned nk = 0, ne = 0;
-  hy_walk_row(c, a, valid, sub, lane, nk, ne, [](int, vidType, bool, unsigned, int) {});
-  if (valid && sub == 0) { c.hv[a] = make_uint4(0, nk, 0, ne); units[a] = ((nk + 3u) >> 2) + ((ne + 3u) >> 2); }
-}
-__global__ void k_hy_offsets(vidType nv, const uint32_t *off_units, uint4 *hv) {
-  const vidType v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nv) return;
-  uint4 h = hv[v];
-  h.x = off_units[v]; h.z = h.x + ((h.y + 3u) >> 2);
-  hv[v] = h;
-}
-__global__ void __launch_bounds__(256)
-k_hy_fill(HyCtx c, RowCtx rc, const eidType *prow, unsigned *cursor, uint4 *prec) {
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const vidType a = vidType(t >> 3); const int sub = int(t & 7), lane = threadIdx.x & 31;
-  const bool valid = a < c.nv;
-  const uint4 h = valid ? c.hv[a] : make_uint4(0, 0, 0, 0);
-  const uint32_t base_k = h.x << 2, base_e = h.z << 2;
-  const int d = valid ? int(c.vinfo[a].y) : 0;
+  hy_walk_row(c, row, d, sub, lane, nk, ne, [](int, vidType, bool, unsigned, int) {});
+  const uint32_t unit_k = vi.x + uint32_t(a), unit_e = unit_k + ((nk + 3u) >> 2);
+  const uint32_t base_k = unit_k << 2, base_e = unit_e << 2, base_plain = vi.x << 2;
+  if (valid && sub == 0) c.hv[a] = make_uint4(unit_k, nk, unit_e, ne);
   bool keep_src = false;
   if (valid) { const vidType v = rc.orig_of[a]; keep_src = v >= rc.src_begin && v < rc.src_end; }
-  unsigned nk = 0, ne = 0;
-  hy_walk_row(c, a, valid, sub, lane, nk, ne, [&](int i, vidType x, bool is_hub, unsigned entry, int blk) {
+  // pass 2 (the row is in L1 now): keys, entries, records
+  unsigned nk2, ne2;
+  hy_walk_row(c, row, d, sub, lane, nk2, ne2, [&](int i, vidType x, bool is_hub, unsigned entry, int blk) {
     if (is_hub) atomicOr(&c.data[base_e + entry], (uint32_t(blk) << 17) | (1u << (uint32_t(x - c.hb) & 15u)));
     else c.data[base_k + i] = (uint32_t(x) << 2) | 1u;
     if (i + 1 < d && rec_kept(rc, keep_src, x)) {
-      const unsigned p = atomicAdd(&cursor[x], 1u);
-      prec[prow[x] + eidType(p)] = is_hub ? make_uint4(0u, 0u, base_e + entry, h.w - entry)
-                                          : make_uint4(base_k + uint32_t(i) + 1u, h.y - uint32_t(i) - 1u, base_e, h.w);
+      const eidType slot = prow[x] + eidType(atomicAdd(&cursor[x], 1u));
+      if (c.prec_plain && c.vinfo[x].y <= 32u) c.prec_plain[slot] = make_uint2(base_plain + uint32_t(i) + 1u, uint32_t(d - i - 1));
+      else prec[slot] = is_hub ? make_uint2(base_e + entry, ne - entry)
+                               : make_uint2(base_k + uint32_t(i) + 1u, ((nk - uint32_t(i) - 1u) << 13) | ne);
     }
   });
-  if (valid) for (uint32_t i = h.y + sub; i < ((h.y + 3u) & ~3u); i += 8) c.data[base_k + i] = kHyPad;
+  if (valid) for (uint32_t i = nk + sub; i < ((nk + 3u) & ~3u); i += 8) c.data[base_k + i] = kHyPad;
 }
 __global__ void k_hy_tail(uint32_t *data, uint32_t total_units) {
   const int i = threadIdx.x;
@@ -364,6 +359,8 @@ __global__ void k_widen(int64_t n, const unsigned *in, eidType *out) {
 }
 
 static int bits_of(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b < 1 ? 1 : b; }
+
+bool hybrid_eligible(const gm_graph *g);
 
 int ensure_ranked(gm_graph *g) {
   if (g->rk_ready) return GM_OK;
@@ -461,8 +458,13 @@ int ensure_ranked(gm_graph *g) {
     k_widen<<<nblk(int64_t(nv) + 1), 256, 0, g->stream>>>(int64_t(nv) + 1, cnt, g->rk_prow);
     GM_TRY(scan_inplace(g, g->rk_prow, nv));
     GM_CUDA(dmalloc(g, &g->rk_prec, sizeof(uint2) * size_t(ne)));
-    GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * nv1, g->stream));
-    k_partner_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, g->rk_prow, cnt, g->rk_prec);
+    // a handle prepared for the hybrid TC kernel (tc.flat=5: prepare_tc sets want_hybrid) leaves the records to
+    // ensure_hybrid: its own form for the big roots, the plain ones of the small roots into rk_prec
+    g->rk_prec_full = !(g->want_hybrid && hybrid_eligible(g));
+    if (g->rk_prec_full) {
+      GM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * nv1, g->stream));
+      k_partner_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, g->rk_prow, cnt, g->rk_prec);
+    }
     int h_bad = 0;
     GM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     GM_CUDA(cudaStreamSynchronize(g->stream));
@@ -485,49 +487,67 @@ int ensure_ranked(gm_graph *g) {
   return GM_OK;
 }
 
+static RowCtx persistent_rowctx(gm_graph *g) {
+  RowCtx r{};
+  r.nv = g->nv; r.vinfo = g->rk_vinfo; r.acol = g->rk_acol; r.orig_of = g->rk_orig;
+  r.src_begin = g->src_begin; r.src_end = g->src_end;
+  r.by_dest = options().tc_shard == "dest" || g->force_dest_shard;
+  r.full_range = g->src_begin == 0 && g->src_end == g->nv;
+  return r;
+}
+
+// the hybrid form needs keys 4 * rank + 1 below 2^31, suffix lengths below 2^18 and 32-bit element offsets
+bool hybrid_eligible(const gm_graph *g) {
+  return uint64_t(g->nv) < (1ull << 29) && g->max_degree < (1 << 18) &&
+         (uint64_t(g->ne) + 7ull * uint64_t(g->nv) + 64ull) < (1ull << 32);
+}
+
+// rk_prec for EVERY root (the plain ranked kernels and tc.algo=merge); a no-op unless ensure_ranked left the
+// records to ensure_hybrid
+int ensure_full_prec(gm_graph *g) {
+  GM_TRY(ensure_ranked(g));
+  if (!g->rk_valid || g->rk_prec_full) return GM_OK;
+  GM_CUDA(cudaSetDevice(g->device));
+  unsigned *cursor = nullptr;
+  GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned) * (size_t(g->nv) + 1)));
+  GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * (size_t(g->nv) + 1), g->stream));
+  k_partner_fill<<<nblk(int64_t(g->nv) * 8), 256, 0, g->stream>>>(persistent_rowctx(g), g->rk_prow, cursor, g->rk_prec);
+  GM_CUDA(cudaGetLastError());
+  GM_CUDA(dfree(g, cursor));
+  g->rk_prec_full = true;
+  trace_phase(g->stream, "rank: partner records (all roots)");
+  return GM_OK;
+}
+
 // builds the hybrid rows and their partner records on top of the ranked graph (same record counts: rk_prow)
 int ensure_hybrid(gm_graph *g) {
   if (g->hy_ready) return GM_OK;
   GM_TRY(ensure_ranked(g));
   g->hy_ready = true; g->hy_valid = false;
   const vidType nv = g->nv;
-  if (!g->rk_valid || uint64_t(nv) >= (1ull << 29)) return GM_OK;          // keys are 4 * rank + 1 below 2^31
+  if (!g->rk_valid || !hybrid_eligible(g)) return ensure_full_prec(g);
   GM_CUDA(cudaSetDevice(g->device));
-  HyCtx c; c.nv = nv; c.hb = nv > vidType(kHubRanks) ? nv - vidType(kHubRanks) : 0;
+  const vidType hub = vidType(std::min(options().tc_hub, kHubRanks));
+  HyCtx c; c.nv = nv; c.hb = nv > hub ? nv - hub : 0;
   c.vinfo = g->rk_vinfo; c.acol = g->rk_acol;
-  uint32_t *units = nullptr; unsigned *cursor = nullptr;
+  c.prec_plain = g->rk_prec_full ? nullptr : g->rk_prec;
+  unsigned *cursor = nullptr;
+  const uint32_t total_units = uint32_t(g->rk_acol_len >> 2) + uint32_t(nv);
+  const size_t words = (size_t(total_units) + 2) << 2;
   GM_CUDA(dmalloc(g, &g->hy_vinfo, sizeof(uint4) * size_t(nv)));
-  GM_CUDA(dmalloc(g, &units, sizeof(uint32_t) * (size_t(nv) + 1)));
+  GM_CUDA(dmalloc(g, &g->hy_data, sizeof(uint32_t) * words));
+  GM_CUDA(dmalloc(g, &g->hy_prec, sizeof(uint2) * size_t(g->ne > 0 ? g->ne : 1)));
   GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned) * (size_t(nv) + 1)));
-  c.hv = g->hy_vinfo; c.data = nullptr;
-  int rc = [&]() -> int {
-    GM_CUDA(cudaMemsetAsync(units + nv, 0, sizeof(uint32_t), g->stream));
-    GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * (size_t(nv) + 1), g->stream));
-    k_hy_count<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, units);
-    GM_TRY(scan_inplace(g, units, nv));
-    uint32_t total_units = 0;
-    GM_CUDA(cudaMemcpyAsync(&total_units, units + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
-    GM_CUDA(cudaStreamSynchronize(g->stream));
-    k_hy_offsets<<<nblk(nv), 256, 0, g->stream>>>(nv, units, g->hy_vinfo);
-    const size_t words = (size_t(total_units) + 2) << 2;
-    GM_CUDA(dmalloc(g, &g->hy_data, sizeof(uint32_t) * words));
-    GM_CUDA(cudaMemsetAsync(g->hy_data, 0, sizeof(uint32_t) * words, g->stream));      // entries are OR-ed in; padding entries stay 0
-    GM_CUDA(dmalloc(g, &g->hy_prec, sizeof(uint4) * size_t(g->ne > 0 ? g->ne : 1)));
-    c.data = g->hy_data;
-    RowCtx r{};
-    r.nv = nv; r.orig_of = g->rk_orig; r.src_begin = g->src_begin; r.src_end = g->src_end;
-    r.by_dest = options().tc_shard == "dest" || g->force_dest_shard;
-    r.full_range = g->src_begin == 0 && g->src_end == nv;
-    k_hy_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, r, g->rk_prow, cursor, g->hy_prec);
-    k_hy_tail<<<1, 32, 0, g->stream>>>(g->hy_data, total_units);
-    GM_CUDA(cudaGetLastError());
-    g->hy_units = total_units; g->hy_hb = c.hb;
-    return GM_OK;
-  }();
-  dfree(g, units); dfree(g, cursor);
-  if (rc != GM_OK) return rc;
+  GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * (size_t(nv) + 1), g->stream));
+  GM_CUDA(cudaMemsetAsync(g->hy_data, 0, sizeof(uint32_t) * words, g->stream));      // entries are OR-ed in; padding entries stay 0
+  c.hv = g->hy_vinfo; c.data = g->hy_data;
+  k_hy_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, persistent_rowctx(g), g->rk_prow, cursor, g->hy_prec);
+  k_hy_tail<<<1, 32, 0, g->stream>>>(g->hy_data, total_units);
+  GM_CUDA(cudaGetLastError());
+  GM_CUDA(dfree(g, cursor));
+  g->hy_units = total_units; g->hy_hb = c.hb;
   g->hy_valid = true;
-  trace_phase(g->stream, "rank: hybrid rows (hub bitmaps + keys)");
+  trace_phase(g->stream, "rank: hybrid rows (hub bitmaps + keys) + records");
   return GM_OK;
 }
 

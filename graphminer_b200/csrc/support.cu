@@ -249,6 +249,7 @@ int prepare_diamond_support(gm_graph *g, bool *ok, bool partial) {
   }
   GM_TRY(ensure_ranked(c));
   if (!c->rk_valid) return GM_OK;
+  GM_TRY(ensure_full_prec(c));                             // the support kernel walks the plain records of every root
   GM_TRY(ensure_items(c, 3));
   if (!g->d_support || g->support_len != c->rk_acol_len) {
     if (g->d_support) GM_CUDA(dfree(g, g->d_support));

@@ -609,7 +609,7 @@ __device__ __forceinline__ uint32_t probe_window_hub(uint32_t sb, uint4 e) {
 template <int GT, int MAXB1, int CAP>
 __global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
 tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data, uint32_t pad_keys, uint32_t pad_zero, vidType hb,
-                 const eidType *__restrict__ prow, const uint4 *__restrict__ prec,
+                 const eidType *__restrict__ prow, const uint2 *__restrict__ prec,
                  const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total) {
   static_assert(GT >= 256, "one group per CTA");
   using Cfg = GroupCfg<GT>;
@@ -623,22 +623,21 @@ tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data
   const uint32_t sb = uint32_t(__cvta_generic_to_shared(bitmap));
   const uint4 *units = reinterpret_cast<const uint4 *>(data);
   for (int i = tid; i < kBitmapWords; i += GT) bitmap[i] = 0u;
-  uint4 prev = make_uint4(0, 0, 0, 0);
+  uint4 h = make_uint4(0, 0, 0, 0);                  // the current root's {unit of keys, keys, unit of entries, entries}
   AccType acc = 0;
 
   while (true) {
     __syncthreads();                                 // previous item fully done (also: the bitmap is zeroed)
     {                                                // take the previous root's blocks out of the bitmap again
-      const uint32_t *pe = data + (size_t(prev.z) << 2);
-      for (uint32_t i = tid; i < prev.w; i += GT) sts_u16(sb + (__ldg(pe + i) >> 16), 0u);
+      const uint32_t *pe = data + (size_t(h.z) << 2);
+      for (uint32_t i = tid; i < h.w; i += GT) sts_u16(sb + (__ldg(pe + i) >> 16), 0u);
     }
     if (tid == 0) s_next = int64_t(atomicAdd(ticket, 1));
     __syncthreads();
     const int64_t first = s_next;
     if (first >= nitems) break;
     const WorkItem it = items[first];
-    const uint4 h = hv[it.root];
-    prev = h;
+    h = hv[it.root];
     const uint32_t *keys = data + (size_t(h.x) << 2), *ents = data + (size_t(h.z) << 2);
     const int nk = int(h.y);
     for (uint32_t i = tid; i < h.w; i += GT) { const uint32_t e = __ldg(ents + i); sts_u16(sb + (e >> 16), e & 0xffffu); }
@@ -657,14 +656,21 @@ tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data
     }
     if (!use_keys || !fits) __syncthreads();         // the bitmap stores (the table build ends with a barrier)
     const uint32_t s2 = s1 + (4u << b1);
-    const uint4 *R = prec + prow[it.root] + it.pbegin;
+    const uint2 *R = prec + prow[it.root] + it.pbegin;
+    const bool hub_root = it.root >= hb;
     uint32_t c = 0;
     const int mine = (it.pcount - gwarp + W - 1) / W;
     for (int pb = 0; pb < mine; pb += 32) {
       const int q = pb + lane;
       const bool live = q < mine;
+      // record (rank.cu): hub root {offset of the entries, their number}; else {offset of the key suffix,
+      // its length << 13 | number of entries}, the entries starting on the unit behind the last key
       uint4 rec = make_uint4(0, 0, 0, 0);
-      if (live) rec = __ldg(R + q * W + gwarp);
+      if (live) {
+        const uint2 r2 = __ldg(R + q * W + gwarp);
+        if (hub_root) rec = make_uint4(0u, 0u, r2.x, r2.y);
+        else { const uint32_t la = r2.y >> 13; rec = make_uint4(r2.x, la, (r2.x + la + 3u) & ~3u, r2.y & 0x1fffu); }
+      }
       if (use_keys) {
         if (fits) {
           const uint32_t u0 = rec.y ? rec.x >> 2 : pad_keys;
@@ -761,6 +767,7 @@ k_sum_u64(int64_t n, const unsigned long long *__restrict__ in, AccType *total) 
 
 static int prepare_tc_merge(gm_graph *g) {
   if (g->mg_npairs >= 0) return GM_OK;
+  GM_TRY(ensure_full_prec(g));
   eidType nrec = 0;
   GM_CUDA(cudaMemcpyAsync(&nrec, g->rk_prow + g->nv, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
@@ -870,6 +877,7 @@ int tc_alg_bytes(gm_graph *g, uint64_t *out, int sym_break) {
 static int resolve_tc_algo(gm_graph *g, std::string *out) {
   std::string algo = options().tc_algo;
   if (algo == "auto" || algo == "rank" || algo == "merge") {
+    if (!g->rk_ready) g->want_hybrid = algo != "merge" && options().tc_flat == 5 && !options().tc_pipe;
     GM_TRY(ensure_ranked(g));
     if (!g->rk_valid) algo = "hash_rev"; else if (algo == "auto") algo = "rank";
   }
@@ -884,7 +892,8 @@ int prepare_tc(gm_graph *g) {
   if (algo == "rank") {
     GM_TRY(ensure_items(g, 3));
     // keys as 4 * rank for tc_rank_kernel (tc.flat=4); needs 4 * nv below the padding value
-    if (options().tc_flat == 5) GM_TRY(ensure_hybrid(g));
+    if (options().tc_flat == 5 && !options().tc_pipe) GM_TRY(ensure_hybrid(g));
+    if (!(options().tc_flat == 5 && !options().tc_pipe && g->hy_valid)) GM_TRY(ensure_full_prec(g));
     if (options().tc_flat == 4 && !g->rk_acol4 && g->rk_valid && uint64_t(g->nv) < (uint64_t(kPad4) >> 2)) {
       const int64_t n_alloc = g->rk_acol_len + 8;                     // + two units of padding: the dead slots of a last window read them
       GM_CUDA(dmalloc(g, &g->rk_acol4, sizeof(uint32_t) * size_t(n_alloc)));

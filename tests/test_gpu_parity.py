@@ -35,6 +35,8 @@ def _reset_options():
     capi.set_option("c4.persist", 1)
     capi.set_option("tc.short", 0)
     capi.set_option("tc.pipe", 0)
+    capi.set_option("tc.flat", 5)
+    capi.set_option("tc.hub", 65536)
 
 
 def _graph(name):
@@ -725,3 +727,56 @@ def test_house_on_the_dag_machinery(small_max, cta_max, mid_max, hash_tier, cite
         g.set_source_range(10, 500)                              # a shard keeps the operator-API kernel
         capi.set_option("sgl.algo", "auto")
         assert g.sgl("house") == oracle.sgl(rp, ci, "house", (10, 500))
+
+
+@pytest.mark.parametrize("hub", [16, 256, 4096, 65536])
+def test_tc_hybrid_rows_split_at_every_hub_range(hub):
+    """tc.flat=5 keeps the top `tc.hub` ranks of every row as 16-rank bitmap blocks and the rest as hashed keys;
+    the golden graphs are smaller than the default range (everything a hub), so the range is shrunk to put
+    roots and partners on both sides of the split.  The other stream loops (0: per record, 1: flat windows,
+    4: scaled keys) count the same on the SAME handle: switching rebuilds the plain partner records."""
+    capi.set_option("tc.hub", hub)
+    for name in ("rmat8", "rmat12", "rmat14", "rmat16", "shaped3000"):
+        rp, ci = _graph(name)
+        orp, oci, md = _dag(rp, ci)
+        capi.set_option("tc.flat", 5)
+        capi.set_option("tc.algo", "rank")
+        with capi.DeviceGraph(orp, oci, md) as g:
+            assert g.tc() == GOLD[name]["tc"], (name, hub)
+            for flat in (1, 4, 0, 5):
+                capi.set_option("tc.flat", flat)
+                assert g.tc() == GOLD[name]["tc"], (name, hub, flat)
+            capi.set_option("tc.algo", "merge")
+            assert g.tc() == GOLD[name]["tc"], (name, hub, "merge")
+    capi.set_option("tc.flat", 5)
+    capi.set_option("tc.algo", "rank")
+    n = 700                                                  # K_700: rows of every length, all blocks dense
+    rp, ci, md = _complete_dag(n)
+    with capi.DeviceGraph(rp, ci, md) as g:
+        assert g.tc() == n * (n - 1) * (n - 2) // 6
+
+
+def test_tc_hybrid_rows_beyond_the_default_hub_range():
+    """R-MAT scale 18 has 4x more vertices than the default hub range: keys and bitmap blocks both in play,
+    checked against the operator-API kernel and the plain ranked kernels, whole graph and shards (by source and
+    by destination)"""
+    rp, ci = rmat_graph(18)
+    orp, oci, md = capi.host_orient(rp.numpy(), ci.numpy())
+    capi.set_option("tc.algo", "bs")
+    with capi.DeviceGraph(orp, oci, md) as g:
+        want = g.tc()
+    capi.set_option("tc.algo", "rank")
+    nv = len(orp) - 1
+    for flat in (5, 1):
+        capi.set_option("tc.flat", flat)
+        with capi.DeviceGraph(orp, oci, md) as g:
+            assert g.tc() == want, flat
+    capi.set_option("tc.flat", 5)
+    for shard in ("source", "dest"):
+        capi.set_option("tc.shard", shard)
+        total = 0
+        for lo, hi in ((0, nv // 3), (nv // 3, nv // 2), (nv // 2, nv)):
+            with capi.DeviceGraph(orp, oci, md) as g:
+                g.set_source_range(lo, hi)
+                total += g.tc()
+        assert total == want, shard
