@@ -28,7 +28,7 @@ ALGOS = {"auto": 0, "bsearch": 1, "merge": 2, "hash": 3, "gallop": 4}
 SYMBOLS = [
     "gm_last_error", "gm_version", "gm_device_count", "gm_device_init", "gm_set_option",
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
-    "gm_host_alloc", "gm_host_free", "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
+    "gm_host_alloc", "gm_host_free", "gm_host_map_graph", "gm_host_unmap_graph", "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
     "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_motif_support_begin", "gm_motif_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
     "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info", "gm_graph_device_view",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
@@ -73,6 +73,8 @@ def lib():
     L.gm_host_shard_bounds.argtypes = [i32, _i64p, _i32p, C.c_int, C.c_int, _i32p]
     L.gm_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.POINTER(C.c_int)]
     L.gm_host_free.argtypes = [vp]
+    L.gm_host_map_graph.argtypes = [C.c_char_p, i32, i64, C.c_int, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int)]
+    L.gm_host_unmap_graph.argtypes = [vp, vp]
     L.gm_host_read_meta.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]
     L.gm_host_read_graph.argtypes = [C.c_char_p, i32, i64, _i64p, _i32p]
     L.gm_host_write_graph.argtypes = [C.c_char_p, i32, i64, i32, _i64p, _i32p]
@@ -208,6 +210,25 @@ def read_graph_pinned(prefix: str):
         out.append(a); pinned_all = pinned_all and bool(pin.value)
     check(lib().gm_host_read_graph(prefix.encode(), nv.value, ne.value, out[0], out[1]))
     return out[0], out[1][: ne.value], md.value, pinned_all
+
+
+def map_graph(prefix: str, pin: bool = True):
+    """Reference on-disk format mapped read-only (the reference's map_file, custom_alloc.h:46-58) and, with
+    `pin`, registered with the CUDA driver.  Returns (rowptr, colidx, max_degree, pinned); the numpy views keep
+    the mappings alive through a finaliser."""
+    import weakref
+    nv, ne, md = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+    check(lib().gm_host_read_meta(prefix.encode(), C.byref(nv), C.byref(ne), C.byref(md)))
+    rp, ci, pinned = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.c_int(0)
+    check(lib().gm_host_map_graph(prefix.encode(), nv.value, ne.value, int(pin), C.byref(rp), C.byref(ci), C.byref(pinned)))
+    a_rp = np.ctypeslib.as_array(rp, shape=(nv.value + 1,))
+    a_ci = np.ctypeslib.as_array(ci, shape=(ne.value,)) if ne.value else np.zeros(0, np.int32)
+    keep = (C.cast(rp, C.c_void_p), C.cast(ci, C.c_void_p))
+    weakref.finalize(a_rp, lib().gm_host_unmap_graph, keep[0], keep[1])
+    a_rp.flags.writeable = False
+    if ne.value:
+        a_ci.flags.writeable = False
+    return a_rp, a_ci, md.value, bool(pinned.value)
 
 
 def sort_neighbors(rowptr, colidx):

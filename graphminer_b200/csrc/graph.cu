@@ -4,6 +4,10 @@
 // Replaces GraphGPU::init / init_edgelist / clean of the reference (include/graph_gpu.h:56-210).
 // Everything after the initial H2D copy is built ON THE DEVICE: the reference
 // builds the COO list in a single host thread (src/common/graph.cc:308-321).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "gm_internal.cuh"
 #include <chrono>
 #include <cstdlib>
@@ -617,6 +621,58 @@ int gm_host_free(void *ptr) {
       if (g_pinned[i] == ptr) { g_pinned[i] = g_pinned.back(); g_pinned.pop_back(); was_pinned = true; break; }
   }
   if (was_pinned) { cudaFreeHost(ptr); cudaGetLastError(); } else free(ptr);
+  return GM_OK;
+}
+
+// map_file (custom_alloc.h:46-58): the two arrays of the on-disk format as read-only mappings
+struct Mapping { void *ptr; size_t bytes; bool registered; };
+static std::vector<Mapping> g_maps;
+static int map_one(const std::string &path, size_t bytes, int pin, void **out, bool *registered) {
+  *registered = false;
+  if (bytes == 0) { *out = nullptr; return GM_OK; }
+  const int fd = open(path.c_str(), O_RDONLY, 0);
+  if (fd < 0) { set_error("cannot open %s", path.c_str()); return GM_EIO; }
+  struct stat st;
+  if (fstat(fd, &st) != 0 || size_t(st.st_size) < bytes) { close(fd); set_error("%s is shorter than %zu bytes", path.c_str(), bytes); return GM_EIO; }
+  void *p = mmap(nullptr, bytes, PROT_READ, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) { set_error("mmap of %s failed", path.c_str()); return GM_EIO; }
+  int ndev = 0; gm_device_count(&ndev);
+  if (pin && ndev > 0) {
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly) == cudaSuccess) *registered = true;
+    else cudaGetLastError();                              // pageable mapping: the upload stages it like any other host array
+  }
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_maps.push_back({p, bytes, *registered});
+  *out = p;
+  return GM_OK;
+}
+static void unmap_one(const void *ptr) {
+  if (!ptr) return;
+  Mapping m{nullptr, 0, false};
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_maps.size(); i++)
+      if (g_maps[i].ptr == ptr) { m = g_maps[i]; g_maps[i] = g_maps.back(); g_maps.pop_back(); break; }
+  }
+  if (!m.ptr) return;
+  if (m.registered) { cudaHostUnregister(m.ptr); cudaGetLastError(); }
+  munmap(m.ptr, m.bytes);
+}
+int gm_host_map_graph(const char *prefix, int32_t nv, int64_t ne, int pin,
+                      const int64_t **rowptr, const int32_t **colidx, int *pinned) {
+  if (!prefix || !rowptr || !colidx || nv < 0 || ne < 0) { set_error("gm_host_map_graph: bad argument"); return GM_EINVAL; }
+  void *rp = nullptr, *ci = nullptr;
+  bool r1 = false, r2 = false;
+  GM_TRY(map_one(std::string(prefix) + ".vertex.bin", sizeof(int64_t) * (size_t(nv) + 1), pin, &rp, &r1));
+  const int rc = map_one(std::string(prefix) + ".edge.bin", sizeof(int32_t) * size_t(ne), pin, &ci, &r2);
+  if (rc != GM_OK) { unmap_one(rp); return rc; }
+  *rowptr = static_cast<const int64_t *>(rp); *colidx = static_cast<const int32_t *>(ci);
+  if (pinned) *pinned = (r1 && (r2 || ne == 0)) ? 1 : 0;
+  return GM_OK;
+}
+int gm_host_unmap_graph(const int64_t *rowptr, const int32_t *colidx) {
+  unmap_one(rowptr); unmap_one(colidx);
   return GM_OK;
 }
 

@@ -61,8 +61,12 @@ int gm_device_init(int device);
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source
  *       (the reference's semantics, default) or by their destination (same total over a partition of
  *       the vertex set; keeps each root's table on one shard -- set before gm_graph_prepare),
- *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.pipe" = 0|1 (cross-partner
- *       prefetch in the TC stream loop; measured slower, off by default), "tc.gt2" = 256|512, "sup.gt2" =
+ *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.flat" = 5|4|3|2|1|0 (stream loop of
+ *       the ranked TC kernel: 5 = hybrid rows, hub bitmaps + hashed keys, the default; 4 = keys stored as
+ *       4*rank+1; 1 = flat windows over plain rows, 2|3 = with prefetch; 0 = a loop per partner record, then
+ *       "tc.short" = lane-private walk of suffixes up to that length), "tc.hub" = multiple of 16 in [16, 65536]
+ *       (ranks kept as bitmap blocks by tc.flat=5; smaller values only for tests), "tc.pipe" = 0|1 (cross-partner
+ *       prefetch in the per-record loop; measured slower, off by default), "tc.gt2" = 256|512, "sup.gt2" =
  *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
  *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers), "c4.hash" = -1|0|1
  *       (cluster tier on dense |V|-sized arrays or per-root hash tables; auto by |V|), "c4.persist" = 0|1 (pin the
@@ -104,6 +108,14 @@ int gm_host_write_graph(const char *prefix, int32_t nv, int64_t ne, int32_t max_
  * Without a CUDA device the memory comes from malloc and *pinned is 0.  gm_host_free takes either kind. */
 int gm_host_alloc(size_t bytes, void **ptr, int *pinned);
 int gm_host_free(void *ptr);
+/* map_file, include/custom_alloc.h:46-58 (Graph's map_vertices / map_edges switches, src/common/graph.cc:37-41):
+ * <prefix>.vertex.bin and .edge.bin mapped read-only (MAP_SHARED) instead of read -- nothing is copied until a
+ * page is touched.  With pin != 0 and a CUDA device present the mappings are also registered with the driver
+ * (cudaHostRegister, read-only), so that gm_*_host uploads them by DMA like the arrays of gm_host_alloc;
+ * *pinned reports whether that happened.  The pointers stay valid until gm_host_unmap_graph(rowptr, colidx). */
+int gm_host_map_graph(const char *prefix, int32_t nv, int64_t ne, int pin,
+                      const int64_t **rowptr, const int32_t **colidx, int *pinned);
+int gm_host_unmap_graph(const int64_t *rowptr, const int32_t *colidx);
 /* Graph::sort_neighbors, src/common/graph.cc:138-146: sort every adjacency row in place (the
  * `adj_sorted = 0` path of triangle/main.cc:21-22). */
 int gm_host_sort_neighbors(int32_t nv, const int64_t *rowptr, int32_t *colidx);

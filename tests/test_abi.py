@@ -135,3 +135,26 @@ def test_pinned_loader_roundtrip(tmp_path):
     assert np.array_equal(got_rp, rp) and np.array_equal(got_ci, ci) and md == int(deg.max())
     assert pinned == (capi.device_count() > 0)
     del got_rp, got_ci                                   # finalisers hand the arrays back to gm_host_free
+
+
+def test_mapped_loader_roundtrip(tmp_path):
+    """gm_host_map_graph: the reference's map_file path (custom_alloc.h:46-58) -- read-only mappings of the two
+    arrays, registered with the CUDA driver when a device is present; truncated files are an error, not a fault"""
+    rng = np.random.default_rng(10)
+    nv = 2500
+    deg = rng.integers(0, 7, nv)
+    rp = np.zeros(nv + 1, np.int64); np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(nv, d, replace=False)) for d in deg]).astype(np.int32)
+    prefix = str(tmp_path / "graph")
+    capi.write_graph(prefix, rp, ci, int(deg.max()))
+    got_rp, got_ci, md, pinned = capi.map_graph(prefix)
+    assert np.array_equal(got_rp, rp) and np.array_equal(got_ci, ci) and md == int(deg.max())
+    assert not got_rp.flags.writeable
+    assert isinstance(pinned, bool) and (capi.device_count() > 0 or not pinned)
+    orp, oci, omd = capi.host_orient(np.array(got_rp), np.array(got_ci))      # host logic reads the mapping directly
+    assert len(orp) == nv + 1
+    del got_rp, got_ci                                   # finalisers unmap
+    with open(prefix + ".edge.bin", "r+b") as f:
+        f.truncate(max(0, ci.nbytes - 8))
+    with pytest.raises(capi.GMError):
+        capi.map_graph(prefix)

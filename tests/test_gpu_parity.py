@@ -780,3 +780,16 @@ def test_tc_hybrid_rows_beyond_the_default_hub_range():
                 g.set_source_range(lo, hi)
                 total += g.tc()
         assert total == want, shard
+
+
+def test_mapped_graph_feeds_the_host_entry_points(tmp_path):
+    """gm_host_map_graph -> gm_tc_host: the read-only, driver-registered mapping is uploaded like pinned memory"""
+    rp, ci = _graph("rmat14")
+    orp, oci, md = _dag(rp, ci)
+    prefix = str(tmp_path / "dag")
+    capi.write_graph(prefix, orp, oci, md)
+    m_rp, m_ci, m_md, pinned = capi.map_graph(prefix)
+    assert isinstance(pinned, bool)                       # registration needs read-only host-register support
+    assert capi.tc_host(m_rp, m_ci, m_md) == GOLD["rmat14"]["tc"]
+    u_rp, u_ci, u_md, _ = capi.map_graph(prefix, pin=False)
+    assert capi.tc_host(u_rp, u_ci, u_md) == GOLD["rmat14"]["tc"]
