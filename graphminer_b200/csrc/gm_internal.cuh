@@ -54,6 +54,8 @@ struct Options {
   int tc_short = 16;               // TC: partner suffixes of at most this many elements are walked by one lane each (0: all warp-wide)
   int tc_flat = 5;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (0: a loop per record, 2: flat with 40 registers / 1536 threads per SM)
   int tc_hub = kHubRanks;          // hybrid rows: ranks kept as bitmap blocks (a multiple of 16, at most kHubRanks; smaller values are a test hook)
+  int tc_ld = 2;                   // hybrid kernel: load flavour of the streamed entries (0 ld.global.nc, 1 + L1::no_allocate, 2 ld.global.cg)
+  int tc_occ = 0;                  // hybrid kernel: 0 = 32 registers / 2048 threads per SM, 1 = 40 registers / 1536 threads
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)

@@ -722,6 +722,12 @@ int gm_set_option(const char *key, const char *value) {
     char *end = nullptr; long t = strtol(value, &end, 10);
     if (end == value || *end || t < 16 || t > kHubRanks || (t & 15)) { set_error("tc.hub: a multiple of 16 in [16, %d], got '%s'", kHubRanks, value); return GM_EINVAL; }
     options().tc_hub = int(t);
+  } else if (k == "tc.ld") {
+    if (v != "0" && v != "1" && v != "2") { set_error("tc.ld: 0, 1 or 2"); return GM_EINVAL; }
+    options().tc_ld = atoi(value);
+  } else if (k == "tc.occ") {
+    if (v != "0" && v != "1") { set_error("tc.occ: 0 or 1"); return GM_EINVAL; }
+    options().tc_occ = atoi(value);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";
