@@ -260,6 +260,246 @@ __device__ __forceinline__ uint32_t stream_partners_flat_pipe(const RowTable &ta
   asm volatile("" : "+r"(s1));
   asm volatile("" : "+r"(s2));
   uint32_t started = 0, c = 0;
+  auto fetch = [&](uint32_t w) {
+    const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(1u, pos - w));
+    const int j = int(started + __popc(heads & le_mask)) - 1;
+    started += __popc(heads);
+    const uint32_t s = w + ln;
+    const uint32_t u = __shfl_sync(kFullMask, delta, j) + s;
+    return ldg4_or_pad(units + u, s < total);
+  };
+  if (total == 0) return 0;
+  uint4 y = fetch(0);
+  for (uint32_t w = 32; ; w += 32) {
+    const uint4 x = y;
+    const bool more = w < total;                                   // warp-uniform
+    if (more) y = fetch(w);
+    c += probe_window(tab, s1, s2, x);
+    if (!more) break;
+  }
+  return c;
+}
+
+// Fallback when the root row does not fit the table: search it where it lies (global / L2).
+__device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, const vidType *list, int len, int lane) {
+  uint32_t c = 0;
+  for (int i = lane; i < len; i += 32) c += binary_search(root, __ldg(list + i), vidType(d));
+  return c;
+}
+
+// MODE 0: partners = out-neighbours of the root (rows read through g's aligned view)
+// MODE 1: partners = in-neighbours (prow/pcol = reverse adjacency)
+// MODE 2: RANKED graph (rank.cu): g's aligned view holds the rank-relabelled rows, partners are
+//         records {element offset of the row suffix to stream, its length} in prec
+// VAR 0: stream loop chosen at run time (flat / mixed / per record), 1: cross-partner prefetch (tc.pipe),
+// 2: flat with prefetch, 3: flat with prefetch and the relaxed register allocation
+template <int GT, int MAXB1, int CAP, int MODE, int VAR>
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, VAR == 3 ? GroupCfg<GT>::kMinCtasRelaxed : GroupCfg<GT>::kMinCtas)
+tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
+               const uint2 *__restrict__ prec,
+               const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int short_max) {
+  using Cfg = GroupCfg<GT>;
+  extern __shared__ uint32_t smem[];
+  __shared__ int64_t s_next;
+  constexpr int kWords = RowTable::words_for_bits(MAXB1, CAP);
+  constexpr int kBatch = GT == 32 ? 4 : 1;
+  const int lane = threadIdx.x & 31;
+  const int gtid = threadIdx.x % GT;                 // rank in group
+  const int gwarp = gtid >> 5;                       // warp in group
+  uint32_t *gbase = smem + (threadIdx.x / GT) * kWords;
+  AccType acc = 0;
+
+  while (true) {
+    int64_t first;
+    if (GT == 32) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(ticket, kBatch);
+      first = int64_t(__shfl_sync(kFullMask, t, 0));
+    } else {
+      __syncthreads();                               // previous item fully done (also guards s_next)
+      if (threadIdx.x == 0) s_next = int64_t(atomicAdd(ticket, kBatch));
+      __syncthreads();
+      first = s_next;
+    }
+    if (first >= nitems) break;
+    for (int b = 0; b < kBatch && first + b < nitems; b++) {
+      WorkItem it = items[first + b];
+      uint2 ri = g.info(it.root);
+      const int d = int(ri.y);
+      const vidType *rrow = g.NA(ri);
+      RowTable tab;
+      const int b1 = RowTable::bits_for(d);
+      bool fits = b1 <= MAXB1;
+      if (fits) {
+        tab.configure(gbase, b1, CAP);
+        if (GT == 32) __syncwarp();                  // previous item's probes are done
+        tab.build(rrow, d, gtid, GT, [] { group_sync<GT>(); });
+        if (tab.overflowed()) fits = false;          // group-uniform
+      }
+      const vidType *P = MODE == 1 ? pcol + prow[it.root] + it.pbegin
+                                   : MODE == 0 ? g.d_colidx + g.d_rowptr[it.root] + it.pbegin : nullptr;
+      const uint2 *R = MODE == 2 ? prec + prow[it.root] + it.pbegin : nullptr;
+      const uint32_t s1 = fits ? tab.saddr1() : 0u;
+      uint32_t c = 0;
+      // partners are dealt round-robin to the warps of the group (partner q goes to warp q % W), so
+      // every warp has work whenever the item has at least W partners; each warp fetches the row
+      // descriptors of its next 32 partners with one lane-parallel load
+      constexpr int W = Cfg::kWarpsPerGroup;
+      const int mine = (it.pcount - gwarp + W - 1) / W;          // partners owned by this warp
+      for (int pb = 0; pb < mine; pb += 32) {
+        int q = pb + lane;
+        uint2 pv = make_uint2(0, 0);
+        if (q < mine) pv = MODE == 2 ? __ldg(R + q * W + gwarp) : g.info(__ldg(P + q * W + gwarp));
+        int np = min(32, mine - pb);
+        if (fits) {
+          // ranked rows: pv = {element offset, length} of the suffix; whole aligned rows: offsets in 16-byte units
+          const uint2 ev = MODE == 2 ? pv : make_uint2(pv.x << 2, pv.y);
+          c += VAR == 1 ? stream_partners(tab, s1, g.d_acol, ev, np, lane)
+                    : (MODE == 2 && VAR >= 2) ? stream_partners_flat_pipe(tab, s1, g.d_acol, ev, np, lane)
+                    : (MODE == 2 && short_max < 0) ? stream_partners_flat(tab, s1, g.d_acol, ev, np, lane)
+                    : short_max > 0 ? stream_partners_mixed(tab, s1, g.d_acol, ev, np, lane, short_max)
+                                    : stream_partners_simple(tab, s1, g.d_acol, ev, np, lane);
+        } else {
+          for (int j = 0; j < np; j++) {
+            uint32_t off = __shfl_sync(kFullMask, pv.x, j);
+            int len = int(__shfl_sync(kFullMask, pv.y, j));
+            const vidType *list = g.d_acol + (MODE == 2 ? size_t(off) : (size_t(off) << 2));
+            c += stream_bsearch(rrow, d, list, len, lane);
+          }
+        }
+      }
+      acc += c;
+    }
+  }
+  acc = warp_reduce(acc);
+  if (lane == 0 && acc) atomicAdd(total, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// tc.flat = 4: the ranked kernel on keys stored as 4 * rank + 1 (g->rk_acol4, built once by k_scale_keys).
+//
+// After the flat form the stream loop was 84 instructions per window of 128 elements, IPC 3.2 of 4
+// (profiles/r02p_tc_s22_flat1.summary.txt): 36 in the four probes, 14 in the level-2 probe and its checks.
+// With every key = 1 mod 4 and below 2^31:
+//   * the level-1 slot's BYTE offset is one LOP3 (key & mask4; the low bits of a rank are as good as a
+//     multiplicative hash: hub ranks are consecutive, the others arbitrary) and the table base rides in the
+//     LDS address -- IMAD + SHF + LEA before;
+//   * the two low bits count flagged slots: one predicated add (r += key) remembers the key AND counts it,
+//     where the flat form spent SEL + IADD; r & 3 == 1 afterwards means "exactly one, and r is its key".
+// Rows are padded with kPad4 (1 mod 4, above every key), and dead slots of a batch's last window read a unit
+// of padding behind the array instead of presetting four registers.
+constexpr uint32_t kPad4 = kHyPad;
+
+struct ScaledTable {
+  uint32_t *t1, *t2, *stash;
+  int *nstash;
+  uint32_t mask4;    // (S1 - 1) << 2
+  int sh2, stash_cap;
+
+  __device__ __forceinline__ void configure(uint32_t *base, int b1, int cap) {
+    const int b2 = max(b1 - 2, 3);
+    t1 = base; t2 = base + (1 << b1); stash = t2 + (1 << b2);
+    nstash = reinterpret_cast<int *>(stash + cap);
+    mask4 = ((1u << b1) - 1u) << 2; sh2 = 32 - b2; stash_cap = cap;
+  }
+  __device__ __forceinline__ uint32_t &slot1(uint32_t x) const { return t1[(x & mask4) >> 2]; }
+  __device__ __forceinline__ uint32_t &slot2(uint32_t x) const { return t2[(x * kHashK2) >> sh2]; }
+  // same protocol as RowTable::build: store, re-read, losers move one level down, flags mark the way
+  template <typename SYNC>
+  __device__ __forceinline__ void build(const uint32_t *row, int d, int tid, int nthr, SYNC sync) {
+    const int n = int(mask4 >> 2) + 1 + (1 << (32 - sh2));
+    for (int i = tid; i < n; i += nthr) t1[i] = kSlotEmpty;
+    if (tid == 0) *nstash = 0;
+    sync();
+    for (int i = tid; i < d; i += nthr) { const uint32_t x = __ldg(row + i); slot1(x) = x; }
+    sync();
+    for (int i = tid; i < d; i += nthr) {
+      const uint32_t x = __ldg(row + i), t = slot1(x);
+      if ((t & kKeyMask) != x) { slot1(x) = t | kSlotFlag; slot2(x) = x; }
+    }
+    sync();
+    for (int i = tid; i < d; i += nthr) {
+      const uint32_t x = __ldg(row + i);
+      if ((slot1(x) & kKeyMask) == x) continue;
+      const uint32_t t = slot2(x);
+      if ((t & kKeyMask) != x) {
+        slot2(x) = t | kSlotFlag;
+        const int p = atomicAdd(nstash, 1);
+        if (p < stash_cap) stash[p] = x;
+      }
+    }
+    sync();
+  }
+  __device__ __forceinline__ bool overflowed() const { return *nstash > stash_cap; }
+  __device__ __forceinline__ bool contains(uint32_t x) const {
+    uint32_t t = slot1(x);
+    if ((t & kKeyMask) == x) return true;
+    if (!(t & kSlotFlag)) return false;
+    t = slot2(x);
+    if ((t & kKeyMask) == x) return true;
+    if (!(t & kSlotFlag)) return false;
+    const int n = min(*nstash, stash_cap);
+    for (int i = 0; i < n; i++) if (stash[i] == x) return true;
+    return false;
+  }
+};
+
+__device__ __forceinline__ void probe_scaled(uint32_t s1, uint32_t mask4, uint32_t x, uint32_t &c, uint32_t &r) {
+  const uint32_t tw = RowTable::lds(s1 + (x & mask4));
+  asm("{\n\t.reg .pred pm, pf;\n\t.reg .b32 t;\n\t"
+      "xor.b32 t, %2, %3;\n\tand.b32 t, t, 0x7fffffff;\n\tsetp.ne.u32 pm, t, 0;\n\t"
+      "@!pm add.u32 %0, %0, 1;\n\t"
+      "setp.lt.and.s32 pf, %2, 0, pm;\n\t"
+      "@pf add.u32 %1, %1, %3;\n\t}"
+      : "+r"(c), "+r"(r) : "r"(tw), "r"(x));
+}
+
+__device__ __forceinline__ uint32_t probe_window_scaled(const ScaledTable &tab, uint32_t s1, uint32_t s2, uint4 x) {
+  uint32_t c = 0, r = 0;
+  probe_scaled(s1, tab.mask4, x.x, c, r);
+  probe_scaled(s1, tab.mask4, x.y, c, r);
+  probe_scaled(s1, tab.mask4, x.z, c, r);
+  probe_scaled(s1, tab.mask4, x.w, c, r);
+  const uint32_t t = RowTable::lds(s2 + (((r * kHashK2) >> tab.sh2) << 2));     // r = the key when r & 3 == 1; 0 (never stored) when no slot was flagged
+  const bool miss2 = ((t ^ r) & kKeyMask) != 0;
+  c += miss2 ? 0u : 1u;
+  const uint32_t k = r & 3u;
+  const bool rare = k == 1u ? (miss2 && int32_t(t) < 0) : r != 0u;   // several flagged slots in the lane, or on to the stash
+  if (__any_sync(kFullMask, rare)) {
+    if (rare) c = uint32_t(tab.contains(x.x)) + uint32_t(tab.contains(x.y)) + uint32_t(tab.contains(x.z)) + uint32_t(tab.contains(x.w));
+  }
+  return c;
+}
+
+// the window walk of the flat form over per-lane segments {first unit u0, nu units}: PROBE(uint4) -> count.
+// Every live lane must own at least one unit (an empty segment is given one unit of padding by its caller):
+// the slot -> record rule counts head bits, and two records starting on one slot would share theirs.
+// the entries are streamed once per use and never re-read through L1: tc.ld picks the load flavour (A/B hook;
+// ld.global.cg measured 2-4 % faster than ld.global.nc, L1::no_allocate 3-10 % slower)
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p, int mode) {
+  uint4 v;
+  if (mode == 1) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (mode == 2) asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else v = __ldg(p);
+  return v;
+}
+
+template <typename PROBE>
+__device__ __forceinline__ uint32_t walk_windows(const uint4 *units, uint32_t pad_unit, uint32_t u0, uint32_t nu, int lane, PROBE probe, int ldmode = 0) {
+  uint32_t inc = nu;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const uint32_t pos = inc - nu;
+  const uint32_t total = __shfl_sync(kFullMask, inc, 31);
+  const uint32_t delta = u0 - pos;
+  uint32_t le_mask = 0xffffffffu >> (31 - lane), ln = uint32_t(lane), one = 1u;
+  asm volatile("" : "+r"(ln));
+  asm volatile("" : "+r"(le_mask));
+  asm volatile("" : "+r"(one));
+  uint32_t started = 0, c = 0;
   for (uint32_t w = 0; w < total; w += 32) {
     const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(one, pos - w));
     const int j = int(started + __popc(heads & le_mask)) - 1;
