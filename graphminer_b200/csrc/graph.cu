@@ -848,6 +848,22 @@ int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, 
   return GM_OK;
 }
 
+int gm_graph_orient(gm_graph_t *g, gm_graph_t **dag) {
+  if (!g || !dag) { set_error("gm_graph_orient: null argument"); return GM_EINVAL; }
+  GM_TRY(ensure_dag_child(g));
+  *dag = g->dag_child;
+  return GM_OK;
+}
+
+int gm_graph_download(gm_graph_t *g, int64_t *rowptr, int32_t *colidx) {
+  if (!g || !rowptr || (!colidx && g->ne > 0)) { set_error("gm_graph_download: null argument"); return GM_EINVAL; }
+  GM_CUDA(cudaSetDevice(g->device));
+  GM_CUDA(cudaMemcpyAsync(rowptr, g->d_rowptr, sizeof(eidType) * (size_t(g->nv) + 1), cudaMemcpyDeviceToHost, g->stream));
+  if (g->ne > 0) GM_CUDA(cudaMemcpyAsync(colidx, g->d_colidx, sizeof(vidType) * size_t(g->ne), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  return GM_OK;
+}
+
 int gm_graph_device_view(gm_graph_t *g, int sym_break, void *view_out, size_t view_size, void **stream_out,
                          int *num_sms, int32_t *max_degree) {
   if (!g || !view_out || (sym_break != 0 && sym_break != 1)) { set_error("gm_graph_device_view: bad arguments"); return GM_EINVAL; }

@@ -150,6 +150,12 @@ int gm_graph_set_source_range(gm_graph_t *g, int32_t begin, int32_t end);
  * "motif:formula4" (DAG, supports, 4-cycle tiers of the fast formula path), or "all".  Solvers call it lazily. */
 int gm_graph_prepare(gm_graph_t *g, const char *what);
 int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, int *device);
+/* Graph::orientation (src/common/graph.cc:233-279) on the device: *dag becomes a handle on the (degree, id)-oriented
+ * copy of an UNDIRECTED graph g -- the copy the diamond / house / motif fast paths run on.  It is owned by g (freed
+ * with it, do not gm_graph_free it) and shares g's stream.  gm_graph_download copies a handle's CSR back to host
+ * arrays of nv + 1 and ne entries (gm_graph_info gives the sizes). */
+int gm_graph_orient(gm_graph_t *g, gm_graph_t **dag);
+int gm_graph_download(gm_graph_t *g, int64_t *rowptr, int32_t *colidx);
 /* For kernels written against the header-only operator API (a GraphMiner kernel author's own, or one emitted by
  * graphminer_b200/codegen.py): the device view of the graph -- a gm::GraphGPU (include/gm/graph_gpu.cuh) copied into
  * view_out, with the COO task list of Graph::init_edgelist(sym_break) built (graph_gpu.h:124-178) -- plus the

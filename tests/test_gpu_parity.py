@@ -604,6 +604,11 @@ def test_host_entry_points_on_two_devices(citeseer, mico):
             assert capi.motif_host(rp, ci, 3, False, md, n_gpus=2) == k["motif3"]
     rp, ci, md = citeseer
     assert capi.sgl_host(rp, ci, "rectangle", md, n_gpus=2) == KAT["citeseer"]["rectangle"]
+    for hub in (1024, 65536):                             # hybrid rows on both sides of the hub split, sharded
+        capi.set_option("tc.hub", hub)
+        grp, gci = _graph("rmat16")
+        orp, oci, omd = _dag(grp, gci)
+        assert capi.tc_host(orp, oci, omd, n_gpus=2) == GOLD["rmat16"]["tc"]
     capi.set_option("sgl.algo", "list"); capi.set_option("motif.algo", "list")
     assert capi.sgl_host(rp, ci, "diamond", md, n_gpus=2) == KAT["citeseer"]["diamond"]
     assert capi.motif_host(rp, ci, 4, True, md, n_gpus=2) == KAT["citeseer"]["motif4"]
@@ -793,3 +798,18 @@ def test_mapped_graph_feeds_the_host_entry_points(tmp_path):
     assert capi.tc_host(m_rp, m_ci, m_md) == GOLD["rmat14"]["tc"]
     u_rp, u_ci, u_md, _ = capi.map_graph(prefix, pin=False)
     assert capi.tc_host(u_rp, u_ci, u_md) == GOLD["rmat14"]["tc"]
+
+
+@pytest.mark.parametrize("name", ["rmat8", "rmat12", "rmat14", "shaped3000"])
+def test_device_orientation_matches_the_host_and_the_oracle(name):
+    """k_orient (support.cu) against Graph::orientation as restated by the host library and by the oracle:
+    the same rows in the same order, bit for bit"""
+    rp, ci = _graph(name)
+    want_rp, want_ci, _ = capi.host_orient(rp, ci)
+    o_rp, o_ci = oracle.orient(rp, ci)[:2]
+    assert np.array_equal(want_rp, o_rp) and np.array_equal(want_ci, o_ci)
+    with capi.DeviceGraph(rp, ci, 0) as g:
+        got_rp, got_ci = g.orient()
+        assert np.array_equal(got_rp, want_rp) and np.array_equal(got_ci, want_ci)
+        back_rp, back_ci = g.download()
+        assert np.array_equal(back_rp, rp) and np.array_equal(back_ci, ci)
