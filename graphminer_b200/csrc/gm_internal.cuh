@@ -56,6 +56,7 @@ struct Options {
   int tc_hub = kHubRanks;          // hybrid rows: ranks kept as bitmap blocks (a multiple of 16, at most kHubRanks; smaller values are a test hook)
   int tc_ld = 2;                   // hybrid kernel: load flavour of the streamed entries (0 ld.global.nc, 1 + L1::no_allocate, 2 ld.global.cg)
   int tc_occ = 0;                  // hybrid kernel: 0 = 32 registers / 2048 threads per SM, 1 = 40 registers / 1536 threads
+  bool arena = true;               // per-handle device arena for graphs whose arrays exceed ~256 MB (mem.arena)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)
@@ -112,6 +113,7 @@ struct gm_graph {
 
   // rank-relabelled DAG (rank.cu): new id = position in the (total degree, id) order, so every edge
   // goes from a lower to a higher id and rows are sorted by new id
+  char *arena = nullptr; size_t arena_size = 0, arena_used = 0; bool arena_tried = false;   // see dmalloc
   bool rk_ready = false, rk_valid = false;
   uint2 *rk_vinfo = nullptr; gm::vidType *rk_acol = nullptr;
   gm::eidType *rk_nrow = nullptr;      // compact rowptr of the relabelled graph (nv+1)
@@ -181,11 +183,22 @@ struct gm_graph {
 
 namespace gm {
 // stream-ordered allocation on the graph's stream (cudaMallocAsync pool, see device_info())
+// Large graphs take their device arrays from ONE per-handle arena (a single pool allocation whose size depends
+// on |V| and |E| only, bump-allocated, released as a whole with the handle): a gm_*_host call makes ~40
+// allocations between 4 bytes and several GB, and the pool's reuse of freed blocks of ever different sizes
+// fragmented from call to call -- on R-MAT scale 24 an end-to-end call took 71 ms or 93 ms or, after a few calls,
+// 800-2000 ms (profiles/README: r02r).  Same-sized arenas are reused exactly.  Whatever does not fit (or a small
+// graph) goes to cudaMallocAsync as before; freeing an arena block is a no-op.
+cudaError_t arena_alloc(gm_graph *g, void **p, size_t bytes);      // graph.cu
 template <typename T>
 inline cudaError_t dmalloc(gm_graph *g, T **p, size_t bytes) {
-  return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 4, g->stream);
+  return arena_alloc(g, reinterpret_cast<void **>(p), bytes ? bytes : 4);
 }
-inline cudaError_t dfree(gm_graph *g, void *p) { return p ? cudaFreeAsync(p, g->stream) : cudaSuccess; }
+inline cudaError_t dfree(gm_graph *g, void *p) {
+  if (!p) return cudaSuccess;
+  if (g->arena && static_cast<char *>(p) >= g->arena && static_cast<char *>(p) < g->arena + g->arena_size) return cudaSuccess;
+  return cudaFreeAsync(p, g->stream);
+}
 // a handle that OWNS uninitialised CSR arrays of the given byte sizes (>= the CSR itself); the caller fills them
 // on g->stream and then calls graph_finish_owned (solvers.cu: sharded upload + all-gather)
 int graph_alloc_owned(int32_t nv, int64_t ne, int32_t max_degree, int device, size_t rowptr_bytes, size_t colidx_bytes, gm_graph **out);

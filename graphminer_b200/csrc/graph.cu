@@ -377,6 +377,26 @@ static void free_aux(gm_graph *g) {
   dfree(g, g->d_rrowptr); dfree(g, g->d_rcolidx); g->d_rrowptr = nullptr; g->d_rcolidx = nullptr;
 }
 
+cudaError_t arena_alloc(gm_graph *g, void **p, size_t bytes) {
+  const size_t need = (bytes + 255) & ~size_t(255);
+  if (!g->arena_tried) {
+    g->arena_tried = true;
+    // what the ranked + hybrid TC pipeline allocates, temporaries included: ~130 B per vertex + ~29 B per edge
+    const size_t want = size_t(176) * size_t(g->nv) + size_t(40) * size_t(g->ne) + (size_t(64) << 20);
+    if (options().arena && want >= (size_t(256) << 20) && want <= (size_t(24) << 30)) {
+      void *a = nullptr;
+      if (cudaMallocAsync(&a, want, g->stream) == cudaSuccess) { g->arena = static_cast<char *>(a); g->arena_size = want; g->arena_used = 0; }
+      else cudaGetLastError();
+    }
+  }
+  if (g->arena && g->arena_used + need <= g->arena_size) {
+    *p = g->arena + g->arena_used;
+    g->arena_used += need;
+    return cudaSuccess;
+  }
+  return cudaMallocAsync(p, bytes, g->stream);
+}
+
 // Per-device one-time setup: keep freed blocks in the stream-ordered pool (repeated gm_*_host calls
 // then allocate without going to the driver) and cache the slow cudaGetDeviceProperties.
 struct DeviceInfo { bool ready = false; int sms = kNumSMsB200; int smem_optin = 0; };
@@ -728,6 +748,9 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "tc.occ") {
     if (v != "0" && v != "1") { set_error("tc.occ: 0 or 1"); return GM_EINVAL; }
     options().tc_occ = atoi(value);
+  } else if (k == "mem.arena") {
+    if (v != "0" && v != "1") { set_error("mem.arena: 0 or 1"); return GM_EINVAL; }
+    options().arena = v == "1";
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";
@@ -795,6 +818,7 @@ int gm_graph_free(gm_graph_t *g) {
   dfree(g, g->dag_rowptr); dfree(g, g->dag_colidx); dfree(g, g->d_support); dfree(g, g->d_indeg); dfree(g, g->d_sq);
   if (g->own_csr) { dfree(g, g->d_rowptr); dfree(g, g->d_colidx); }
   dfree(g, g->d_counts); dfree(g, g->d_ticket); dfree(g, g->d_scratch); dfree(g, g->d_gmat);
+  if (g->arena) { cudaFreeAsync(g->arena, g->stream); g->arena = nullptr; }
   // complete the stream-ordered frees now: the blocks return to the pool free of stream dependencies, so
   // the next handle (usually on another stream) reuses them instead of growing the pool
   if (g->stream) cudaStreamSynchronize(g->stream);

@@ -280,7 +280,14 @@ struct HyCtx {
   const uint2 *vinfo; const vidType *acol;           // ranked plain rows
   uint4 *hv; uint32_t *data;
   uint2 *prec_plain;                                 // rk_prec (records of small roots only), may be null
+  const uint32_t *small_bits;                        // bit v: ranked row v has at most 32 elements (the plain-kernel class)
 };
+
+__global__ void k_small_bits(vidType nv, const uint2 *__restrict__ vinfo, uint32_t *__restrict__ bits) {
+  const vidType v = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned m = __ballot_sync(kFullMask, v < nv && vinfo[v].y <= 32u);
+  if ((threadIdx.x & 31) == 0 && v < nv) bits[v >> 5] = m;
+}
 
 // 8 lanes per row walk its sorted elements 8 at a time.  head = first element of a 16-rank hub block; the entry
 // index of a hub element = heads up to and including it - 1.  F(i, x, is_hub, entry, block) is called per element.
@@ -310,7 +317,7 @@ __device__ __forceinline__ void hy_walk_row(const HyCtx &c, const vidType *row, 
 }
 
 __global__ void __launch_bounds__(256)
-k_hy_fill(HyCtx c, RowCtx rc, const eidType *prow, unsigned *cursor, uint2 *prec) {
+k_hy_fill(HyCtx c, RowCtx rc, unsigned long long *cursor, uint2 *prec) {     // cursor[b] starts at rk_prow[b]: one gather per record
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const vidType a = vidType(t >> 3); const int sub = int(t & 7), lane = threadIdx.x & 31;
   const bool valid = a < c.nv;
@@ -331,8 +338,8 @@ k_hy_fill(HyCtx c, RowCtx rc, const eidType *prow, unsigned *cursor, uint2 *prec
     if (is_hub) atomicOr(&c.data[base_e + entry], (uint32_t(blk) << 17) | (1u << (uint32_t(x - c.hb) & 15u)));
     else c.data[base_k + i] = (uint32_t(x) << 2) | 1u;
     if (i + 1 < d && rec_kept(rc, keep_src, x)) {
-      const eidType slot = prow[x] + eidType(atomicAdd(&cursor[x], 1u));
-      if (c.prec_plain && c.vinfo[x].y <= 32u) c.prec_plain[slot] = make_uint2(base_plain + uint32_t(i) + 1u, uint32_t(d - i - 1));
+      const eidType slot = eidType(atomicAdd(&cursor[x], 1ull));
+      if (c.prec_plain && ((c.small_bits[uint32_t(x) >> 5] >> (uint32_t(x) & 31u)) & 1u)) c.prec_plain[slot] = make_uint2(base_plain + uint32_t(i) + 1u, uint32_t(d - i - 1));
       else prec[slot] = is_hub ? make_uint2(base_e + entry, ne - entry)
                                : make_uint2(base_k + uint32_t(i) + 1u, ((nk - uint32_t(i) - 1u) << 13) | ne);
     }
@@ -531,20 +538,24 @@ int ensure_hybrid(gm_graph *g) {
   HyCtx c; c.nv = nv; c.hb = nv > hub ? nv - hub : 0;
   c.vinfo = g->rk_vinfo; c.acol = g->rk_acol;
   c.prec_plain = g->rk_prec_full ? nullptr : g->rk_prec;
-  unsigned *cursor = nullptr;
+  unsigned long long *cursor = nullptr;
+  uint32_t *small_bits = nullptr;
   const uint32_t total_units = uint32_t(g->rk_acol_len >> 2) + uint32_t(nv);
   const size_t words = (size_t(total_units) + 2) << 2;
   GM_CUDA(dmalloc(g, &g->hy_vinfo, sizeof(uint4) * size_t(nv)));
   GM_CUDA(dmalloc(g, &g->hy_data, sizeof(uint32_t) * words));
   GM_CUDA(dmalloc(g, &g->hy_prec, sizeof(uint2) * size_t(g->ne > 0 ? g->ne : 1)));
-  GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned) * (size_t(nv) + 1)));
-  GM_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * (size_t(nv) + 1), g->stream));
+  static_assert(sizeof(eidType) == sizeof(unsigned long long), "the record cursors start as a copy of rk_prow");
+  GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned long long) * (size_t(nv) + 1)));
+  GM_CUDA(dmalloc(g, &small_bits, sizeof(uint32_t) * ((size_t(nv) >> 5) + 1)));
+  GM_CUDA(cudaMemcpyAsync(cursor, g->rk_prow, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, g->stream));
   GM_CUDA(cudaMemsetAsync(g->hy_data, 0, sizeof(uint32_t) * words, g->stream));      // entries are OR-ed in; padding entries stay 0
-  c.hv = g->hy_vinfo; c.data = g->hy_data;
-  k_hy_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, persistent_rowctx(g), g->rk_prow, cursor, g->hy_prec);
+  k_small_bits<<<nblk((int64_t(nv) + 31) / 32 * 32), 256, 0, g->stream>>>(nv, g->rk_vinfo, small_bits);
+  c.hv = g->hy_vinfo; c.data = g->hy_data; c.small_bits = small_bits;
+  k_hy_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, persistent_rowctx(g), cursor, g->hy_prec);
   k_hy_tail<<<1, 32, 0, g->stream>>>(g->hy_data, total_units);
   GM_CUDA(cudaGetLastError());
-  GM_CUDA(dfree(g, cursor));
+  GM_CUDA(dfree(g, cursor)); GM_CUDA(dfree(g, small_bits));
   g->hy_units = total_units; g->hy_hb = c.hb;
   g->hy_valid = true;
   trace_phase(g->stream, "rank: hybrid rows (hub bitmaps + keys) + records");
