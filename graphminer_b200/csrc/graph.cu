@@ -751,6 +751,9 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "mem.arena") {
     if (v != "0" && v != "1") { set_error("mem.arena: 0 or 1"); return GM_EINVAL; }
     options().arena = v == "1";
+  } else if (k == "sup.flat") {
+    if (v != "0" && v != "1") { set_error("sup.flat: 0 or 1"); return GM_EINVAL; }
+    options().sup_flat = atoi(value);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";

@@ -17,6 +17,7 @@
 // A last pass sums C(t,2) over the edges owned by the source range.  All integer, bit-exact.
 #include "gm_internal.cuh"
 #include "hash_table.cuh"
+#include "stream_walk.cuh"
 
 #include <cub/cub.cuh>
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void sup_sync() { if (GT == 32) __syncwarp(); else __
 template <int GT, int MAXB1, int CAP>
 __global__ void __launch_bounds__(SupCfg<GT, MAXB1, CAP>::kCtaThreads)
 tc_support_kernel(GraphGPU g, const eidType *__restrict__ prow, const uint2 *__restrict__ prec,
-                  const WorkItem *__restrict__ items, int64_t nitems, int *ticket, uint32_t *__restrict__ sup) {
+                  const WorkItem *__restrict__ items, int64_t nitems, int *ticket, uint32_t *__restrict__ sup, int flat) {
   using Cfg = SupCfg<GT, MAXB1, CAP>;
   extern __shared__ uint32_t smem[];
   __shared__ int64_t s_next;
@@ -151,6 +152,38 @@ tc_support_kernel(GraphGPU g, const eidType *__restrict__ prow, const uint2 *__r
       uint2 pv = make_uint2(0, 0);
       if (q < mine) pv = __ldg(R + q * W + gwarp);
       const int np = min(32, mine - pb);
+      if (fits && flat) {
+        // the suffixes of the warp's 32 records as one sequence of 16-byte units (stream_walk.cuh): one LDG.128
+        // and four probes per lane and window.  The elements a whole unit adds in front of a suffix are <= b,
+        // the padding behind it is kVidMax: neither is in the table of N+(b).
+        const uint32_t nu = q < mine ? ((pv.x & 3u) + pv.y + 3u) >> 2 : 0u;
+        walk_windows(reinterpret_cast<const uint4 *>(g.d_acol), 0u, pv.x >> 2, nu, lane, [&](uint4 x, uint32_t u, int j, bool live) {
+          uint32_t hits = 0;
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+          if (live) {
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const uint32_t h = (xs[i] * kHashK1) >> tab.sh1;
+              const uint32_t tw = RowTable::lds(s1 + (h << 2));
+              int slot = -1;
+              if ((tw & kKeyMask) == xs[i]) slot = int(h);
+              else if (int32_t(tw) < 0) slot = tab.find_slot(xs[i]);         // overflowed slot: level 2 / stash
+              if (slot >= 0) {
+                hits++;
+                atomicAdd(sup + (size_t(u) << 2) + i, 1u);                    // edge (a,c): the streamed element's own slot
+                atomicAdd(cnt + pay[slot], 1u);                               // edge (b,c), flushed below
+              }
+            }
+          }
+          // edge (a,b): b sits right before the suffix; the lanes of one record add up first
+          const uint32_t ab = __shfl_sync(kFullMask, pv.x, j) - 1u;
+          const unsigned peers = __match_any_sync(kFullMask, live ? j : 32 + lane);
+          const uint32_t rec_hits = __reduce_add_sync(peers, hits);
+          if (rec_hits && lane == __ffs(peers) - 1) atomicAdd(sup + ab, rec_hits);
+          return 0u;
+        }, 2);
+        continue;
+      }
       for (int j = 0; j < np; j++) {
         const uint32_t off = __shfl_sync(kFullMask, pv.x, j);
         const int len = int(__shfl_sync(kFullMask, pv.y, j));
@@ -226,7 +259,7 @@ static int launch_support_class(gm_graph *g, gm_graph *c, int cls, cudaStream_t 
   int grid = int(std::min<int64_t>(want, int64_t(occ) * g->num_sms));
   GraphGPU view = c->view(0);
   view.d_vinfo = c->rk_vinfo; view.d_acol = c->rk_acol;
-  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, c->rk_prow, c->rk_prec, il.d_items, il.n, g->d_ticket + cls, g->d_support);
+  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, c->rk_prow, c->rk_prec, il.d_items, il.n, g->d_ticket + cls, g->d_support, options().sup_flat);
   (*launches)++;
   return GM_OK;
 }

@@ -13,6 +13,7 @@
 //                       implementation for cross-checking and as the "operator API" consumer.
 #include "gm_internal.cuh"
 #include "hash_table.cuh"
+#include "stream_walk.cuh"
 
 namespace gm {
 
@@ -197,11 +198,6 @@ __device__ __forceinline__ uint32_t probe_window(const RowTable &tab, uint32_t s
   return c;
 }
 
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // PTX shl: shift amounts above 31 give 0
-  uint32_t r;
-  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
-  return r;
-}
 
 __device__ __forceinline__ uint32_t stream_partners_flat(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane) {
   const uint4 *units = reinterpret_cast<const uint4 *>(acol);
@@ -471,54 +467,13 @@ __device__ __forceinline__ uint32_t probe_window_scaled(const ScaledTable &tab, 
   return c;
 }
 
-// the window walk of the flat form over per-lane segments {first unit u0, nu units}: PROBE(uint4) -> count.
-// Every live lane must own at least one unit (an empty segment is given one unit of padding by its caller):
-// the slot -> record rule counts head bits, and two records starting on one slot would share theirs.
-// the entries are streamed once per use and never re-read through L1: tc.ld picks the load flavour (A/B hook;
-// ld.global.cg measured 2-4 % faster than ld.global.nc, L1::no_allocate 3-10 % slower)
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p, int mode) {
-  uint4 v;
-  if (mode == 1) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  else if (mode == 2) asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  else v = __ldg(p);
-  return v;
-}
-
-template <typename PROBE>
-__device__ __forceinline__ uint32_t walk_windows(const uint4 *units, uint32_t pad_unit, uint32_t u0, uint32_t nu, int lane, PROBE probe, int ldmode = 0) {
-  uint32_t inc = nu;
-  #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
-    if (lane >= d) inc += t;
-  }
-  const uint32_t pos = inc - nu;
-  const uint32_t total = __shfl_sync(kFullMask, inc, 31);
-  const uint32_t delta = u0 - pos;
-  uint32_t le_mask = 0xffffffffu >> (31 - lane), ln = uint32_t(lane), one = 1u;
-  asm volatile("" : "+r"(ln));
-  asm volatile("" : "+r"(le_mask));
-  asm volatile("" : "+r"(one));
-  uint32_t started = 0, c = 0;
-  for (uint32_t w = 0; w < total; w += 32) {
-    const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(one, pos - w));
-    const int j = int(started + __popc(heads & le_mask)) - 1;
-    started += __popc(heads);
-    const uint32_t s = w + ln;
-    uint32_t u = __shfl_sync(kFullMask, delta, j) + s;
-    u = s < total ? u : pad_unit;
-    c += probe(ld_stream(units + u, ldmode));
-  }
-  return c;
-}
-
 __device__ __forceinline__ uint32_t stream_partners_scaled(const ScaledTable &tab, uint32_t s1, uint32_t s2, const uint4 *units, uint32_t pad_unit,
                                                            uint2 pv, int np, int lane) {
   // {element offset, length} -> whole units; an empty suffix reads one unit of padding
   const bool live = lane < np;
   const uint32_t u0 = pv.y ? pv.x >> 2 : pad_unit;
   const uint32_t nu = !live ? 0u : pv.y ? ((pv.x & 3u) + pv.y + 3u) >> 2 : 1u;
-  return walk_windows(units, pad_unit, u0, nu, lane, [&](uint4 x) { return probe_window_scaled(tab, s1, s2, x); });
+  return walk_windows(units, pad_unit, u0, nu, lane, [&](uint4 x, uint32_t, int, bool) { return probe_window_scaled(tab, s1, s2, x); });
 }
 
 template <int GT, int MAXB1, int CAP>
@@ -685,7 +640,7 @@ tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data
         if (fits) {
           const uint32_t u0 = rec.y ? rec.x >> 2 : pad_keys;
           const uint32_t nu = !live ? 0u : rec.y ? ((rec.x & 3u) + rec.y + 3u) >> 2 : 1u;
-          c += walk_windows(units, pad_keys, u0, nu, lane, [&](uint4 x) { return probe_window_scaled(tab, s1, s2, x); });
+          c += walk_windows(units, pad_keys, u0, nu, lane, [&](uint4 x, uint32_t, int, bool) { return probe_window_scaled(tab, s1, s2, x); });
         } else {
           const int np = min(32, mine - pb);
           for (int j = 0; j < np; j++) {
@@ -698,7 +653,7 @@ tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data
       if (h.w) {
         const uint32_t u0 = rec.w ? rec.z >> 2 : pad_zero;
         const uint32_t nu = !live ? 0u : rec.w ? ((rec.z & 3u) + rec.w + 3u) >> 2 : 1u;
-        c += walk_windows(units, pad_zero, u0, nu, lane, [&](uint4 e) { return probe_window_hub(sb, e); }, ldmode);
+        c += walk_windows(units, pad_zero, u0, nu, lane, [&](uint4 e, uint32_t, int, bool) { return probe_window_hub(sb, e); }, ldmode);
       }
     }
     acc += c;
