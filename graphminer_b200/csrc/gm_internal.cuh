@@ -52,7 +52,7 @@ struct Options {
   std::string tc_algo = "auto";
   std::string clique_algo = "auto";
   int tc_short = 16;               // TC: partner suffixes of at most this many elements are walked by one lane each (0: all warp-wide)
-  int tc_flat = 5;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (0: a loop per record, 2: flat with 40 registers / 1536 threads per SM)
+  int tc_flat = 5;                 // TC (ranked): walk the suffixes of 32 records as one sequence of 16-byte units (5: hybrid rows, 4: scaled keys, 1: flat windows on plain rows, 0: a loop per record)
   int tc_hub = kHubRanks;          // hybrid rows: ranks kept as bitmap blocks (a multiple of 16, at most kHubRanks; smaller values are a test hook)
   int tc_ld = 2;                   // hybrid kernel: load flavour of the streamed entries (0 ld.global.nc, 1 + L1::no_allocate, 2 ld.global.cg)
   int tc_occ = 0;                  // hybrid kernel: 0 = 32 registers / 2048 threads per SM, 1 = 40 registers / 1536 threads

@@ -736,7 +736,7 @@ int gm_set_option(const char *key, const char *value) {
     if (end == value || *end || t < 0 || t > 1024) { set_error("tc.short: suffix length in [0, 1024] (0 = off), got '%s'", value); return GM_EINVAL; }
     options().tc_short = int(t);
   } else if (k == "tc.flat") {
-    if (v != "0" && v != "1" && v != "2" && v != "3" && v != "4" && v != "5") { set_error("tc.flat: 0 .. 5"); return GM_EINVAL; }
+    if (v != "0" && v != "1" && v != "4" && v != "5") { set_error("tc.flat: 0, 1, 4 or 5"); return GM_EINVAL; }
     options().tc_flat = atoi(value);
   } else if (k == "tc.hub") {
     char *end = nullptr; long t = strtol(value, &end, 10);

@@ -26,7 +26,7 @@ struct GroupCfg {
   // resident CTAs the register allocation must allow: 1536 threads per SM for the two main classes (the
   // prefetching stream loop holds two blocks of elements in registers: ~42 registers per thread)
   static constexpr int kMinCtas = GT == 256 ? 8 : GT == 512 ? 4 : 1;
-  // tc.flat=3: 1536 threads per SM (40 registers): room for the prefetched window
+  // tc.occ=1 (hybrid kernel A/B hook): 1536 threads per SM, 40 registers
   static constexpr int kMinCtasRelaxed = GT == 256 ? 6 : GT == 512 ? 3 : 1;
 };
 
@@ -234,48 +234,6 @@ __device__ __forceinline__ uint32_t stream_partners_flat(const RowTable &tab, ui
   return c;
 }
 
-// The flat form with the loads of window w+1 issued before window w is probed (tc.flat = 2 | 3): the chain
-// REDUX -> SHFL -> LDG -> LDS -> LDS of one window is ~10 dependent steps, one of them a trip to L2 or HBM.
-__device__ __forceinline__ uint32_t stream_partners_flat_pipe(const RowTable &tab, uint32_t s1, const vidType *acol, uint2 pv, int np, int lane) {
-  const uint4 *units = reinterpret_cast<const uint4 *>(acol);
-  uint32_t s2 = uint32_t(__cvta_generic_to_shared(tab.t2));
-  const uint32_t nu = lane < np ? ((pv.x & 3u) + pv.y + 3u) >> 2 : 0u;
-  uint32_t inc = nu;
-  #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
-    if (lane >= d) inc += t;
-  }
-  const uint32_t pos = inc - nu;
-  const uint32_t total = __shfl_sync(kFullMask, inc, 31);
-  const uint32_t delta = (pv.x >> 2) - pos;
-  uint32_t le_mask = 0xffffffffu >> (31 - lane);
-  uint32_t ln = uint32_t(lane);
-  asm volatile("" : "+r"(ln));
-  asm volatile("" : "+r"(le_mask));
-  asm volatile("" : "+r"(s1));
-  asm volatile("" : "+r"(s2));
-  uint32_t started = 0, c = 0;
-  auto fetch = [&](uint32_t w) {
-    const uint32_t heads = __reduce_or_sync(kFullMask, shl_clamp(1u, pos - w));
-    const int j = int(started + __popc(heads & le_mask)) - 1;
-    started += __popc(heads);
-    const uint32_t s = w + ln;
-    const uint32_t u = __shfl_sync(kFullMask, delta, j) + s;
-    return ldg4_or_pad(units + u, s < total);
-  };
-  if (total == 0) return 0;
-  uint4 y = fetch(0);
-  for (uint32_t w = 32; ; w += 32) {
-    const uint4 x = y;
-    const bool more = w < total;                                   // warp-uniform
-    if (more) y = fetch(w);
-    c += probe_window(tab, s1, s2, x);
-    if (!more) break;
-  }
-  return c;
-}
-
 // Fallback when the root row does not fit the table: search it where it lies (global / L2).
 __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, const vidType *list, int len, int lane) {
   uint32_t c = 0;
@@ -287,10 +245,11 @@ __device__ __forceinline__ uint32_t stream_bsearch(const vidType *root, int d, c
 // MODE 1: partners = in-neighbours (prow/pcol = reverse adjacency)
 // MODE 2: RANKED graph (rank.cu): g's aligned view holds the rank-relabelled rows, partners are
 //         records {element offset of the row suffix to stream, its length} in prec
-// VAR 0: stream loop chosen at run time (flat / mixed / per record), 1: cross-partner prefetch (tc.pipe),
-// 2: flat with prefetch, 3: flat with prefetch and the relaxed register allocation
+// VAR 0: stream loop chosen at run time (flat / mixed / per record), 1: cross-partner prefetch (tc.pipe).
+// (Flat windows with the next window prefetched, at 32 and at 40 registers, measured 3-8 % slower than the plain
+// flat loop and were removed.)
 template <int GT, int MAXB1, int CAP, int MODE, int VAR>
-__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, VAR == 3 ? GroupCfg<GT>::kMinCtasRelaxed : GroupCfg<GT>::kMinCtas)
+__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, GroupCfg<GT>::kMinCtas)
 tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__restrict__ pcol,
                const uint2 *__restrict__ prec,
                const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int short_max) {
@@ -351,7 +310,6 @@ tc_hash_kernel(GraphGPU g, const eidType *__restrict__ prow, const vidType *__re
           // ranked rows: pv = {element offset, length} of the suffix; whole aligned rows: offsets in 16-byte units
           const uint2 ev = MODE == 2 ? pv : make_uint2(pv.x << 2, pv.y);
           c += VAR == 1 ? stream_partners(tab, s1, g.d_acol, ev, np, lane)
-                    : (MODE == 2 && VAR >= 2) ? stream_partners_flat_pipe(tab, s1, g.d_acol, ev, np, lane)
                     : (MODE == 2 && short_max < 0) ? stream_partners_flat(tab, s1, g.d_acol, ev, np, lane)
                     : short_max > 0 ? stream_partners_mixed(tab, s1, g.d_acol, ev, np, lane, short_max)
                                     : stream_partners_simple(tab, s1, g.d_acol, ev, np, lane);
@@ -789,8 +747,6 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
     return GM_OK;
   }
   auto kern = options().tc_pipe ? tc_hash_kernel<GT, MAXB1, CAP, MODE, 1>
-              : (MODE == 2 && options().tc_flat == 2) ? tc_hash_kernel<GT, MAXB1, CAP, MODE, MODE == 2 ? 2 : 0>
-              : (MODE == 2 && options().tc_flat == 3) ? tc_hash_kernel<GT, MAXB1, CAP, MODE, MODE == 2 ? 3 : 0>
                                                       : tc_hash_kernel<GT, MAXB1, CAP, MODE, 0>;
   size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
   GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -61,12 +61,15 @@ int gm_device_init(int device);
  *       "tc.shard" = source|dest: whether gm_graph_set_source_range selects edges by their source
  *       (the reference's semantics, default) or by their destination (same total over a partition of
  *       the vertex set; keeps each root's table on one shard -- set before gm_graph_prepare),
- *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.flat" = 5|4|3|2|1|0 (stream loop of
+ *       "batch.*" = tuning of the streaming pipeline; tuning / test hooks: "tc.flat" = 5|4|1|0 (stream loop of
  *       the ranked TC kernel: 5 = hybrid rows, hub bitmaps + hashed keys, the default; 4 = keys stored as
- *       4*rank+1; 1 = flat windows over plain rows, 2|3 = with prefetch; 0 = a loop per partner record, then
+ *       4*rank+1; 1 = flat windows over plain rows; 0 = a loop per partner record, then
  *       "tc.short" = lane-private walk of suffixes up to that length), "tc.hub" = multiple of 16 in [16, 65536]
  *       (ranks kept as bitmap blocks by tc.flat=5; smaller values only for tests), "tc.pipe" = 0|1 (cross-partner
- *       prefetch in the per-record loop; measured slower, off by default), "tc.gt2" = 256|512, "sup.gt2" =
+ *       prefetch in the per-record loop; measured slower, off by default), "tc.ld" = 0|1|2 (load flavour of the
+ *       streamed entries: ld.global.nc | + L1::no_allocate | ld.global.cg, the default), "tc.occ" = 0|1 (hybrid
+ *       kernel at 32 | 40 registers), "sup.flat" = 1|0 (support pass: flat windows | a loop per record),
+ *       "mem.arena" = 1|0 (one device arena per handle for graphs beyond ~256 MB), "tc.gt2" = 256|512, "sup.gt2" =
  *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
  *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers), "c4.hash" = -1|0|1
  *       (cluster tier on dense |V|-sized arrays or per-root hash tables; auto by |V|), "c4.persist" = 0|1 (pin the

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""GPU-side A/B of the TC stream loops on R-MAT graphs: tc.flat = 0 (loop per record) | 1 (flat windows) |
-2 (flat windows, 40 registers).  Usage: python tools/tc_flat_ab.py [scales...] [key=value ...] (run on the GPU box)"""
+"""GPU-side A/B of the TC stream loops on R-MAT graphs: tc.flat = 0 (loop per record) | 1 (flat windows) | 4 (scaled keys) | 5 (hybrid rows).
+Usage: python tools/tc_flat_ab.py [scales...] [key=value ...] (run on the GPU box)"""
 import os, sys, json
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
@@ -9,7 +9,7 @@ from graphminer_b200.rmat import rmat_graph, orient_dag
 
 scales = [int(a) for a in sys.argv[1:] if a.isdigit()] or [20]
 extra = [a.split("=", 1) for a in sys.argv[1:] if "=" in a]
-variants = os.environ.get("GM_AB_VARIANTS", "tc.flat=0,tc.flat=1,tc.flat=2").split(",")
+variants = os.environ.get("GM_AB_VARIANTS", "tc.flat=0,tc.flat=1,tc.flat=4,tc.flat=5").split(",")
 out = {}
 for scale in scales:
     rp, ci = rmat_graph(scale, device="cuda")
