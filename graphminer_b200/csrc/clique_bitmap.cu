@@ -20,6 +20,7 @@
 // global slab (d <= 2048).  Larger roots go to the list-based warp-per-edge kernel (patterns.cu).
 #include "gm_internal.cuh"
 #include "hash_table.cuh"
+#include "stream_walk.cuh"
 
 namespace gm {
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ AccType count_row(int k, int i, int W, Words<SMM> M, 
 template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS, bool TRI>
 __global__ void __launch_bounds__(CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>::kCtaThreads)
 kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int64_t nitems, int *ticket,
-                      uint32_t *gmat, AccType *total) {
+                      uint32_t *gmat, AccType *total, int flat) {
   using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>;
   extern __shared__ uint32_t smem[];
   __shared__ int64_t s_next;
@@ -193,6 +194,32 @@ kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int
         uint2 pvl = make_uint2(0, 0);
         if (q < mine) pvl = g.info(__ldg(row + q * WG + gwarp));
         const int nr = min(32, mine - rb);
+        if (hashed && flat) {
+          // the rows of the warp's 32 members as one sequence of 16-byte units (stream_walk.cuh): aligned rows,
+          // whole units, padding is a guaranteed miss; the unit's segment lane names the matrix row
+          const uint32_t nu = q < mine ? (pvl.y + 3u) >> 2 : 0u;
+          if (__any_sync(kFullMask, nu != 0u)) {
+            // a member without out-neighbours owns no unit: it is given unit 0, ignored below
+            const uint32_t nu1 = q < mine ? max(nu, 1u) : 0u;
+            const uint32_t empty = __ballot_sync(kFullMask, q < mine && nu == 0u);
+            walk_windows(reinterpret_cast<const uint4 *>(g.d_acol), 0u, nu ? pvl.x : 0u, nu1, lane, [&](uint4 x, uint32_t, int seg, bool live) {
+              if (!live || ((empty >> seg) & 1u)) return 0u;
+              uint32_t *Ai = M + size_t((rb + seg) * WG + gwarp) * stride;
+              const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+              #pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const uint32_t h = (xs[u] * kHashK1) >> tab.sh1;
+                const uint32_t tw = RowTable::lds(s1 + (h << 2));
+                int j = -1;
+                if ((tw & kKeyMask) == xs[u]) j = int(pay[h]);
+                else if (int32_t(tw) < 0) { const int slot = tab.find_slot(xs[u]); if (slot >= 0) j = int(pay[slot]); }
+                if (j >= 0) atomicOr(Ai + (j >> 5), 1u << (j & 31));
+              }
+              return 0u;
+            }, 2);
+          }
+          continue;
+        }
         for (int t = 0; t < nr; t++) {
           const uint32_t off = __shfl_sync(kFullMask, pvl.x, t);
           const int len = int(__shfl_sync(kFullMask, pvl.y, t));
@@ -283,7 +310,7 @@ static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream,
   if (reserve_only) return GM_OK;          // slabs sized on the main stream ahead of fork_streams()
   GraphGPU view = g->view(0);
   if (TRI) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; }     // rank-relabelled rows
-  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, k, il.d_items, il.n, g->d_ticket + 4 + cls, gmat, g->d_counts);
+  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, k, il.d_items, il.n, g->d_ticket + 4 + cls, gmat, g->d_counts, options().clique_flat);
   (*launches)++;
   return GM_OK;
 }

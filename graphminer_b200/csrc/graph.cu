@@ -754,6 +754,9 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "sup.flat") {
     if (v != "0" && v != "1") { set_error("sup.flat: 0 or 1"); return GM_EINVAL; }
     options().sup_flat = atoi(value);
+  } else if (k == "clique.flat") {
+    if (v != "0" && v != "1") { set_error("clique.flat: 0 or 1"); return GM_EINVAL; }
+    options().clique_flat = atoi(value);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";
