@@ -131,7 +131,7 @@ __device__ __forceinline__ AccType count_row(int k, int i, int W, Words<SMM> M, 
 template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS, bool TRI>
 __global__ void __launch_bounds__(CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>::kCtaThreads)
 kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int64_t nitems, int *ticket,
-                      uint32_t *gmat, AccType *total, int flat) {
+                      uint32_t *gmat, AccType *total, int flat, int dlo, int dhi) {
   using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>;
   extern __shared__ uint32_t smem[];
   __shared__ int64_t s_next;
@@ -160,7 +160,7 @@ kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int
     const WorkItem it = items[idx];
     const uint2 ri = g.info(it.root);
     const int d = int(ri.y);
-    if (d < k - 1) continue;                               // too few candidates for a k-clique
+    if (d < k - 1 || d < dlo || d > dhi) continue;         // too few candidates for a k-clique / another launch's share of the class
     const vidType *row = g.NA(ri);
     const int W = (d + 31) >> 5, stride = W | 1;
     uint32_t *M = (d <= SMEM_MAXD) ? smat : gmat + size_t(blockIdx.x) * Cfg::kGlobalMatWords;
@@ -283,7 +283,8 @@ kclique_bitmap_kernel(GraphGPU g, int k, const WorkItem *__restrict__ items, int
 }
 
 template <int GT, int MAXB1, int CAP, int MAXD, int SMEM_MAXD, int LEVELS, bool TRI>
-static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream, int *launches, bool reserve_only = false) {
+static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream, int *launches, bool reserve_only = false,
+                               int dlo = 0, int dhi = 0x7fffffff, int ticket = -1) {
   const ItemList &il = g->items[TRI ? 4 : 2][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = CliqueCfg<GT, MAXB1, CAP, MAXD, SMEM_MAXD, LEVELS>;
@@ -310,7 +311,7 @@ static int launch_clique_class(gm_graph *g, int k, int cls, cudaStream_t stream,
   if (reserve_only) return GM_OK;          // slabs sized on the main stream ahead of fork_streams()
   GraphGPU view = g->view(0);
   if (TRI) { view.d_vinfo = g->rk_vinfo; view.d_acol = g->rk_acol; }     // rank-relabelled rows
-  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, k, il.d_items, il.n, g->d_ticket + 4 + cls, gmat, g->d_counts, options().clique_flat);
+  kern<<<grid, Cfg::kCtaThreads, Cfg::kSmemBytes, stream>>>(view, k, il.d_items, il.n, g->d_ticket + (ticket >= 0 ? ticket : 4 + cls), gmat, g->d_counts, options().clique_flat, dlo, dhi);
   (*launches)++;
   return GM_OK;
 }
@@ -340,6 +341,13 @@ static int run_bitmap_classes(gm_graph *g, int k, int *launches) {
   GM_TRY(fork_streams(g));
   if (k == 4) {           // no per-warp mask levels needed: the big class affords 1024 threads
     if (options().clique_gt1 == 512) GM_TRY((launch_clique_class<512, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));
+    else if (options().clique_split) {
+      // the 33..512 class in two launches over the same item list: roots up to 256 neighbours need a 9 KB matrix
+      // and a 5 KB table, 17 KB per CTA instead of 50 KB -- 6 resident CTAs instead of 4 (the count phase is
+      // latency-bound at 50 % occupancy, profiles/r02t_clique4_s22.summary.txt)
+      GM_TRY((launch_clique_class<256, 10, 64, 256, 256, 0, TRI>(g, k, 1, g->stream, launches, false, 0, 256, 7)));
+      GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->side[2], launches, false, 257, 0x7fffffff)));
+    }
     else GM_TRY((launch_clique_class<256, 11, 64, 512, 512, 0, TRI>(g, k, 1, g->stream, launches)));
     GM_TRY((launch_clique_class<1024, 13, 64, 2048, 1024, 0, TRI>(g, k, 2, g->side[0], launches)));
     GM_TRY((launch_clique_class<32, 7, 16, 32, 32, 0, TRI>(g, k, 0, g->side[1], launches)));

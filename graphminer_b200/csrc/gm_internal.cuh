@@ -59,6 +59,7 @@ struct Options {
   bool arena = true;               // per-handle device arena for graphs whose arrays exceed ~256 MB (mem.arena)
   int sup_flat = 1;                // support pass: flat window streaming (0: a loop per partner record)
   int clique_flat = 1;             // k-clique matrix build: flat window streaming of the members' rows (0: a loop per row)
+  int clique_split = 1;            // 4-clique: the 33..512 class as two launches (<= 256: small shared-memory footprint)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
   int sup_gt2 = 1024;                // same for the support kernel (256 | 512 | 1024)

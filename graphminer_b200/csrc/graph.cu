@@ -757,6 +757,9 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "clique.flat") {
     if (v != "0" && v != "1") { set_error("clique.flat: 0 or 1"); return GM_EINVAL; }
     options().clique_flat = atoi(value);
+  } else if (k == "clique.split") {
+    if (v != "0" && v != "1") { set_error("clique.split: 0 or 1"); return GM_EINVAL; }
+    options().clique_split = atoi(value);
   } else if (k == "tc.pipe") {
     if (v != "0" && v != "1") { set_error("tc.pipe: 0 or 1"); return GM_EINVAL; }
     options().tc_pipe = v == "1";

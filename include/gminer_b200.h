@@ -69,6 +69,8 @@ int gm_device_init(int device);
  *       prefetch in the per-record loop; measured slower, off by default), "tc.ld" = 0|1|2 (load flavour of the
  *       streamed entries: ld.global.nc | + L1::no_allocate | ld.global.cg, the default), "tc.occ" = 0|1 (hybrid
  *       kernel at 32 | 40 registers), "sup.flat" = 1|0 (support pass: flat windows | a loop per record),
+ *       "clique.flat" = 1|0 (bit-matrix build likewise), "clique.split" = 1|0 (4-clique: roots of 33..256 and 257..512
+ *       neighbours in two launches with their own shared-memory footprint),
  *       "mem.arena" = 1|0 (one device arena per handle for graphs beyond ~256 MB), "tc.gt2" = 256|512, "sup.gt2" =
  *       256|512|1024, "clique.gt1" = 256|512 (threads per group of a size class), "c4.small_max" /
  *       "c4.cta_max" / "c4.mid_max" >= 0 (wedges per root that bound the 4-cycle tiers), "c4.hash" = -1|0|1
