@@ -655,13 +655,23 @@ static int map_one(const std::string &path, size_t bytes, int pin, void **out, b
   struct stat st;
   if (fstat(fd, &st) != 0 || size_t(st.st_size) < bytes) { close(fd); set_error("%s is shorter than %zu bytes", path.c_str(), bytes); return GM_EIO; }
   void *p = mmap(nullptr, bytes, PROT_READ, MAP_SHARED, fd, 0);
-  close(fd);
-  if (p == MAP_FAILED) { set_error("mmap of %s failed", path.c_str()); return GM_EIO; }
+  if (p == MAP_FAILED) { close(fd); set_error("mmap of %s failed", path.c_str()); return GM_EIO; }
   int ndev = 0; gm_device_count(&ndev);
   if (pin && ndev > 0) {
-    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly) == cudaSuccess) *registered = true;
-    else cudaGetLastError();                              // pageable mapping: the upload stages it like any other host array
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly) == cudaSuccess) {
+      *registered = true;
+    } else {
+      // the driver refuses read-only file mappings on some systems: a private copy-on-write mapping of the same
+      // file registers like ordinary memory (nothing is written, so no page is ever copied)
+      cudaGetLastError();
+      void *q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+      if (q != MAP_FAILED) {
+        if (cudaHostRegister(q, bytes, cudaHostRegisterPortable) == cudaSuccess) { munmap(p, bytes); p = q; *registered = true; }
+        else { cudaGetLastError(); munmap(q, bytes); }   // pageable mapping: the upload stages it like any other host array
+      }
+    }
   }
+  close(fd);
   std::lock_guard<std::mutex> lk(g_pin_mu);
   g_maps.push_back({p, bytes, *registered});
   *out = p;

@@ -116,7 +116,8 @@ int gm_host_free(void *ptr);
 /* map_file, include/custom_alloc.h:46-58 (Graph's map_vertices / map_edges switches, src/common/graph.cc:37-41):
  * <prefix>.vertex.bin and .edge.bin mapped read-only (MAP_SHARED) instead of read -- nothing is copied until a
  * page is touched.  With pin != 0 and a CUDA device present the mappings are also registered with the driver
- * (cudaHostRegister, read-only), so that gm_*_host uploads them by DMA like the arrays of gm_host_alloc;
+ * (cudaHostRegister; read-only, or through a private copy-on-write mapping of the same file where the driver
+ * refuses read-only registration -- nothing is written either way), so that gm_*_host uploads them by DMA like the arrays of gm_host_alloc;
  * *pinned reports whether that happened.  The pointers stay valid until gm_host_unmap_graph(rowptr, colidx). */
 int gm_host_map_graph(const char *prefix, int32_t nv, int64_t ne, int pin,
                       const int64_t **rowptr, const int32_t **colidx, int *pinned);
