@@ -30,7 +30,7 @@ SYMBOLS = [
     "gm_host_orient", "gm_host_edgelist", "gm_host_partition_part", "gm_host_shard_bounds",
     "gm_host_alloc", "gm_host_free", "gm_host_map_graph", "gm_host_unmap_graph", "gm_host_read_meta", "gm_host_read_graph", "gm_host_write_graph", "gm_host_sort_neighbors", "gm_host_check_sorted",
     "gm_sgl_support_begin", "gm_graph_support", "gm_sgl_support_finish", "gm_motif_support_begin", "gm_motif_support_finish", "gm_graph_upload", "gm_graph_adopt", "gm_graph_free", "gm_graph_set_stream", "gm_graph_set_result_buffer",
-    "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info", "gm_graph_device_view", "gm_graph_orient", "gm_graph_download",
+    "gm_graph_set_source_range", "gm_graph_prepare", "gm_graph_info", "gm_graph_device_view", "gm_graph_orient", "gm_graph_download", "gm_graph_partition",
     "gm_tc", "gm_kclique", "gm_sgl", "gm_motif", "gm_motif_formula", "gm_motif_formula_raw",
     "gm_motif_formula_finish", "gm_last_stats", "gm_last_alg_bytes",
     "gm_tc_host", "gm_kclique_host", "gm_sgl_host", "gm_motif_host",
@@ -95,6 +95,7 @@ def lib():
     L.gm_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_int)]
     L.gm_graph_orient.argtypes = [vp, C.POINTER(vp)]
     L.gm_graph_download.argtypes = [vp, vp, vp]
+    L.gm_graph_partition.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), vp]
     L.gm_tc.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.gm_kclique.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     L.gm_sgl.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
@@ -327,6 +328,17 @@ class DeviceGraph:
         rp = np.empty(nv.value + 1, np.int64); ci = np.empty(max(ne.value, 1), np.int32)
         check(lib().gm_graph_download(h, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p)))
         return rp, ci[: ne.value]
+
+    def partition(self, begin, end):
+        """1-hop induced part of [begin, end) built on the device (graph_partition.cc:24-132).  Returns
+        (part: DeviceGraph, idx_map, local_begin, local_end)."""
+        nv, ne, lb, le = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        check(lib().gm_graph_partition(self._h, begin, end, None, C.byref(nv), C.byref(ne), C.byref(lb), C.byref(le), None))
+        idx = np.empty(max(nv.value, 1), np.int32)
+        h = C.c_void_p()
+        check(lib().gm_graph_partition(self._h, begin, end, C.byref(h), C.byref(nv), C.byref(ne), C.byref(lb), C.byref(le),
+                                       idx.ctypes.data_as(C.c_void_p)))
+        return DeviceGraph(_handle=h, _keep=()), idx[: nv.value], lb.value, le.value
 
     def orient(self):
         """Graph::orientation on the device: (rowptr, colidx) of the (degree, id)-oriented copy, downloaded"""

@@ -594,6 +594,34 @@ int graph_finish_owned(gm_graph *g) {
   return GM_OK;
 }
 
+// ---- 1-hop induced partition on the device (graph_partition.cc:24-132) ------------------------------------
+__global__ void k_part_mark(vidType begin, vidType end, const eidType *__restrict__ rowptr, const vidType *__restrict__ colidx, uint32_t *mask) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const vidType v = begin + vidType(t >> 3); const int sub = int(t & 7);
+  if (v >= end) return;
+  if (sub == 0) mask[v] = 1u;
+  for (eidType e = rowptr[v] + sub; e < rowptr[v + 1]; e += 8) mask[colidx[e]] = 1u;        // every writer stores 1
+}
+// PASS 0: induced degree of a kept vertex -> sub_rowptr[newid]; PASS 1 writes the relabelled row and the index map
+template <int PASS>
+__global__ void k_part_rows(vidType nv, const eidType *__restrict__ rowptr, const vidType *__restrict__ colidx, const uint32_t *__restrict__ mask,
+                            const uint32_t *__restrict__ newid, eidType *sub_rowptr, vidType *sub_colidx, vidType *idx_map) {
+  const int lane = threadIdx.x & 31;
+  const vidType v = vidType((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  if (v >= nv || !mask[v]) return;
+  const uint32_t k = newid[v];
+  eidType out = PASS == 1 ? sub_rowptr[k] : 0;
+  for (eidType base = rowptr[v]; base < rowptr[v + 1]; base += 32) {                         // warp-uniform trip count
+    const eidType e = base + lane;
+    vidType u = 0; bool keep = false;
+    if (e < rowptr[v + 1]) { u = __ldg(colidx + e); keep = mask[u] != 0u; }
+    const unsigned m = __ballot_sync(kFullMask, keep);
+    if (PASS == 1 && keep) sub_colidx[out + __popc(m & ((1u << lane) - 1u))] = vidType(newid[u]);
+    out += __popc(m);
+  }
+  if (lane == 0) { if (PASS == 0) sub_rowptr[k] = out; else idx_map[k] = v; }              // degrees; scanned exclusively by the caller
+}
+
 }  // namespace gm
 
 using namespace gm;
@@ -905,6 +933,59 @@ int gm_graph_download(gm_graph_t *g, int64_t *rowptr, int32_t *colidx) {
   if (g->ne > 0) GM_CUDA(cudaMemcpyAsync(colidx, g->d_colidx, sizeof(vidType) * size_t(g->ne), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
   return GM_OK;
+}
+
+int gm_graph_partition(gm_graph_t *g, int32_t begin, int32_t end, gm_graph_t **part,
+                       int32_t *sub_nv, int64_t *sub_ne, int32_t *local_begin, int32_t *local_end, int32_t *idx_map) {
+  if (!g || begin < 0 || end > g->nv || begin > end) { set_error("gm_graph_partition: bad arguments"); return GM_EINVAL; }
+  GM_CUDA(cudaSetDevice(g->device));
+  const vidType nv = g->nv;
+  uint32_t *mask = nullptr, *newid = nullptr; vidType *d_map = nullptr; eidType *sub_rp = nullptr;
+  gm_graph *sub = nullptr;
+  int rc = [&]() -> int {
+    GM_CUDA(dmalloc(g, &mask, sizeof(uint32_t) * (size_t(nv) + 1)));
+    GM_CUDA(dmalloc(g, &newid, sizeof(uint32_t) * (size_t(nv) + 1)));
+    GM_CUDA(cudaMemsetAsync(mask, 0, sizeof(uint32_t) * (size_t(nv) + 1), g->stream));
+    if (end > begin) k_part_mark<<<nblk(int64_t(end - begin) * 8), 256, 0, g->stream>>>(begin, end, g->d_rowptr, g->d_colidx, mask);
+    GM_CUDA(cudaMemcpyAsync(newid, mask, sizeof(uint32_t) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, g->stream));
+    GM_TRY(exclusive_scan_inplace(g, newid, nv));
+    uint32_t h[3] = {0, 0, 0};                                   // kept vertices, newid[begin], newid[end - 1]
+    GM_CUDA(cudaMemcpyAsync(&h[0], newid + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    if (end > begin) {
+      GM_CUDA(cudaMemcpyAsync(&h[1], newid + begin, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+      GM_CUDA(cudaMemcpyAsync(&h[2], newid + end - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    }
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    const vidType m = vidType(h[0]);
+    if (sub_nv) *sub_nv = m;
+    if (local_begin) *local_begin = end > begin ? int32_t(h[1]) : 0;
+    if (local_end) *local_end = end > begin ? int32_t(h[2]) + 1 : 0;
+    GM_CUDA(dmalloc(g, &sub_rp, sizeof(eidType) * (size_t(m) + 1)));
+    GM_CUDA(cudaMemsetAsync(sub_rp, 0, sizeof(eidType) * (size_t(m) + 1), g->stream));
+    if (nv > 0) k_part_rows<0><<<nblk(int64_t(nv) * 32), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, mask, newid, sub_rp, nullptr, nullptr);
+    GM_TRY(exclusive_scan_inplace(g, sub_rp, m));
+    eidType ne_sub = 0;
+    GM_CUDA(cudaMemcpyAsync(&ne_sub, sub_rp + m, sizeof(eidType), cudaMemcpyDeviceToHost, g->stream));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    if (sub_ne) *sub_ne = ne_sub;
+    if (!part) return GM_OK;                                     // sizes only
+    // the part owns its arrays: a handle with uninitialised CSR storage, filled on its own stream
+    GM_TRY(graph_alloc_owned(m, ne_sub, 0, g->device, 0, 0, &sub));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    GM_CUDA(cudaMemcpyAsync(sub->d_rowptr, sub_rp, sizeof(eidType) * (size_t(m) + 1), cudaMemcpyDeviceToDevice, sub->stream));
+    GM_CUDA(dmalloc(g, &d_map, sizeof(vidType) * size_t(m > 0 ? m : 1)));
+    GM_CUDA(cudaStreamSynchronize(sub->stream));
+    if (nv > 0) k_part_rows<1><<<nblk(int64_t(nv) * 32), 256, 0, g->stream>>>(nv, g->d_rowptr, g->d_colidx, mask, newid, sub->d_rowptr, sub->d_colidx, d_map);
+    if (idx_map && m > 0) GM_CUDA(cudaMemcpyAsync(idx_map, d_map, sizeof(vidType) * size_t(m), cudaMemcpyDeviceToHost, g->stream));
+    GM_CUDA(cudaStreamSynchronize(g->stream));
+    GM_CUDA(cudaGetLastError());
+    GM_TRY(graph_finish_owned(sub));
+    *part = sub; sub = nullptr;
+    return GM_OK;
+  }();
+  dfree(g, mask); dfree(g, newid); dfree(g, d_map); dfree(g, sub_rp);
+  if (sub) gm_graph_free(sub);
+  return rc;
 }
 
 int gm_graph_device_view(gm_graph_t *g, int sym_break, void *view_out, size_t view_size, void **stream_out,

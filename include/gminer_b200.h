@@ -162,6 +162,13 @@ int gm_graph_info(gm_graph_t *g, int32_t *nv, int64_t *ne, int32_t *max_degree, 
  * arrays of nv + 1 and ne entries (gm_graph_info gives the sizes). */
 int gm_graph_orient(gm_graph_t *g, gm_graph_t **dag);
 int gm_graph_download(gm_graph_t *g, int64_t *rowptr, int32_t *colidx);
+/* PartitionedGraph::edgecut_induced_partition1D for ONE part, on the device (src/common/graph_partition.cc:24-132;
+ * gm_host_partition_part is the host form): vertices [begin,end) of g plus their 1-hop neighbours, order-preserving
+ * relabel, vertex-induced CSR.  *part is a new, independent handle on the same device (free it with gm_graph_free);
+ * [*local_begin, *local_end) is the part's own range in the new numbering (its source range, triangle/multigpu.cu:73-75);
+ * idx_map (host, optional, room for the part's vertex count -- call once with part == NULL to learn sub_nv) maps new to old ids. */
+int gm_graph_partition(gm_graph_t *g, int32_t begin, int32_t end, gm_graph_t **part,
+                       int32_t *sub_nv, int64_t *sub_ne, int32_t *local_begin, int32_t *local_end, int32_t *idx_map);
 /* For kernels written against the header-only operator API (a GraphMiner kernel author's own, or one emitted by
  * graphminer_b200/codegen.py): the device view of the graph -- a gm::GraphGPU (include/gm/graph_gpu.cuh) copied into
  * view_out, with the COO task list of Graph::init_edgelist(sym_break) built (graph_gpu.h:124-178) -- plus the

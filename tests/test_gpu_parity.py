@@ -813,3 +813,25 @@ def test_device_orientation_matches_the_host_and_the_oracle(name):
         assert np.array_equal(got_rp, want_rp) and np.array_equal(got_ci, want_ci)
         back_rp, back_ci = g.download()
         assert np.array_equal(back_rp, rp) and np.array_equal(back_ci, ci)
+
+
+@pytest.mark.parametrize("name", ["rmat10", "rmat14", "shaped3000"])
+def test_device_partition_matches_the_host(name):
+    """gm_graph_partition (1-hop induced part built on the device) against gm_host_partition_part: same vertex
+    set, relabelling, rows and local range; and the part counts its share of the triangles (the reference's
+    multi-GPU TC scheme, triangle/multigpu.cu:45-75)"""
+    rp, ci = _graph(name)
+    orp, oci, md = _dag(rp, ci)
+    nv = len(orp) - 1
+    total = 0
+    with capi.DeviceGraph(orp, oci, md) as g:
+        for lo, hi in ((0, nv // 3), (nv // 3, nv // 3), (nv // 3, nv)):
+            want = capi.host_partition_part(orp, oci, lo, hi)
+            part, idx, lb, le = g.partition(lo, hi)
+            with part:
+                got_rp, got_ci = part.download()
+                assert np.array_equal(got_rp, want[0]) and np.array_equal(got_ci, want[1])
+                assert np.array_equal(idx, want[2]) and (lb, le) == (want[3], want[4])
+                part.set_source_range(lb, le)
+                total += part.tc()
+    assert total == GOLD[name]["tc"]
