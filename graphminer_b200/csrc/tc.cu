@@ -2,15 +2,24 @@
 // (reference: src/triangle/omp_base.cc:15-21 for the definition, src/triangle/gpu_base.cu:25-74 +
 // gpu_kernels/bs_warp_edge.cuh:2-18 for the GPU solver this replaces).
 //
-// Two kernels:
-//   tc_hash_kernel   -- the production path.  Vertex-centric: a thread group owns a root row, hashes
-//                       it into a shared-memory RowTable once, and streams the rows of the root's
-//                       partners (its out-neighbours, or with REVERSE its in-neighbours) from HBM,
-//                       one shared-memory probe per streamed element.  Work items (root, partner
-//                       slice) are size-classed by the root degree and handed out dynamically.
+// Kernels (all vertex-centric except the last: a thread group owns a ROOT row, keeps it on chip and streams the
+// rows of the root's partners from HBM; work items (root, partner slice) are size-classed by the root degree and
+// handed out dynamically to persistent grids):
+//   tc_hybrid_kernel -- the production path on the rank-relabelled DAG (tc.flat=5, rank.cu: ensure_hybrid): the
+//                       root's neighbours below the hub range in a shared-memory hash table, its hub neighbours
+//                       as a dense bitmap; partners stream their key suffix against the table and their sparse
+//                       bitmap entries against the bitmap, both as flat windows of 16-byte units
+//                       (stream_walk.cuh).  Roots with at most 32 neighbours stay on tc_hash_kernel.
+//   tc_hash_kernel   -- the table-only kernels: MODE 2 = ranked rows, suffixes of the partners (stream loops:
+//                       flat windows / lane-private short suffixes / per record / with prefetch, A/B hooks);
+//                       MODE 0 / 1 = the graph as given, partners = out- / in-neighbours (inputs that are not
+//                       the reference's orientation).
+//   tc_rank_kernel   -- tc.flat=4: ranked rows with keys stored as 4 * rank + 1 (the table half of the hybrid
+//                       kernel on its own; kept as the A/B that showed the flat loop is not issue-bound).
 //   tc_warp_edge_bs  -- warp-per-COO-edge with the header-only operator API (gm/set_ops.cuh); the
 //                       straightforward re-expression of the reference's kernel, kept as a second
 //                       implementation for cross-checking and as the "operator API" consumer.
+// tc.algo=merge feeds every partner record to the TMA ring pipeline of gm_intersect_batch instead.
 #include "gm_internal.cuh"
 #include "hash_table.cuh"
 #include "stream_walk.cuh"
@@ -23,8 +32,8 @@ struct GroupCfg {
   static constexpr int kCtaThreads = GT < 256 ? 256 : GT;
   static constexpr int kGroupsPerCta = kCtaThreads / GT;
   static constexpr int kWarpsPerGroup = GT / 32;
-  // resident CTAs the register allocation must allow: 1536 threads per SM for the two main classes (the
-  // prefetching stream loop holds two blocks of elements in registers: ~42 registers per thread)
+  // resident CTAs the register allocation must allow: 2048 threads per SM (32 registers) for the two main
+  // classes -- every stream loop measured faster at full occupancy than with more registers (tc.occ)
   static constexpr int kMinCtas = GT == 256 ? 8 : GT == 512 ? 4 : 1;
   // tc.occ=1 (hybrid kernel A/B hook): 1536 threads per SM, 40 registers
   static constexpr int kMinCtasRelaxed = GT == 256 ? 6 : GT == 512 ? 3 : 1;
