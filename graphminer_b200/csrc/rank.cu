@@ -281,6 +281,7 @@ struct HyCtx {
   uint4 *hv; uint32_t *data;
   uint2 *prec_plain;                                 // rk_prec (records of small roots only), may be null
   const uint32_t *small_bits;                        // bit v: ranked row v has at most 32 elements (the plain-kernel class)
+  unsigned *big_tables;                              // set when a non-hub root has more than 512 keys
 };
 
 __global__ void k_small_bits(vidType nv, const uint2 *__restrict__ vinfo, uint32_t *__restrict__ bits) {
@@ -329,7 +330,10 @@ k_hy_fill(HyCtx c, RowCtx rc, unsigned long long *cursor, uint2 *prec) {     // 
   hy_walk_row(c, row, d, sub, lane, nk, ne, [](int, vidType, bool, unsigned, int) {});
   const uint32_t unit_k = vi.x + uint32_t(a), unit_e = unit_k + ((nk + 3u) >> 2);
   const uint32_t base_k = unit_k << 2, base_e = unit_e << 2, base_plain = vi.x << 2;
-  if (valid && sub == 0) c.hv[a] = make_uint4(unit_k, nk, unit_e, ne);
+  if (valid && sub == 0) {
+    c.hv[a] = make_uint4(unit_k, nk, unit_e, ne);
+    if (nk > 512u && a < c.hb) atomicOr(c.big_tables, 1u);        // some root needs a key table beyond the 256-thread configuration (tc.cu)
+  }
   bool keep_src = false;
   if (valid) { const vidType v = rc.orig_of[a]; keep_src = v >= rc.src_begin && v < rc.src_end; }
   // pass 2 (the row is in L1 now): keys, entries, records
@@ -547,14 +551,20 @@ int ensure_hybrid(gm_graph *g) {
   GM_CUDA(dmalloc(g, &g->hy_prec, sizeof(uint2) * size_t(g->ne > 0 ? g->ne : 1)));
   static_assert(sizeof(eidType) == sizeof(unsigned long long), "the record cursors start as a copy of rk_prow");
   GM_CUDA(dmalloc(g, &cursor, sizeof(unsigned long long) * (size_t(nv) + 1)));
-  GM_CUDA(dmalloc(g, &small_bits, sizeof(uint32_t) * ((size_t(nv) >> 5) + 1)));
+  GM_CUDA(dmalloc(g, &small_bits, sizeof(uint32_t) * ((size_t(nv) >> 5) + 2)));       // + the big_tables flag word
+  unsigned *big_tables = small_bits + (size_t(nv) >> 5) + 1;
+  GM_CUDA(cudaMemsetAsync(big_tables, 0, sizeof(unsigned), g->stream));
   GM_CUDA(cudaMemcpyAsync(cursor, g->rk_prow, sizeof(eidType) * (size_t(nv) + 1), cudaMemcpyDeviceToDevice, g->stream));
   GM_CUDA(cudaMemsetAsync(g->hy_data, 0, sizeof(uint32_t) * words, g->stream));      // entries are OR-ed in; padding entries stay 0
   k_small_bits<<<nblk((int64_t(nv) + 31) / 32 * 32), 256, 0, g->stream>>>(nv, g->rk_vinfo, small_bits);
-  c.hv = g->hy_vinfo; c.data = g->hy_data; c.small_bits = small_bits;
+  c.hv = g->hy_vinfo; c.data = g->hy_data; c.small_bits = small_bits; c.big_tables = big_tables;
   k_hy_fill<<<nblk(int64_t(nv) * 8), 256, 0, g->stream>>>(c, persistent_rowctx(g), cursor, g->hy_prec);
   k_hy_tail<<<1, 32, 0, g->stream>>>(g->hy_data, total_units);
   GM_CUDA(cudaGetLastError());
+  unsigned h_big = 0;
+  GM_CUDA(cudaMemcpyAsync(&h_big, big_tables, sizeof(unsigned), cudaMemcpyDeviceToHost, g->stream));
+  GM_CUDA(cudaStreamSynchronize(g->stream));
+  g->hy_big_tables = h_big != 0;
   GM_CUDA(dfree(g, cursor)); GM_CUDA(dfree(g, small_bits));
   g->hy_units = total_units; g->hy_hb = c.hb;
   g->hy_valid = true;

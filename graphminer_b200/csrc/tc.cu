@@ -521,6 +521,7 @@ tc_rank_kernel(const uint2 *__restrict__ vinfo, const uint32_t *__restrict__ aco
 // partner record two flat passes: the key suffix against the table (only when the root has non-hub keys and is
 // no hub itself), the bitmap entries against the bitmap.
 constexpr int kBitmapWords = kHubRanks / 32;
+constexpr int kSmallTableBits = 11;                  // key tables of up to 512 keys: the 256-thread configuration
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   uint16_t v;
@@ -542,7 +543,7 @@ template <int GT, int MAXB1, int CAP, int OCC>
 __global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, OCC ? GroupCfg<GT>::kMinCtasRelaxed : GroupCfg<GT>::kMinCtas)
 tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data, uint32_t pad_keys, uint32_t pad_zero, vidType hb,
                  const eidType *__restrict__ prow, const uint2 *__restrict__ prec,
-                 const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int ldmode) {
+                 const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int ldmode, int share) {
   static_assert(GT >= 256, "one group per CTA");
   using Cfg = GroupCfg<GT>;
   extern __shared__ uint32_t smem[];
@@ -570,6 +571,12 @@ tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data
     if (first >= nitems) break;
     const WorkItem it = items[first];
     h = hv[it.root];
+    // two launches may share one item list (class 2, launch_hash_class): share 1 takes the roots whose key table
+    // fits THIS configuration and leaves the others to the launch with the large table (share 2)
+    if (share) {
+      const bool small = !(h.y > 0 && it.root < hb) || RowTable::bits_for(int(h.y)) <= kSmallTableBits;
+      if (small != (share == 1)) { h = make_uint4(0, 0, 0, 0); continue; }
+    }
     const uint32_t *keys = data + (size_t(h.x) << 2), *ents = data + (size_t(h.z) << 2);
     const int nk = int(h.y);
     for (uint32_t i = tid; i < h.w; i += GT) { const uint32_t e = __ldg(ents + i); sts_u16(sb + (e >> 16), e & 0xffffu); }
@@ -724,7 +731,7 @@ static int run_tc_merge(gm_graph *g, int *launches) {
 }
 
 template <int GT, int MAXB1, int CAP, int MODE>
-static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *launches) {
+static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *launches, int share = 0, int ticket = -1) {
   const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
@@ -737,7 +744,7 @@ static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *lau
     if (occ < 1) { set_error("tc_hybrid_kernel<%d,%d> does not fit on an SM (smem %zu)", GT, MAXB1, smem); return GM_ECUDA; }
     const int grid = int(std::min<int64_t>(il.n, int64_t(occ) * g->num_sms));
     kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(g->hy_vinfo, g->hy_data, g->hy_units, g->hy_units + 1, g->hy_hb, g->rk_prow, g->hy_prec,
-                                                   il.d_items, il.n, g->d_ticket + cls, g->d_counts, options().tc_ld);
+                                                   il.d_items, il.n, g->d_ticket + (ticket >= 0 ? ticket : cls), g->d_counts, options().tc_ld, share);
     (*launches)++;
     return GM_OK;
   }
@@ -781,7 +788,16 @@ static int run_tc_hash(gm_graph *g, int *launches) {
   GM_TRY(fork_streams(g));
   GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 1, g->stream, launches)));
   // class 2 (41 KB tables): 512-thread groups keep the SM at full occupancy (5 x 256 threads otherwise)
-  if (options().tc_gt2 == 512) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[0], launches)));
+  // hybrid rows: a root's table holds its few non-hub keys only, so the roots of 513..2048 neighbours run in
+  // 256-thread groups with the 10 KB table like the class below (fewer warps per barrier, twice the roots in
+  // flight: scale 22 4.76 -> 4.50 ms, scale 24 28.5 -> 25.5 ms); the rare root with more than 512 non-hub
+  // neighbours is left to a second launch over the same items with the 41 KB table
+  const bool hybrid = MODE == 2 && options().tc_flat == 5 && !options().tc_pipe && g->hy_valid;
+  if (hybrid && options().tc_c2split) {
+    GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 2, g->side[0], launches, 1)));
+    if (g->hy_big_tables) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[1], launches, 2, 6)));
+  }
+  else if (options().tc_gt2 == 512) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[0], launches)));
   else GM_TRY((launch_hash_class<256, 13, 64, MODE>(g, 2, g->side[0], launches)));
   GM_TRY((launch_hash_class<1024, 15, 64, MODE>(g, 3, g->side[1], launches)));
   GM_TRY((launch_hash_class<32, 7, 16, MODE>(g, 0, g->side[2], launches)));
