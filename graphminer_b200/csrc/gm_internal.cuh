@@ -60,6 +60,7 @@ struct Options {
   int sup_flat = 1;                // support pass: flat window streaming (0: a loop per partner record)
   int clique_flat = 1;             // k-clique matrix build: flat window streaming of the members' rows (0: a loop per row)
   int clique_split = 1;            // 4-clique: the 33..512 class as two launches (<= 256: small shared-memory footprint)
+  int tc_c1split = -1;             // hybrid TC: roots of 33..512 neighbours in 128-thread groups with a 5 KB key table (-1: when the hybrid rows are below 512 MB)
   int tc_c2split = 1;              // hybrid TC: roots of 513..2048 neighbours in 256-thread groups with the small key table (+ a second launch for the rest)
   int tc_pipe = 0;                 // TC stream loop: prefetch the next block of elements across partner boundaries (0: per-partner loop)
   int tc_gt2 = 512;                  // threads per group of the second TC size class (256 | 512)
@@ -130,7 +131,7 @@ struct gm_graph {
   uint4 *hy_vinfo = nullptr; uint32_t *hy_data = nullptr; uint2 *hy_prec = nullptr;
   bool want_hybrid = false;            // set by prepare_tc before the ranked graph is built: ensure_hybrid will write the partner records
   bool rk_prec_full = false;           // rk_prec holds the records of every root (else: of the roots with <= 32 neighbours only)
-  uint32_t hy_units = 0; gm::vidType hy_hb = 0; bool hy_big_tables = false;   // some root's key table needs more than 11 bits
+  uint32_t hy_units = 0; gm::vidType hy_hb = 0; bool hy_mid_tables = false, hy_big_tables = false;   // some root's key table needs more than 10 / 11 bits
   int64_t rk_acol_len = 0;             // elements of rk_acol (aligned, padded)
   // tc.algo=merge: every kept partner record as one (row suffix, root row) pair of gm_intersect_batch
   int64_t *mg_aoff = nullptr, *mg_boff = nullptr; int32_t *mg_alen = nullptr, *mg_blen = nullptr;

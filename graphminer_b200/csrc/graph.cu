@@ -798,6 +798,9 @@ int gm_set_option(const char *key, const char *value) {
   } else if (k == "clique.split") {
     if (v != "0" && v != "1") { set_error("clique.split: 0 or 1"); return GM_EINVAL; }
     options().clique_split = atoi(value);
+  } else if (k == "tc.c1split") {
+    if (v != "0" && v != "1" && v != "-1") { set_error("tc.c1split: -1 (auto), 0 or 1"); return GM_EINVAL; }
+    options().tc_c1split = atoi(value);
   } else if (k == "tc.c2split") {
     if (v != "0" && v != "1") { set_error("tc.c2split: 0 or 1"); return GM_EINVAL; }
     options().tc_c2split = atoi(value);

@@ -281,7 +281,7 @@ struct HyCtx {
   uint4 *hv; uint32_t *data;
   uint2 *prec_plain;                                 // rk_prec (records of small roots only), may be null
   const uint32_t *small_bits;                        // bit v: ranked row v has at most 32 elements (the plain-kernel class)
-  unsigned *big_tables;                              // set when a non-hub root has more than 512 keys
+  unsigned *big_tables;                              // bit 0 / 1: a non-hub root has more than 256 / 512 keys
 };
 
 __global__ void k_small_bits(vidType nv, const uint2 *__restrict__ vinfo, uint32_t *__restrict__ bits) {
@@ -332,7 +332,7 @@ k_hy_fill(HyCtx c, RowCtx rc, unsigned long long *cursor, uint2 *prec) {     // 
   const uint32_t base_k = unit_k << 2, base_e = unit_e << 2, base_plain = vi.x << 2;
   if (valid && sub == 0) {
     c.hv[a] = make_uint4(unit_k, nk, unit_e, ne);
-    if (nk > 512u && a < c.hb) atomicOr(c.big_tables, 1u);        // some root needs a key table beyond the 256-thread configuration (tc.cu)
+    if (nk > 256u && a < c.hb) atomicOr(c.big_tables, nk > 512u ? 3u : 1u);   // key tables beyond the 128- / 256-thread configurations (tc.cu)
   }
   bool keep_src = false;
   if (valid) { const vidType v = rc.orig_of[a]; keep_src = v >= rc.src_begin && v < rc.src_end; }
@@ -564,7 +564,7 @@ int ensure_hybrid(gm_graph *g) {
   unsigned h_big = 0;
   GM_CUDA(cudaMemcpyAsync(&h_big, big_tables, sizeof(unsigned), cudaMemcpyDeviceToHost, g->stream));
   GM_CUDA(cudaStreamSynchronize(g->stream));
-  g->hy_big_tables = h_big != 0;
+  g->hy_mid_tables = (h_big & 1u) != 0; g->hy_big_tables = (h_big & 2u) != 0;
   GM_CUDA(dfree(g, cursor)); GM_CUDA(dfree(g, small_bits));
   g->hy_units = total_units; g->hy_hb = c.hb;
   g->hy_valid = true;

@@ -521,7 +521,6 @@ tc_rank_kernel(const uint2 *__restrict__ vinfo, const uint32_t *__restrict__ aco
 // partner record two flat passes: the key suffix against the table (only when the root has non-hub keys and is
 // no hub itself), the bitmap entries against the bitmap.
 constexpr int kBitmapWords = kHubRanks / 32;
-constexpr int kSmallTableBits = 11;                  // key tables of up to 512 keys: the 256-thread configuration
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   uint16_t v;
@@ -540,16 +539,15 @@ __device__ __forceinline__ uint32_t probe_window_hub(uint32_t sb, uint4 e) {
 }
 
 template <int GT, int MAXB1, int CAP, int OCC>
-__global__ void __launch_bounds__(GroupCfg<GT>::kCtaThreads, OCC ? GroupCfg<GT>::kMinCtasRelaxed : GroupCfg<GT>::kMinCtas)
+__global__ void __launch_bounds__(GT, GT >= 1024 ? 1 : (OCC ? 1536 : 2048) / GT)      // one group = one CTA of GT threads
 tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data, uint32_t pad_keys, uint32_t pad_zero, vidType hb,
                  const eidType *__restrict__ prow, const uint2 *__restrict__ prec,
-                 const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int ldmode, int share) {
-  static_assert(GT >= 256, "one group per CTA");
-  using Cfg = GroupCfg<GT>;
+                 const WorkItem *__restrict__ items, int64_t nitems, int *ticket, AccType *total, int ldmode, int share, int small_bits) {
+  static_assert(GT >= 128 && GT % 32 == 0, "one group per CTA");
   extern __shared__ uint32_t smem[];
   __shared__ int64_t s_next;
   constexpr int kWords = RowTable::words_for_bits(MAXB1, CAP);
-  constexpr int W = Cfg::kWarpsPerGroup;
+  constexpr int W = GT / 32;
   const int lane = threadIdx.x & 31, tid = threadIdx.x, gwarp = tid >> 5;
   uint32_t *bitmap = smem + kWords;
   const uint32_t s1 = uint32_t(__cvta_generic_to_shared(smem));
@@ -571,11 +569,11 @@ tc_hybrid_kernel(const uint4 *__restrict__ hv, const uint32_t *__restrict__ data
     if (first >= nitems) break;
     const WorkItem it = items[first];
     h = hv[it.root];
-    // two launches may share one item list (class 2, launch_hash_class): share 1 takes the roots whose key table
-    // fits THIS configuration and leaves the others to the launch with the large table (share 2)
+    // two launches may share one item list (run_tc_hash): share 1 takes the roots whose key table fits THIS
+    // configuration, share 2 those whose table needs more than `small_bits` bits (what the share-1 launch left)
     if (share) {
-      const bool small = !(h.y > 0 && it.root < hb) || RowTable::bits_for(int(h.y)) <= kSmallTableBits;
-      if (small != (share == 1)) { h = make_uint4(0, 0, 0, 0); continue; }
+      const int need = (h.y > 0 && it.root < hb) ? RowTable::bits_for(int(h.y)) : 0;
+      if (share == 1 ? need > MAXB1 : need <= small_bits) { h = make_uint4(0, 0, 0, 0); continue; }
     }
     const uint32_t *keys = data + (size_t(h.x) << 2), *ents = data + (size_t(h.z) << 2);
     const int nk = int(h.y);
@@ -730,24 +728,30 @@ static int run_tc_merge(gm_graph *g, int *launches) {
   return GM_OK;
 }
 
+// one launch of the hybrid kernel over the items of size class `cls`: groups of GT threads (= CTAs), key tables of
+// up to 2^MAXB1 slots; share / small_bits: see the kernel
+template <int GT, int MAXB1, int CAP>
+static int launch_hybrid(gm_graph *g, int cls, cudaStream_t stream, int *launches, int share = 0, int small_bits = 0, int ticket = -1) {
+  const ItemList &il = g->items[3][cls];
+  if (il.n == 0) return GM_OK;
+  auto kern = options().tc_occ ? tc_hybrid_kernel<GT, MAXB1, CAP, 1> : tc_hybrid_kernel<GT, MAXB1, CAP, 0>;
+  const size_t smem = sizeof(uint32_t) * (size_t(RowTable::words_for_bits(MAXB1, CAP)) + kBitmapWords);
+  GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int occ = 0;
+  GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GT, smem));
+  if (occ < 1) { set_error("tc_hybrid_kernel<%d,%d> does not fit on an SM (smem %zu)", GT, MAXB1, smem); return GM_ECUDA; }
+  const int grid = int(std::min<int64_t>(il.n, int64_t(occ) * g->num_sms));
+  kern<<<grid, GT, smem, stream>>>(g->hy_vinfo, g->hy_data, g->hy_units, g->hy_units + 1, g->hy_hb, g->rk_prow, g->hy_prec,
+                                   il.d_items, il.n, g->d_ticket + (ticket >= 0 ? ticket : cls), g->d_counts, options().tc_ld, share, small_bits);
+  (*launches)++;
+  return GM_OK;
+}
+
 template <int GT, int MAXB1, int CAP, int MODE>
-static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *launches, int share = 0, int ticket = -1) {
+static int launch_hash_class(gm_graph *g, int cls, cudaStream_t stream, int *launches) {
   const ItemList &il = g->items[MODE == 2 ? 3 : MODE][cls];
   if (il.n == 0) return GM_OK;
   using Cfg = GroupCfg<GT>;
-  if (MODE == 2 && GT >= 256 && options().tc_flat == 5 && !options().tc_pipe && g->hy_valid) {
-    auto kern = options().tc_occ ? tc_hybrid_kernel<(GT >= 256 ? GT : 256), MAXB1, CAP, 1> : tc_hybrid_kernel<(GT >= 256 ? GT : 256), MAXB1, CAP, 0>;
-    const size_t smem = sizeof(uint32_t) * (size_t(RowTable::words_for_bits(MAXB1, CAP)) + kBitmapWords);
-    GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int occ = 0;
-    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::kCtaThreads, smem));
-    if (occ < 1) { set_error("tc_hybrid_kernel<%d,%d> does not fit on an SM (smem %zu)", GT, MAXB1, smem); return GM_ECUDA; }
-    const int grid = int(std::min<int64_t>(il.n, int64_t(occ) * g->num_sms));
-    kern<<<grid, Cfg::kCtaThreads, smem, stream>>>(g->hy_vinfo, g->hy_data, g->hy_units, g->hy_units + 1, g->hy_hb, g->rk_prow, g->hy_prec,
-                                                   il.d_items, il.n, g->d_ticket + (ticket >= 0 ? ticket : cls), g->d_counts, options().tc_ld, share);
-    (*launches)++;
-    return GM_OK;
-  }
   if (MODE == 2 && options().tc_flat == 4 && !options().tc_pipe && g->rk_acol4) {
     auto kern = tc_rank_kernel<GT, MAXB1, CAP>;
     const size_t smem = sizeof(uint32_t) * size_t(RowTable::words_for_bits(MAXB1, CAP)) * Cfg::kGroupsPerCta;
@@ -786,20 +790,37 @@ template <int MODE>
 static int run_tc_hash(gm_graph *g, int *launches) {
   // the four size classes are independent: run them concurrently so their tails overlap
   GM_TRY(fork_streams(g));
-  GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 1, g->stream, launches)));
-  // class 2 (41 KB tables): 512-thread groups keep the SM at full occupancy (5 x 256 threads otherwise)
-  // hybrid rows: a root's table holds its few non-hub keys only, so the roots of 513..2048 neighbours run in
-  // 256-thread groups with the 10 KB table like the class below (fewer warps per barrier, twice the roots in
-  // flight: scale 22 4.76 -> 4.50 ms, scale 24 28.5 -> 25.5 ms); the rare root with more than 512 non-hub
-  // neighbours is left to a second launch over the same items with the 41 KB table
   const bool hybrid = MODE == 2 && options().tc_flat == 5 && !options().tc_pipe && g->hy_valid;
-  if (hybrid && options().tc_c2split) {
-    GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 2, g->side[0], launches, 1)));
-    if (g->hy_big_tables) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[1], launches, 2, 6)));
+  if (hybrid) {
+    // Hybrid rows: a root's table holds its few non-hub keys only, so the group width is chosen for the barriers
+    // and the number of roots in flight, not for the table: roots of 513..2048 neighbours run in 256-thread groups
+    // with the 10 KB table (scale 22 4.80 -> 4.63 ms, scale 24 28.5 -> 26.1 ms against the 512-thread class), and
+    // with tc.c1split the roots of 33..512 in 128-thread groups with a 5 KB table.  Roots whose key table needs
+    // more are left to a second launch over the same items (only when k_hy_fill saw such a root).
+    // 128-thread groups double the roots in flight once more: a gain while the hybrid rows mostly live in the
+    // 126 MB L2 (R-MAT scale 20 0.97 -> 0.79 ms, scale 22 4.63 -> 4.25 ms), a 3 % loss when every stream comes from
+    // HBM (scale 24, 1.3 GB of rows) -- auto: on below 512 MB of hybrid rows
+    const bool c1split = options().tc_c1split < 0 ? (size_t(g->hy_units) << 4) < (size_t(512) << 20) : options().tc_c1split != 0;
+    if (c1split) {
+      GM_TRY((launch_hybrid<128, 10, 64>(g, 1, g->stream, launches, 1)));
+      if (g->hy_mid_tables) GM_TRY((launch_hybrid<256, 11, 64>(g, 1, g->side[2], launches, 2, 10, 5)));
+    } else {
+      GM_TRY((launch_hybrid<256, 11, 64>(g, 1, g->stream, launches)));
+    }
+    if (options().tc_c2split) {
+      GM_TRY((launch_hybrid<256, 11, 64>(g, 2, g->side[0], launches, 1)));
+      if (g->hy_big_tables) GM_TRY((launch_hybrid<512, 13, 64>(g, 2, g->side[1], launches, 2, 11, 6)));
+    } else {
+      GM_TRY((launch_hybrid<512, 13, 64>(g, 2, g->side[0], launches)));
+    }
+    GM_TRY((launch_hybrid<1024, 15, 64>(g, 3, g->side[1], launches)));
+  } else {
+    GM_TRY((launch_hash_class<256, 11, 64, MODE>(g, 1, g->stream, launches)));
+    // class 2 (41 KB tables): 512-thread groups keep the SM at full occupancy (5 x 256 threads otherwise)
+    if (options().tc_gt2 == 512) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[0], launches)));
+    else GM_TRY((launch_hash_class<256, 13, 64, MODE>(g, 2, g->side[0], launches)));
+    GM_TRY((launch_hash_class<1024, 15, 64, MODE>(g, 3, g->side[1], launches)));
   }
-  else if (options().tc_gt2 == 512) GM_TRY((launch_hash_class<512, 13, 64, MODE>(g, 2, g->side[0], launches)));
-  else GM_TRY((launch_hash_class<256, 13, 64, MODE>(g, 2, g->side[0], launches)));
-  GM_TRY((launch_hash_class<1024, 15, 64, MODE>(g, 3, g->side[1], launches)));
   GM_TRY((launch_hash_class<32, 7, 16, MODE>(g, 0, g->side[2], launches)));
   GM_TRY(join_streams(g));
   return GM_OK;

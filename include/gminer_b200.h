@@ -69,7 +69,8 @@ int gm_device_init(int device);
  *       prefetch in the per-record loop; measured slower, off by default), "tc.ld" = 0|1|2 (load flavour of the
  *       streamed entries: ld.global.nc | + L1::no_allocate | ld.global.cg, the default), "tc.occ" = 0|1 (hybrid
  *       kernel at 32 | 40 registers), "tc.c2split" = 1|0 (hybrid kernel: roots of 513..2048 neighbours in 256-thread
- *       groups with the small key table | the 512-thread class), "sup.flat" = 1|0 (support pass: flat windows | a loop per record),
+ *       groups with the small key table | the 512-thread class), "tc.c1split" = -1|0|1 (roots of 33..512 neighbours
+ *       in 128-thread groups; auto: while the hybrid rows are below 512 MB), "sup.flat" = 1|0 (support pass: flat windows | a loop per record),
  *       "clique.flat" = 1|0 (bit-matrix build likewise), "clique.split" = 1|0 (4-clique: roots of 33..256 and 257..512
  *       neighbours in two launches with their own shared-memory footprint),
  *       "mem.arena" = 1|0 (one device arena per handle for graphs beyond ~256 MB), "tc.gt2" = 256|512, "sup.gt2" =

@@ -37,6 +37,8 @@ def _reset_options():
     capi.set_option("tc.pipe", 0)
     capi.set_option("tc.flat", 5)
     capi.set_option("tc.hub", 65536)
+    capi.set_option("tc.c1split", -1)
+    capi.set_option("tc.c2split", 1)
 
 
 def _graph(name):
@@ -751,6 +753,10 @@ def test_tc_hybrid_rows_split_at_every_hub_range(hub):
             for flat in (1, 4, 0, 5):
                 capi.set_option("tc.flat", flat)
                 assert g.tc() == GOLD[name]["tc"], (name, hub, flat)
+            for c1, c2 in ((0, 0), (1, 1), (0, 1), (1, 0)):          # group widths of the hybrid kernel's size classes
+                capi.set_option("tc.c1split", c1); capi.set_option("tc.c2split", c2)
+                assert g.tc() == GOLD[name]["tc"], (name, hub, c1, c2)
+            capi.set_option("tc.c1split", -1); capi.set_option("tc.c2split", 1)
             capi.set_option("tc.algo", "merge")
             assert g.tc() == GOLD[name]["tc"], (name, hub, "merge")
     capi.set_option("tc.flat", 5)
@@ -758,7 +764,9 @@ def test_tc_hybrid_rows_split_at_every_hub_range(hub):
     n = 700                                                  # K_700: rows of every length, all blocks dense
     rp, ci, md = _complete_dag(n)
     with capi.DeviceGraph(rp, ci, md) as g:
-        assert g.tc() == n * (n - 1) * (n - 2) // 6
+        for c1, c2 in ((0, 0), (1, 1)):                      # with a small hub range: key tables beyond both small configurations
+            capi.set_option("tc.c1split", c1); capi.set_option("tc.c2split", c2)
+            assert g.tc() == n * (n - 1) * (n - 2) // 6, (hub, c1, c2)
 
 
 def test_tc_hybrid_rows_beyond_the_default_hub_range():
