@@ -133,7 +133,10 @@ int gm_host_check_sorted(int32_t nv, const int64_t *rowptr, const int32_t *colid
 
 /* ---- device graph ------------------------------------------------------------------------- */
 /* GraphGPU::init, include/graph_gpu.h:69-122: copy a host CSR to `device`.  Host arrays are
- * borrowed only for the duration of the call.  max_degree <= 0 means "compute it". */
+ * borrowed only for the duration of the call.  max_degree <= 0 means "compute it".
+ * Device memory: a handle whose arrays would exceed ~256 MB takes them from one arena of
+ * 176 * nv + 40 * ne + 64 MB bytes (capped at 24 GB; released by gm_graph_free), allocated on first use --
+ * what makes repeated gm_*_host calls run at a steady time ("mem.arena" = 0 turns it off). */
 int gm_graph_upload(const int64_t *rowptr, const int32_t *colidx, int32_t nv, int64_t ne,
                     int32_t max_degree, int device, gm_graph_t **out);
 /* Adopt a CSR that is already resident on `device` (no copy; caller keeps ownership of the two
